@@ -1,0 +1,180 @@
+"""ctypes loader for the CPU checkers under oracle/ — TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py (cpu_baseline / --impl reference legs) may import this module.
+The product package (nlsolver_b200/) never does: it has no CPU path at all.
+
+Two libraries share one call surface (oracle/oracle_abi.h):
+  * ``oracle()``    -> oracle/_build/liboracle.so : the restatement (popsolve_oracle.cpp), prefix ``oracle_``
+  * ``reference()`` -> oracle/_ref/libnls_ref.so  : the UNMODIFIED reference templates behind ref_harness.cpp,
+                       prefix ``ref_``; ``None`` when it was never built (reference tree absent and no prebuilt .so)
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+F32, F64 = 0, 1
+SPHERE, ROSENBROCK, RASTRIGIN, ACKLEY, ROSENBROCK_EX = range(5)
+DE_BEST, DE_RANDOM = 0, 1
+PSO_VANILLA, PSO_ACCELERATED = 0, 1
+RNG_TAPE, RNG_XORSHIFT = 0, 1
+
+u64, i32, f64 = C.c_uint64, C.c_int32, C.c_double
+
+
+class DECfg(C.Structure):
+    _fields_ = [("dtype", i32), ("objective", i32), ("strategy", i32), ("minimize", i32),
+                ("pop_size", u64), ("dim", u64),
+                ("crossover_prob", f64), ("differential_weight", f64), ("eps", f64),
+                ("max_iter", u64), ("best_val_no_change", u64),
+                ("rng_mode", i32), ("_pad", i32),
+                ("seed", u64), ("agent_offset", u64), ("xs_state", u64 * 2)]
+
+
+class PSOCfg(C.Structure):
+    _fields_ = [("dtype", i32), ("objective", i32), ("pso_type", i32), ("minimize", i32),
+                ("n_particles", u64), ("dim", u64),
+                ("inertia", f64), ("cognitive_coef", f64), ("social_coef", f64), ("eps", f64),
+                ("max_iter", u64), ("best_val_no_change", u64),
+                ("constrained", i32), ("social_index_j", i32), ("rng_mode", i32), ("_pad", i32),
+                ("seed", u64), ("particle_offset", u64), ("n_particles_global", u64), ("xs_state", u64 * 2)]
+
+
+class Status(C.Structure):
+    _fields_ = [("f_value", f64), ("iterations", u64), ("function_calls", u64), ("best_index", u64),
+                ("val_no_change", u64), ("draws_consumed", u64), ("best_valid", i32), ("stop_reason", i32),
+                ("std_err", f64)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+class DEOut(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in
+                ("x_best", "rows", "scores", "trial_scores", "donors", "dim_idx", "rejects", "accepted", "masks")]
+
+
+class PSOOut(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("x_best", "positions", "velocities", "pbest_values", "last_values")]
+
+
+def np_dtype(dtype):
+    return np.float64 if dtype == F64 else np.float32
+
+
+def build(ref=True):
+    """Compile the checkers (g++; seconds). The reference harness is built only where /root/reference exists."""
+    subprocess.run(["make", "-s", "-C", HERE, "oracle"], check=True)
+    if ref:
+        subprocess.run(["make", "-s", "-C", HERE, "ref"], check=True)
+
+
+_cache = {}
+
+
+def _load(path, prefix, with_extras):
+    lib = C.CDLL(path)
+    de, pso = getattr(lib, prefix + "de_run"), getattr(lib, prefix + "pso_run")
+    de.argtypes = [C.POINTER(DECfg), C.c_void_p, C.POINTER(DEOut), C.POINTER(Status)]
+    pso.argtypes = [C.POINTER(PSOCfg), C.c_void_p, C.c_void_p, C.POINTER(PSOOut), C.POINTER(Status)]
+    de.restype = pso.restype = C.c_int
+    lib.oracle_objective.argtypes = [C.c_int, C.c_int, C.c_void_p, u64]
+    lib.oracle_objective.restype = f64
+    lib.oracle_tape_key.argtypes = [u64, u64, u64]
+    lib.oracle_tape_key.restype = u64
+    lib.oracle_tape_draw.argtypes = [u64, u64]
+    lib.oracle_tape_draw.restype = u64
+    lib.oracle_unit_f64.argtypes = [u64]
+    lib.oracle_unit_f64.restype = f64
+    lib.oracle_unit_f32.argtypes = [u64]
+    lib.oracle_unit_f32.restype = C.c_float
+    lib.oracle_xorshift_default.argtypes = [C.POINTER(u64), C.POINTER(u64), u64]
+    lib.oracle_std_err_f64.argtypes = [C.c_void_p, u64]
+    lib.oracle_std_err_f64.restype = f64
+    if with_extras:
+        lib.ref_de_time.argtypes = [C.POINTER(DECfg), C.c_void_p, C.POINTER(f64), C.POINTER(Status)]
+        lib.ref_pso_time.argtypes = [C.POINTER(PSOCfg), C.c_void_p, C.POINTER(f64), C.POINTER(Status)]
+        lib.ref_objective_2d.argtypes = [C.c_int, f64, f64]
+        lib.ref_objective_2d.restype = f64
+        lib.ref_xorshift_draws.argtypes = [C.c_int, u64, C.c_void_p]
+        lib.ref_last_inconsistencies.restype = u64
+        lib.ref_std_err_f64.argtypes = [C.c_void_p, u64]
+        lib.ref_std_err_f64.restype = f64
+    return lib
+
+
+def oracle():
+    if "oracle" not in _cache:
+        path = os.path.join(HERE, "_build", "liboracle.so")
+        if not os.path.exists(path):
+            build(ref=False)
+        _cache["oracle"] = _load(path, "oracle_", False)
+    return _cache["oracle"]
+
+
+def reference():
+    if "ref" not in _cache:
+        path = os.path.join(HERE, "_ref", "libnls_ref.so")
+        if not os.path.exists(path) and os.path.exists("/root/reference/nlsolver.h"):
+            build(ref=True)
+        _cache["ref"] = _load(path, "ref_", True) if os.path.exists(path) else None
+    return _cache["ref"]
+
+
+def de_cfg(dtype=F64, objective=SPHERE, strategy=DE_RANDOM, minimize=True, pop_size=50, dim=2, crossover_prob=0.9,
+           differential_weight=0.8, eps=10e-4, max_iter=1000, best_val_no_change=50, rng_mode=RNG_TAPE, seed=0,
+           agent_offset=0, xs_state=(0, 0)):
+    return DECfg(dtype, objective, strategy, int(minimize), pop_size, dim, crossover_prob, differential_weight, eps,
+                 max_iter, best_val_no_change, rng_mode, 0, seed, agent_offset, (u64 * 2)(*xs_state))
+
+
+def pso_cfg(dtype=F64, objective=SPHERE, pso_type=PSO_VANILLA, minimize=True, n_particles=10, dim=2, inertia=0.8,
+            cognitive_coef=1.8, social_coef=1.8, eps=10e-4, max_iter=5000, best_val_no_change=50, constrained=False,
+            social_index_j=False, rng_mode=RNG_TAPE, seed=0, particle_offset=0, n_particles_global=0, xs_state=(0, 0)):
+    return PSOCfg(dtype, objective, pso_type, int(minimize), n_particles, dim, inertia, cognitive_coef, social_coef,
+                  eps, max_iter, best_val_no_change, int(constrained), int(social_index_j), rng_mode, 0, seed,
+                  particle_offset, n_particles_global or n_particles, (u64 * 2)(*xs_state))
+
+
+def de_run(lib, cfg, x0, masks=False, prefix=None):
+    """Run DE to its stop rule; returns (status dict, arrays dict)."""
+    prefix = prefix or ("ref_" if hasattr(lib, "ref_de_run") else "oracle_")
+    dt = np_dtype(cfg.dtype)
+    P, d = cfg.pop_size, cfg.dim
+    x0 = np.ascontiguousarray(x0, dtype=dt)
+    a = {"x_best": np.zeros(d, dt), "rows": np.zeros((P, d), dt), "scores": np.zeros(P, dt),
+         "trial_scores": np.zeros(P, dt), "donors": np.zeros((P, 3), np.uint32), "dim_idx": np.zeros(P, np.uint32),
+         "rejects": np.zeros(P, np.uint32), "accepted": np.zeros(P, np.uint8)}
+    if masks:
+        a["masks"] = np.zeros((P, d), np.uint8)
+    out = DEOut(**{k: v.ctypes.data for k, v in a.items()})
+    st = Status()
+    rc = getattr(lib, prefix + "de_run")(C.byref(cfg), x0.ctypes.data, C.byref(out), C.byref(st))
+    if rc != 0:
+        raise RuntimeError(f"{prefix}de_run failed: {rc}")
+    return st.as_dict(), a
+
+
+def pso_run(lib, cfg, lower, upper, prefix=None):
+    prefix = prefix or ("ref_" if hasattr(lib, "ref_pso_run") else "oracle_")
+    dt = np_dtype(cfg.dtype)
+    P, d = cfg.n_particles, cfg.dim
+    lower = np.ascontiguousarray(lower, dtype=dt)
+    upper = np.ascontiguousarray(upper, dtype=dt)
+    a = {"x_best": np.zeros(d, dt), "positions": np.zeros((P, d), dt), "velocities": np.zeros((P, d), dt),
+         "pbest_values": np.zeros(P, dt), "last_values": np.zeros(P, dt)}
+    out = PSOOut(**{k: v.ctypes.data for k, v in a.items()})
+    st = Status()
+    rc = getattr(lib, prefix + "pso_run")(C.byref(cfg), lower.ctypes.data, upper.ctypes.data, C.byref(out),
+                                          C.byref(st))
+    if rc != 0:
+        raise RuntimeError(f"{prefix}pso_run failed: {rc}")
+    return st.as_dict(), a
+
+
+def objective(dtype, obj_id, x):
+    x = np.ascontiguousarray(x, dtype=np_dtype(dtype))
+    return oracle().oracle_objective(dtype, obj_id, x.ctypes.data, x.size)

@@ -1,0 +1,84 @@
+/*
+ * oracle_abi.h — TEST INFRASTRUCTURE ONLY (never linked into the product library).
+ *
+ * Plain-C call surface shared by the two CPU checkers under oracle/:
+ *   - popsolve_oracle.cpp : a from-scratch restatement ("port") of the reference's DE / PSO population loop
+ *                           (nlsolver.h:2302-2477 DE, 2479-2742 PSO, 2037-2052 std_err, 1343-1381 xorshift);
+ *   - ref_harness.cpp     : drives the UNMODIFIED reference templates (compiled from /root/reference where
+ *                           they lie, output only into oracle/_ref/) through a tape RNG + objective hook.
+ * Both export the same entry points with the prefix `oracle_` / `ref_` so the tests can diff them.
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load these.
+ */
+#ifndef ORACLE_ABI_H_
+#define ORACLE_ABI_H_
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum { ORC_F32 = 0, ORC_F64 = 1 };
+/* objective ids: N-D forms that reduce to test_functions.h:51-92 at d = 2; id 4 is example.cpp:41-48 */
+enum { ORC_SPHERE = 0, ORC_ROSENBROCK = 1, ORC_RASTRIGIN = 2, ORC_ACKLEY = 3, ORC_ROSENBROCK_EX = 4 };
+/* same order as the reference enums (nlsolver.h:2377, 2496) */
+enum { ORC_DE_BEST = 0, ORC_DE_RANDOM = 1 };
+enum { ORC_PSO_VANILLA = 0, ORC_PSO_ACCELERATED = 1 };
+/* draw source: the counter tape (DESIGN.md "RNG tape") or the reference's sequential xorshift128+ */
+enum { ORC_RNG_TAPE = 0, ORC_RNG_XORSHIFT = 1 };
+
+typedef struct {
+  int32_t dtype, objective, strategy, minimize;
+  uint64_t pop_size, dim;
+  double crossover_prob, differential_weight, eps;
+  uint64_t max_iter, best_val_no_change;
+  int32_t rng_mode, _pad;
+  uint64_t seed;          /* tape seed (ORC_RNG_TAPE) */
+  uint64_t agent_offset;  /* global id of local agent 0 in the tape key (islands) */
+  uint64_t xs_state[2];   /* xorshift128+ state (ORC_RNG_XORSHIFT); {0,0} = reference default seeding */
+} orc_de_cfg;
+
+typedef struct {
+  int32_t dtype, objective, pso_type, minimize;
+  uint64_t n_particles, dim;
+  double inertia, cognitive_coef, social_coef, eps;
+  uint64_t max_iter, best_val_no_change;
+  int32_t constrained;     /* 1 = bounded overloads (threshold_positions), 0 = unbounded */
+  int32_t social_index_j;  /* vanilla only: 0 = reference quirk swarm_best_position[i] (needs P <= d), 1 = [j] */
+  int32_t rng_mode, _pad;
+  uint64_t seed;
+  uint64_t particle_offset, n_particles_global; /* sharded swarm: slice [offset, offset+n_particles) of a global swarm */
+  uint64_t xs_state[2];
+} orc_pso_cfg;
+
+typedef struct {
+  double f_value;
+  uint64_t iterations, function_calls;
+  uint64_t best_index;     /* DE: best_id ; PSO: index of the particle whose row is swarm_best_position (if valid) */
+  uint64_t val_no_change;
+  uint64_t draws_consumed; /* number of generator() calls made */
+  int32_t best_valid;      /* PSO: 0 if swarm_best_position was never assigned */
+  int32_t stop_reason;     /* 1 max_iter, 2 val_no_change, 3 std_err < eps */
+  double std_err;          /* last std_err evaluated */
+} orc_status;
+
+/*
+ * Buffers are caller-allocated, element type = cfg.dtype, any may be NULL.
+ *  x0[d] in; x_best[d] out; rows[P*d], scores[P] = final population;
+ *  decisions of the LAST executed generation: donors[P*3] (ids[1..3]), dim_idx[P], rejects[P] (rejected index
+ *  proposals), accepted[P] (0/1), masks[P*d] (1 = mutated coordinate), trial_scores[P].
+ */
+typedef struct {
+  void *x_best, *rows, *scores, *trial_scores;
+  uint32_t *donors, *dim_idx, *rejects;
+  uint8_t *accepted, *masks;
+} orc_de_out;
+
+typedef struct {
+  void *x_best, *positions, *velocities, *pbest_values, *last_values;
+} orc_pso_out;
+
+#ifdef __cplusplus
+}
+#endif
+#endif  /* ORACLE_ABI_H_ */

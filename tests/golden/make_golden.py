@@ -1,0 +1,60 @@
+"""Regenerates tests/golden/*.npz from the UNMODIFIED reference (oracle/_ref/libnls_ref.so, built from /root/reference
+by oracle/Makefile).  Run in the build container only:  python tests/golden/make_golden.py
+Each fixture stores the configuration, x0 / bounds and everything the reference produced on the draw tape, so the
+oracle and the CUDA path can be checked against the reference where the reference itself cannot travel."""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+from oracle import binding as B  # noqa: E402
+
+DE_GOLDEN = {
+    # name: (dtype, objective, strategy, minimize, P, d, G, scale, seed)
+    "de_rand_sphere_f64": (B.F64, B.SPHERE, B.DE_RANDOM, True, 96, 10, 8, 10.24, 11),
+    "de_best_rosenbrock_f64": (B.F64, B.ROSENBROCK, B.DE_BEST, True, 64, 8, 25, 4.096, 12),
+    "de_rand_rastrigin_f64": (B.F64, B.RASTRIGIN, B.DE_RANDOM, True, 130, 67, 6, 10.24, 13),
+    "de_rand_ackley_max_f64": (B.F64, B.ACKLEY, B.DE_RANDOM, False, 48, 5, 10, 65.536, 14),
+    "de_rand_sphere_f32": (B.F32, B.SPHERE, B.DE_RANDOM, True, 80, 13, 8, 10.24, 15),
+}
+PSO_GOLDEN = {
+    # name: (dtype, objective, type, minimize, constrained, P, d, G, bound, seed)
+    "pso_vanilla_sphere_f64": (B.F64, B.SPHERE, B.PSO_VANILLA, True, False, 16, 16, 20, 10.24, 21),
+    "pso_vanilla_bounded_rosenbrock_f64": (B.F64, B.ROSENBROCK, B.PSO_VANILLA, True, True, 6, 8, 30, 4.096, 22),
+    "pso_accel_ackley_f64": (B.F64, B.ACKLEY, B.PSO_ACCELERATED, True, False, 200, 32, 10, 32.768, 23),
+    "pso_accel_bounded_rastrigin_f64": (B.F64, B.RASTRIGIN, B.PSO_ACCELERATED, True, True, 40, 8, 40, 5.12, 24),
+    "pso_accel_sphere_f32": (B.F32, B.SPHERE, B.PSO_ACCELERATED, True, False, 64, 16, 10, 10.24, 25),
+}
+
+
+def main():
+    ref = B.reference()
+    assert ref is not None, "build oracle/_ref first (make -C oracle ref)"
+    for name, (dtype, obj, strat, mini, P, d, G, scale, seed) in DE_GOLDEN.items():
+        cfg = B.de_cfg(dtype=dtype, objective=obj, strategy=strat, minimize=mini, pop_size=P, dim=d, eps=0.0,
+                       max_iter=G, best_val_no_change=1 << 40, seed=seed)
+        x0 = np.full(d, scale, dtype=B.np_dtype(dtype))
+        st, a = B.de_run(ref, cfg, x0, masks=True)
+        assert ref.ref_last_inconsistencies() == 0
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), kind="de",
+                            cfg=np.array([dtype, obj, strat, int(mini), P, d, G, seed], dtype=np.int64), x0=x0,
+                            f_value=st["f_value"], iterations=st["iterations"], function_calls=st["function_calls"],
+                            draws_consumed=st["draws_consumed"], best_index=st["best_index"], **a)
+    for name, (dtype, obj, ptype, mini, con, P, d, G, bound, seed) in PSO_GOLDEN.items():
+        cfg = B.pso_cfg(dtype=dtype, objective=obj, pso_type=ptype, minimize=mini, n_particles=P, dim=d, eps=0.0,
+                        max_iter=G, best_val_no_change=1 << 40, constrained=con, seed=seed)
+        up = np.full(d, bound, dtype=B.np_dtype(dtype))
+        st, a = B.pso_run(ref, cfg, -up, up)
+        a.pop("velocities")
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), kind="pso",
+                            cfg=np.array([dtype, obj, ptype, int(mini), int(con), P, d, G, seed], dtype=np.int64),
+                            upper=up, f_value=st["f_value"], iterations=st["iterations"],
+                            function_calls=st["function_calls"], draws_consumed=st["draws_consumed"],
+                            best_valid=st["best_valid"], **a)
+    print("wrote", len(DE_GOLDEN) + len(PSO_GOLDEN), "fixtures to", HERE)
+
+
+if __name__ == "__main__":
+    main()

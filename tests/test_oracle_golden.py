@@ -1,0 +1,33 @@
+"""The oracle against the committed reference fixtures (tests/golden/*.npz) — runs where the reference cannot."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import binding as B
+from tests.golden_util import golden_files, load_de, load_pso
+
+
+def bits(a):
+    a = np.ascontiguousarray(a)
+    return a.view({8: np.uint64, 4: np.uint32, 1: np.uint8}[a.dtype.itemsize]) if a.dtype.kind == "f" else a
+
+
+@pytest.mark.parametrize("path", golden_files("de_"), ids=os.path.basename)
+def test_de_oracle_reproduces_reference_fixture(oracle_lib, path):
+    cfg, x0, z = load_de(path)
+    st, a = B.de_run(oracle_lib, cfg, x0, masks=True)
+    for k in ("f_value", "iterations", "function_calls", "draws_consumed", "best_index"):
+        assert st[k] == z[k].item(), k
+    for k in ("x_best", "rows", "scores", "trial_scores", "donors", "dim_idx", "rejects", "accepted", "masks"):
+        assert np.array_equal(bits(a[k]), bits(z[k])), k
+
+
+@pytest.mark.parametrize("path", golden_files("pso_"), ids=os.path.basename)
+def test_pso_oracle_reproduces_reference_fixture(oracle_lib, path):
+    cfg, up, z = load_pso(path)
+    st, a = B.pso_run(oracle_lib, cfg, -up, up)
+    for k in ("f_value", "iterations", "function_calls", "draws_consumed", "best_valid"):
+        assert st[k] == z[k].item(), k
+    for k in ("x_best", "positions", "pbest_values", "last_values"):
+        assert np.array_equal(bits(a[k]), bits(z[k])), k

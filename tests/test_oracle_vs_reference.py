@@ -1,0 +1,177 @@
+"""Pins the oracle (oracle/popsolve_oracle.cpp) to the reference.
+
+(1) known-answer vectors derived from the reference (BASELINE.md §2 / SURVEY.md §6, §8a R1-R2);
+(2) bit-for-bit agreement with the UNMODIFIED reference templates (oracle/_ref, built from /root/reference by
+    oracle/Makefile) on the same draw tape: final x, f_value, iterations, function calls, draws consumed, the whole
+    population, and the last generation's donors / dim / rejects / masks / accept flags.
+CPU only (-m "not gpu")."""
+import numpy as np
+import pytest
+
+from oracle import binding as B
+
+OBJS = [B.SPHERE, B.ROSENBROCK, B.RASTRIGIN, B.ACKLEY, B.ROSENBROCK_EX]
+
+
+def bits(a):
+    a = np.ascontiguousarray(a)
+    return a.view(np.uint64 if a.dtype == np.float64 else np.uint32 if a.dtype == np.float32 else a.dtype)
+
+
+def same_bits(a, b):
+    return np.array_equal(bits(a), bits(b))
+
+
+# ---------------------------------------------------------------- known answers -----------------------------------
+def test_xorshift_default_state_and_first_draws(oracle_lib):
+    st, raw = (B.u64 * 2)(), (B.u64 * 4)()
+    oracle_lib.oracle_xorshift_default(st, raw, 4)
+    assert (st[0], st[1]) == (0x7c26ca28fb68bc1b, 0x7c26ca28)          # nlsolver.h:1345-1349
+    d = [np.float64(oracle_lib.oracle_unit_f64(x)).view(np.uint64) for x in raw]
+    assert d == [0x3fda16d91834b672, 0x3fea70621141f57f, 0x3fe366ccce7f386d, 0x3fdfa0ee9f259b16]
+    f = [np.float32(oracle_lib.oracle_unit_f32(x)).view(np.uint32) for x in raw]
+    assert f == [0x3ed0b6c9, 0x3f538311, 0x3f1b3666, 0x3efd0775]
+
+
+def test_readme_de_snippet_known_answer(oracle_lib):
+    # README.md:94-110 with example.cpp:41-48's Rosenbrock: DE-random, defaults, xorshift<double>, x0 = {5, 7}
+    cfg = B.de_cfg(objective=B.ROSENBROCK_EX, rng_mode=B.RNG_XORSHIFT)
+    st, a = B.de_run(oracle_lib, cfg, [5, 7])
+    assert (st["function_calls"], st["iterations"]) == (2700, 53)
+    assert np.float64(st["f_value"]).view(np.uint64) == 0x3ee000ea0efc0071
+    assert a["x_best"].tolist() == [0.99754919858453095, 0.99523186613831982]
+
+
+def test_example_cpp_de_best_known_answer(oracle_lib):
+    # example.cpp:184-188: DE-best, xorshift<double>, x0 = {2, 7}
+    cfg = B.de_cfg(objective=B.ROSENBROCK_EX, rng_mode=B.RNG_XORSHIFT, strategy=B.DE_BEST)
+    st, a = B.de_run(oracle_lib, cfg, [2, 7])
+    assert (st["function_calls"], st["iterations"]) == (1950, 38)
+    assert "%g" % st["f_value"] == "2.07418e-05"
+    assert ["%g" % v for v in a["x_best"]] == ["1.00245", "1.00529"]
+
+
+# ---------------------------------------------------------------- primitives vs reference --------------------------
+def test_first_draws_match_reference_generator(oracle_lib, ref_lib):
+    for dtype, unit in ((B.F64, oracle_lib.oracle_unit_f64), (B.F32, oracle_lib.oracle_unit_f32)):
+        n = 1000
+        st, raw = (B.u64 * 2)(), (B.u64 * n)()
+        oracle_lib.oracle_xorshift_default(st, raw, n)
+        ref = np.zeros(n)
+        ref_lib.ref_xorshift_draws(dtype, n, ref.ctypes.data)
+        assert [float(unit(x)) for x in raw] == ref.tolist()
+
+
+def test_objectives_reduce_to_reference_2d_forms(oracle_lib, ref_lib):
+    rng = np.random.default_rng(7)
+    for obj in (B.SPHERE, B.ROSENBROCK, B.RASTRIGIN, B.ACKLEY):
+        for x in rng.uniform(-5, 5, size=(500, 2)):
+            ours = B.objective(B.F64, obj, x)
+            ref = ref_lib.ref_objective_2d(obj, x[0], x[1])
+            # Rosenbrock: the reference calls pow(v, 2.0); glibc's pow is not guaranteed correctly rounded
+            assert ours == ref or (obj == B.ROSENBROCK and abs(ours - ref) <= 2e-16 * abs(ref)), (obj, x)
+
+
+def test_std_err_matches_reference(oracle_lib, ref_lib):
+    x = np.random.default_rng(3).normal(size=1001)
+    assert oracle_lib.oracle_std_err_f64(x.ctypes.data, x.size) == ref_lib.ref_std_err_f64(x.ctypes.data, x.size)
+
+
+# ---------------------------------------------------------------- DE on the tape -----------------------------------
+DE_CASES = [
+    # dtype, objective, strategy, minimize, P, d, G, x0 scale
+    (B.F64, B.SPHERE, B.DE_RANDOM, True, 50, 2, 30, 5.0),
+    (B.F64, B.SPHERE, B.DE_RANDOM, True, 1000, 16, 12, 10.24),
+    (B.F64, B.ROSENBROCK, B.DE_BEST, True, 64, 8, 40, 4.096),
+    (B.F64, B.RASTRIGIN, B.DE_RANDOM, True, 257, 33, 9, 10.24),
+    (B.F64, B.ACKLEY, B.DE_BEST, True, 128, 65, 7, 65.536),
+    (B.F64, B.ROSENBROCK_EX, B.DE_RANDOM, False, 40, 5, 6, 3.0),
+    (B.F64, B.RASTRIGIN, B.DE_RANDOM, True, 4, 1, 25, 10.24),      # smallest legal population, d = 1
+    (B.F64, B.SPHERE, B.DE_BEST, True, 5, 3, 25, 1.0),
+    (B.F32, B.SPHERE, B.DE_RANDOM, True, 300, 17, 10, 10.24),
+    (B.F32, B.ROSENBROCK, B.DE_BEST, True, 100, 12, 10, 4.096),
+    (B.F32, B.RASTRIGIN, B.DE_RANDOM, True, 64, 9, 8, 10.24),
+]
+
+
+@pytest.mark.parametrize("dtype,obj,strategy,minimize,P,d,G,scale", DE_CASES)
+def test_de_restatement_equals_reference_on_tape(oracle_lib, ref_lib, dtype, obj, strategy, minimize, P, d, G, scale):
+    x0 = np.full(d, scale)
+    for g in sorted({0, 1, 2, G}):
+        cfg = B.de_cfg(dtype=dtype, objective=obj, strategy=strategy, minimize=minimize, pop_size=P, dim=d, eps=0.0,
+                       max_iter=g, best_val_no_change=1 << 40, seed=0x1234_5678_9ABC_DEF0 + P)
+        so, ao = B.de_run(oracle_lib, cfg, x0, masks=True)
+        sr, ar = B.de_run(ref_lib, cfg, x0, masks=True)
+        assert ref_lib.ref_last_inconsistencies() == 0
+        for k in ("f_value", "iterations", "function_calls", "draws_consumed", "best_index"):
+            assert so[k] == sr[k], (g, k, so[k], sr[k])
+        assert so["iterations"] == g and so["function_calls"] == P * (g + 1)
+        for k in ("x_best", "rows", "scores"):
+            assert same_bits(ao[k], ar[k]), (g, k)
+        if g > 0:
+            for k in ("donors", "dim_idx", "rejects", "accepted", "masks", "trial_scores"):
+                assert same_bits(ao[k], ar[k]), (g, k)
+
+
+def test_de_stop_rules_match_reference(oracle_lib, ref_lib):
+    # default stop rules (eps = 10e-4, best_val_no_change = 50): both std_err and val_no_change paths
+    for obj, strategy, P, d, scale in ((B.ROSENBROCK, B.DE_BEST, 64, 8, 4.096), (B.SPHERE, B.DE_RANDOM, 50, 2, 1.0),
+                                       (B.RASTRIGIN, B.DE_RANDOM, 20, 2, 0.5)):
+        cfg = B.de_cfg(objective=obj, strategy=strategy, pop_size=P, dim=d, seed=99)
+        so, ao = B.de_run(oracle_lib, cfg, np.full(d, scale))
+        sr, ar = B.de_run(ref_lib, cfg, np.full(d, scale))
+        assert so["stop_reason"] in (1, 2, 3)
+        for k in ("f_value", "iterations", "function_calls", "draws_consumed"):
+            assert so[k] == sr[k], k
+        assert same_bits(ao["x_best"], ar["x_best"]) and same_bits(ao["rows"], ar["rows"])
+
+
+def test_de_sequential_xorshift_matches_reference(oracle_lib, ref_lib):
+    for dtype in (B.F64, B.F32):
+        cfg = B.de_cfg(dtype=dtype, objective=B.RASTRIGIN, pop_size=200, dim=10, eps=0.0, max_iter=20,
+                       best_val_no_change=1 << 40, rng_mode=B.RNG_XORSHIFT)
+        so, ao = B.de_run(oracle_lib, cfg, np.full(10, 10.24))
+        sr, ar = B.de_run(ref_lib, cfg, np.full(10, 10.24))
+        assert so["f_value"] == sr["f_value"] and same_bits(ao["rows"], ar["rows"])
+
+
+# ---------------------------------------------------------------- PSO on the tape ----------------------------------
+PSO_CASES = [
+    # dtype, objective, type, minimize, constrained, P, d, G, bound
+    (B.F64, B.SPHERE, B.PSO_VANILLA, True, False, 8, 8, 40, 10.24),
+    (B.F64, B.ROSENBROCK, B.PSO_VANILLA, True, True, 6, 8, 40, 4.096),
+    (B.F64, B.RASTRIGIN, B.PSO_VANILLA, True, False, 30, 33, 15, 5.12),
+    (B.F64, B.SPHERE, B.PSO_ACCELERATED, True, False, 40, 8, 30, 10.24),
+    (B.F64, B.ACKLEY, B.PSO_ACCELERATED, True, False, 1000, 32, 12, 32.768),
+    (B.F64, B.RASTRIGIN, B.PSO_ACCELERATED, True, True, 40, 8, 50, 5.12),
+    (B.F64, B.ROSENBROCK_EX, B.PSO_ACCELERATED, False, True, 33, 5, 10, 2.0),
+    (B.F32, B.SPHERE, B.PSO_ACCELERATED, True, False, 100, 16, 10, 10.24),
+    (B.F32, B.SPHERE, B.PSO_VANILLA, True, True, 12, 16, 10, 10.24),
+]
+
+
+@pytest.mark.parametrize("dtype,obj,ptype,minimize,constrained,P,d,G,bound", PSO_CASES)
+def test_pso_restatement_equals_reference_on_tape(oracle_lib, ref_lib, dtype, obj, ptype, minimize, constrained, P, d,
+                                                  G, bound):
+    up = np.full(d, bound)
+    lo = -up
+    for g in sorted({0, 1, 2, G}):
+        cfg = B.pso_cfg(dtype=dtype, objective=obj, pso_type=ptype, minimize=minimize, n_particles=P, dim=d, eps=0.0,
+                        max_iter=g, best_val_no_change=1 << 40, constrained=constrained, seed=42 + d)
+        so, ao = B.pso_run(oracle_lib, cfg, lo, up)
+        sr, ar = B.pso_run(ref_lib, cfg, lo, up)
+        for k in ("f_value", "iterations", "function_calls", "draws_consumed", "best_valid"):
+            assert so[k] == sr[k], (g, k, so[k], sr[k])
+        for k in ("x_best", "positions", "pbest_values", "last_values"):
+            assert same_bits(ao[k], ar[k]), (g, k)
+
+
+def test_pso_stop_rules_match_reference(oracle_lib, ref_lib):
+    for ptype, P, d in ((B.PSO_ACCELERATED, 40, 8), (B.PSO_VANILLA, 8, 8)):
+        cfg = B.pso_cfg(objective=B.SPHERE, pso_type=ptype, n_particles=P, dim=d, seed=5)
+        up = np.full(d, 3.0)
+        so, ao = B.pso_run(oracle_lib, cfg, -up, up)
+        sr, ar = B.pso_run(ref_lib, cfg, -up, up)
+        for k in ("f_value", "iterations", "function_calls", "draws_consumed"):
+            assert so[k] == sr[k], k
+        assert same_bits(ao["x_best"], ar["x_best"])
