@@ -1,0 +1,177 @@
+/*
+ * nls_b200.h — C ABI of libnls_b200.so: the B200 (sm_100a) engine for nlsolver's DE / PSO population loop.
+ *
+ * This is the drop-in boundary.  The reference (JSzitas/nlsolver) is a header-only C++17 template library with no
+ * FFI layer of its own; the only process/device boundary on this path is the one introduced here:
+ *
+ *     host C++17 header (include/nlsolver_b200.hpp, same template API as the reference)
+ *         -> extern "C" (this file: plain pointers, sizes and POD structs; no CUDA or torch types)
+ *             -> CUDA kernels (nlsolver_b200/csrc/)
+ *
+ * Each entry point names the reference interface it replaces (paths are into the reference tree).  Every function
+ * returns NLS_OK (0) or a negative nls_error; the message for the calling thread is nls_last_error().  Nothing
+ * throws across this boundary.  There is NO CPU fallback: without a CUDA device nls_ctx_create fails.
+ *
+ * Threading: one solve at a time per solver handle; handles and contexts are independent of one another.
+ */
+#ifndef NLS_B200_H_
+#define NLS_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NLS_B200_VERSION 100
+
+#if defined(__GNUC__)
+#define NLS_API __attribute__((visibility("default")))
+#else
+#define NLS_API
+#endif
+
+typedef enum {
+  NLS_OK = 0,
+  NLS_ERR_INVALID = -1, /* bad argument (NULL, pop_size < 4, dim < 1, unknown enum, ...) */
+  NLS_ERR_CUDA = -2,    /* a CUDA runtime call failed; nls_last_error() has the CUDA message */
+  NLS_ERR_NOMEM = -3,   /* device allocation failed */
+  NLS_ERR_STATE = -4,   /* call not valid in the handle's current state */
+  NLS_ERR_INTERNAL = -5 /* the in-place repair did not converge (should be unreachable) */
+} nls_error;
+
+enum { NLS_F32 = 0, NLS_F64 = 1 };
+
+/* Device objective functors: N-D forms that reduce to test_functions.h:51-92 at d = 2 (summation order is the
+ * canonical one described in DESIGN.md); NLS_ROSENBROCK_EX is example.cpp:41-48 / README.md:83-90. */
+enum { NLS_SPHERE = 0, NLS_ROSENBROCK = 1, NLS_RASTRIGIN = 2, NLS_ACKLEY = 3, NLS_ROSENBROCK_EX = 4 };
+
+/* Same enumerator order as nlsolver::RecombinationStrategy {best, random} (nlsolver.h:2377) */
+enum { NLS_DE_BEST = 0, NLS_DE_RANDOM = 1 };
+/* Same enumerator order as nlsolver::PSOType {Vanilla, Accelerated} (nlsolver.h:2496) */
+enum { NLS_PSO_VANILLA = 0, NLS_PSO_ACCELERATED = 1 };
+
+/* nls_de_cfg.flags / nls_pso_cfg.flags */
+#define NLS_FLAG_RECORD_MASKS 1u   /* DE: keep the crossover mask of the last generation (P*d bytes) for parity checks */
+#define NLS_FLAG_SOCIAL_INDEX_J 2u /* vanilla PSO: social term reads swarm_best_position[j] (corrected) instead of the
+                                      reference's [i] (nlsolver.h:2674), which is only defined for n_particles <= dim */
+
+typedef struct nls_ctx nls_ctx; /* one per (process, GPU): device, stream, scratch */
+typedef struct nls_de nls_de;   /* a DE population resident in HBM */
+typedef struct nls_pso nls_pso; /* a PSO swarm resident in HBM */
+
+/* Mirrors the constructor of nlsolver::DE (nlsolver.h:2390-2402) plus what the template parameters carried. */
+typedef struct {
+  int32_t dtype;     /* NLS_F32 | NLS_F64         <- template parameter scalar_t */
+  int32_t objective; /* NLS_SPHERE ...            <- template parameter Callable (device functor tag) */
+  int32_t strategy;  /* NLS_DE_BEST | NLS_DE_RANDOM  <- template parameter RecombinationType */
+  int32_t minimize;  /* 1 = minimize(), 0 = maximize() (scores multiplied by -1, nlsolver.h:2418) */
+  uint64_t pop_size, dim;
+  double crossover_prob, differential_weight, eps; /* defaults 0.9, 0.8, 10e-4 */
+  uint64_t max_iter, best_val_no_change;           /* defaults 1000, 50 */
+  uint64_t seed;         /* draw-tape seed; the C++ header derives it from two draws of the user's RNG */
+  uint64_t agent_offset; /* global id of local agent 0 in the tape key (island model); 0 for a single population */
+  uint32_t flags, _reserved;
+} nls_de_cfg;
+
+/* Mirrors the constructor of nlsolver::PSO (nlsolver.h:2522-2551). */
+typedef struct {
+  int32_t dtype, objective;
+  int32_t pso_type; /* NLS_PSO_VANILLA | NLS_PSO_ACCELERATED */
+  int32_t minimize;
+  uint64_t n_particles, dim;
+  double inertia, cognitive_coef, social_coef, eps; /* defaults 0.8, 1.8, 1.8, 10e-4 */
+  uint64_t max_iter, best_val_no_change;            /* defaults 5000, 50 */
+  int32_t constrained; /* 1 = the (x, lower, upper) overloads: clamp positions (nlsolver.h:2577-2589, 2701-2715) */
+  uint32_t flags;
+  uint64_t seed;
+  uint64_t particle_offset;    /* sharded swarm: this handle owns global particles [offset, offset + n_particles) */
+  uint64_t n_particles_global; /* 0 = n_particles */
+} nls_pso_cfg;
+
+/* solver_status<scalar_t> (nlsolver.h:2054-2097) plus the loop counters a stepping caller needs. */
+typedef struct {
+  double f_value;          /* scores[best_id] (DE) / swarm_best_value (PSO), as the reference reports it */
+  uint64_t iterations;     /* iter */
+  uint64_t function_calls; /* function_calls_used / f_evals == P * (iter + 1) */
+  uint64_t best_index;     /* DE best_id; PSO: global index of the particle that set swarm_best_position */
+  uint64_t val_no_change;
+  int32_t stopped;     /* a stop rule has fired; further steps are no-ops */
+  int32_t stop_reason; /* 1 iter >= max_iter, 2 val_no_change >= best_val_no_change, 3 std_err < eps */
+  int32_t best_valid;  /* PSO: 0 while swarm_best_position was never assigned (the reference then returns an empty x) */
+  int32_t _reserved;
+  double std_err;           /* last value of the std_err stop statistic (nlsolver.h:2037-2052) */
+  uint64_t repair_reruns;   /* DE diagnostics: trials re-evaluated by the in-place repair passes so far */
+  uint64_t repair_rounds;   /* DE diagnostics: repair rounds executed so far */
+  uint64_t accepted_total;  /* DE diagnostics: trials accepted so far */
+} nls_status;
+
+NLS_API const char *nls_last_error(void);
+NLS_API int nls_version(void);
+
+/* stream: a cudaStream_t to enqueue on (e.g. torch's current stream), or NULL for a stream owned by the context */
+NLS_API int nls_ctx_create(int device, void *stream, nls_ctx **out);
+NLS_API int nls_ctx_destroy(nls_ctx *ctx);
+NLS_API int nls_ctx_device(const nls_ctx *ctx);
+NLS_API int nls_ctx_sm_count(const nls_ctx *ctx);
+
+/* ---- one-shot calls: DE::minimize / DE::maximize (nlsolver.h:2404-2410) and the four PSO::minimize / maximize
+ *      overloads (nlsolver.h:2553-2589).  Host buffers; x_best receives agents[best_id] / swarm_best_position. ---- */
+NLS_API int nls_de_solve(nls_ctx *ctx, const nls_de_cfg *cfg, const void *x0_host, void *x_best_host, nls_status *status);
+NLS_API int nls_pso_solve(nls_ctx *ctx, const nls_pso_cfg *cfg, const void *lower_host, const void *upper_host,
+                  void *x_best_host, nls_status *status);
+
+/* ---- stepwise DE: the same loop (DE::solve, nlsolver.h:2413-2476) cut at generation boundaries ---- */
+/* init_agents + initial scoring + first best scan / stop test (nlsolver.h:2415-2447); synchronous */
+NLS_API int nls_de_create(nls_ctx *ctx, const nls_de_cfg *cfg, const void *x0_host, nls_de **out);
+/* enqueue n generations (loop body nlsolver.h:2449-2474 + the next best scan / stop test); asynchronous */
+NLS_API int nls_de_step(nls_de *de, uint64_t n_generations);
+/* wait for enqueued work; status may be NULL */
+NLS_API int nls_de_sync(nls_de *de, nls_status *status);
+NLS_API int nls_de_read_best(nls_de *de, void *x_host);             /* agents[best_id], dim elements */
+NLS_API int nls_de_read_population(nls_de *de, void *rows_host);    /* agents, pop_size * dim elements, agent-major */
+NLS_API int nls_de_read_scores(nls_de *de, void *scores_host);      /* scores, pop_size elements */
+/* decisions of the last executed generation; any pointer may be NULL.
+ * donors: pop_size*3 (ids[1..3] of generate_indices, nlsolver.h:2331-2355); dim_idx / rejects / accepted: pop_size;
+ * trial_scores: pop_size elements of dtype; masks: pop_size*dim bytes (needs NLS_FLAG_RECORD_MASKS) */
+NLS_API int nls_de_read_decisions(nls_de *de, uint32_t *donors, uint32_t *dim_idx, uint32_t *rejects, uint8_t *accepted,
+                          void *trial_scores, uint8_t *masks);
+NLS_API int nls_de_destroy(nls_de *de);
+
+/* island-model hooks (device pointers, enqueued on the context stream; no reference counterpart) */
+/* record = [f_value (double), best global id (uint64), row (dim elements of dtype, padded to 8 bytes)] */
+NLS_API uint64_t nls_record_bytes(int32_t dtype, uint64_t dim);
+NLS_API int nls_de_export_best(nls_de *de, void *record_dev);
+/* the k best agents (lowest score first, lowest index on ties): rows k*dim elements, scores k elements */
+NLS_API int nls_de_export_top(nls_de *de, uint64_t k, void *rows_dev, void *scores_dev);
+/* replace the k worst agents (highest score first, highest index on ties) by the given rows / scores */
+NLS_API int nls_de_import_migrants(nls_de *de, uint64_t k, const void *rows_dev, const void *scores_dev);
+
+/* ---- stepwise PSO (PSO::solve, nlsolver.h:2592-2624) ---- */
+/* init_solver_state + first update_best_positions (nlsolver.h:2626-2657, 2595); synchronous.
+ * For a sharded swarm the first global exchange must follow before stepping (see nls_pso_apply_candidates). */
+NLS_API int nls_pso_create(nls_ctx *ctx, const nls_pso_cfg *cfg, const void *lower_host, const void *upper_host,
+                   nls_pso **out);
+NLS_API int nls_pso_step(nls_pso *pso, uint64_t n_generations); /* single-GPU swarm: whole generations, asynchronous */
+NLS_API int nls_pso_sync(nls_pso *pso, nls_status *status);
+NLS_API int nls_pso_read_best(nls_pso *pso, void *x_host);            /* swarm_best_position */
+NLS_API int nls_pso_read_positions(nls_pso *pso, void *rows_host);    /* particle_positions */
+NLS_API int nls_pso_read_velocities(nls_pso *pso, void *rows_host);   /* particle_velocities (vanilla) */
+NLS_API int nls_pso_read_pbest_values(nls_pso *pso, void *vals_host); /* particle_best_values */
+NLS_API int nls_pso_read_last_values(nls_pso *pso, void *vals_host);  /* objective values of the last evaluation */
+NLS_API int nls_pso_destroy(nls_pso *pso);
+
+/* sharded swarm (one handle per GPU): a generation is
+ *   nls_pso_step_local   : move + evaluate this shard's particles, reduce to the shard's candidate record
+ *   (all-gather of the records — NCCL / torch.distributed, done by the caller)
+ *   nls_pso_apply_candidates : strict-< min-loc over the gathered records against the running swarm best, lowest
+ *                              global index on ties; adopts the winner's row; updates the counters / stop test */
+NLS_API int nls_pso_step_local(nls_pso *pso, void *record_dev);
+/* copy the shard's current candidate record (e.g. the one produced by nls_pso_create) to record_dev */
+NLS_API int nls_pso_export_candidate(nls_pso *pso, void *record_dev);
+NLS_API int nls_pso_apply_candidates(nls_pso *pso, const void *records_dev, uint64_t n_records);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NLS_B200_H_ */

@@ -1,0 +1,10 @@
+"""nlsolver_b200 — B200 (sm_100a) engine for the DE / PSO population loop of JSzitas/nlsolver.
+
+The product is libnls_b200.so (C ABI: include/nls_b200.h; kernels: nlsolver_b200/csrc/).  This package is the
+Python host binding: `solvers` mirrors the reference's DE / PSO interface, `distributed` shards swarms and islands
+across GPUs with torch.distributed."""
+from ._lib import (ACKLEY, DE_BEST, DE_RANDOM, F32, F64, FLAG_RECORD_MASKS, FLAG_SOCIAL_INDEX_J, PSO_ACCELERATED,  # noqa: F401
+                   PSO_VANILLA, RASTRIGIN, ROSENBROCK, ROSENBROCK_EX, SPHERE, NlsError, lib)
+from .solvers import (DE, PSO, Ackley, Context, DEPopulation, DESolver, PSOSolver, PSOSwarm, PSOType,  # noqa: F401
+                      Rastrigin, RecombinationStrategy, Rosenbrock, RosenbrockExample, SolverStatus, Sphere, de_cfg,
+                      default_context, pso_cfg)

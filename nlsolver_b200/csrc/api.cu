@@ -1,0 +1,610 @@
+// api.cu — host side of the C ABI declared in include/nls_b200.h.
+//
+// Owns every device allocation behind opaque handles, validates arguments (the reference validates nothing:
+// pop_size < 4 loops forever in generate_indices, nlsolver.h:2344-2354), turns CUDA errors into return codes and
+// enqueues the kernels of de_impl.cuh / pso_impl.cuh on the context stream.  No CPU compute path exists here.
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/nls_b200.h"
+#include "common.cuh"
+#include "launch.h"
+#include "reduce.cuh"
+#include "state.h"
+
+using namespace nls;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char *fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+
+#define NLS_CUDA(expr)                                                                                  \
+  do {                                                                                                  \
+    cudaError_t e__ = (expr);                                                                           \
+    if (e__ != cudaSuccess)                                                                             \
+      return fail(e__ == cudaErrorMemoryAllocation ? NLS_ERR_NOMEM : NLS_ERR_CUDA, "%s: %s (%s:%d)", #expr, \
+                  cudaGetErrorString(e__), __FILE__, __LINE__);                                         \
+  } while (0)
+
+size_t elem_size(int dtype) { return dtype == NLS_F64 ? 8 : 4; }
+u64 round_up(u64 v, u64 m) { return (v + m - 1) / m * m; }
+
+// host mirror of unit<T>() for the crossover threshold search
+template <class T> T host_unit(u64 u) { return static_cast<T>(u / static_cast<T>(18446744073709551615U)); }
+
+// `unit(raw) < CR` is monotone in raw, so it equals `raw <= cr_le` for the largest raw that still satisfies it.
+template <class T>
+void crossover_threshold(double cr, u64 *cr_le, int *cr_none) {
+  const T c = static_cast<T>(cr);
+  if (!(host_unit<T>(0) < c)) { *cr_none = 1; *cr_le = 0; return; }
+  *cr_none = 0;
+  u64 lo = 0, hi = ~0ull;                 // invariant: unit(lo) < c
+  if (host_unit<T>(hi) < c) { *cr_le = hi; return; }
+  while (hi - lo > 1) {                   // unit(hi) >= c
+    const u64 mid = lo + (hi - lo) / 2;
+    if (host_unit<T>(mid) < c) lo = mid; else hi = mid;
+  }
+  *cr_le = lo;
+}
+
+}  // namespace
+
+struct nls_ctx {
+  int device;
+  cudaStream_t stream;
+  bool own_stream;
+  int sm_count;
+};
+
+namespace {
+
+struct DeviceBuffers {
+  std::vector<void *> ptrs;
+  int alloc(void **out, size_t bytes) {
+    *out = nullptr;
+    NLS_CUDA(cudaMalloc(out, bytes ? bytes : 1));
+    ptrs.push_back(*out);
+    return NLS_OK;
+  }
+  void release() { for (void *p : ptrs) cudaFree(p); ptrs.clear(); }
+};
+
+LaunchGeom make_geom(const nls_ctx *ctx, u64 n) {
+  LaunchGeom g;
+  g.sm_count = ctx->sm_count;
+  const u64 want = (n + kBlock - 1) / kBlock, cap = u64(ctx->sm_count) * 4;
+  g.reduce_blocks = int(want < cap ? (want < 1 ? 1 : want) : cap);
+  return g;
+}
+
+}  // namespace
+
+struct nls_de {
+  nls_ctx *ctx;
+  nls_de_cfg cfg;
+  DEState s;
+  LaunchGeom g;
+  const DEOps *ops;
+  DeviceBuffers mem;
+  void *record;       // internal exchange record
+  void *staging;      // read-back staging
+  size_t staging_bytes;
+  size_t elem;
+};
+
+struct nls_pso {
+  nls_ctx *ctx;
+  nls_pso_cfg cfg;
+  PSOState s;
+  LaunchGeom g;
+  const PSOOps *ops;
+  DeviceBuffers mem;
+  void *record;
+  u64 record_bytes;
+  u64 enqueued;          // generations enqueued so far (the iter value the next move kernel will see)
+  bool first_apply_pending;
+  size_t elem;
+};
+
+extern "C" {
+
+const char *nls_last_error(void) { return g_err.c_str(); }
+int nls_version(void) { return NLS_B200_VERSION; }
+
+int nls_ctx_create(int device, void *stream, nls_ctx **out) {
+  if (!out) return fail(NLS_ERR_INVALID, "nls_ctx_create: out is NULL");
+  *out = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0)
+    return fail(NLS_ERR_CUDA, "nls_ctx_create: no CUDA device (%s); this library has no CPU path",
+                cudaGetErrorString(e));
+  if (device < 0 || device >= n) return fail(NLS_ERR_INVALID, "nls_ctx_create: device %d out of range [0,%d)", device, n);
+  NLS_CUDA(cudaSetDevice(device));
+  nls_ctx *c = new nls_ctx();
+  c->device = device;
+  c->own_stream = stream == nullptr;
+  c->stream = static_cast<cudaStream_t>(stream);
+  if (c->own_stream) {
+    e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { delete c; return fail(NLS_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
+  }
+  int coop = 0;
+  cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
+  cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device);
+  if (!coop) { delete c; return fail(NLS_ERR_CUDA, "device %d lacks cooperative launch", device); }
+  *out = c;
+  return NLS_OK;
+}
+
+int nls_ctx_destroy(nls_ctx *ctx) {
+  if (!ctx) return NLS_OK;
+  cudaSetDevice(ctx->device);
+  if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+  return NLS_OK;
+}
+int nls_ctx_device(const nls_ctx *ctx) { return ctx ? ctx->device : -1; }
+int nls_ctx_sm_count(const nls_ctx *ctx) { return ctx ? ctx->sm_count : -1; }
+
+uint64_t nls_record_bytes(int32_t dtype, uint64_t dim) {
+  return sizeof(RecordHeader) + round_up(dim * elem_size(dtype), 8);
+}
+
+/* ================================================================ DE ========================================= */
+
+static int de_validate(const nls_de_cfg *c) {
+  if (c->dtype != NLS_F32 && c->dtype != NLS_F64) return fail(NLS_ERR_INVALID, "DE: unknown dtype %d", c->dtype);
+  if (c->objective < 0 || c->objective > NLS_ROSENBROCK_EX) return fail(NLS_ERR_INVALID, "DE: unknown objective %d", c->objective);
+  if (c->strategy != NLS_DE_BEST && c->strategy != NLS_DE_RANDOM) return fail(NLS_ERR_INVALID, "DE: unknown strategy %d", c->strategy);
+  if (c->pop_size < 4) return fail(NLS_ERR_INVALID, "DE: pop_size must be >= 4 (three distinct donors besides the fixed agent)");
+  if (c->dim < 1) return fail(NLS_ERR_INVALID, "DE: dim must be >= 1");
+  if (c->pop_size >= 0xffffffffull || c->dim >= 0xffffffffull) return fail(NLS_ERR_INVALID, "DE: pop_size and dim must fit 32 bits");
+  return NLS_OK;
+}
+
+int nls_de_destroy(nls_de *de) {
+  if (!de) return NLS_OK;
+  cudaSetDevice(de->ctx->device);
+  cudaStreamSynchronize(de->ctx->stream);
+  de->mem.release();
+  delete de;
+  return NLS_OK;
+}
+
+static int de_build(nls_ctx *ctx, const nls_de_cfg *cfg, const void *x0_host, nls_de *de) {
+  const u64 P = cfg->pop_size, d = cfg->dim;
+  de->ctx = ctx;
+  de->cfg = *cfg;
+  de->elem = elem_size(cfg->dtype);
+  de->ops = cfg->dtype == NLS_F64 ? de_ops_f64() : de_ops_f32();
+  de->g = make_geom(ctx, P);
+  DEState &s = de->s;
+  std::memset(&s, 0, sizeof(s));
+  s.P = P; s.d = d;
+  s.stride = round_up(d, 32 / de->elem);            // rows start on 32-byte sector boundaries
+  s.seed = cfg->seed; s.offset = cfg->agent_offset;
+  s.strategy = cfg->strategy; s.objective = cfg->objective;
+  s.F = cfg->differential_weight; s.fm = cfg->minimize ? 1.0 : -1.0; s.eps = cfg->eps;
+  s.max_iter = cfg->max_iter; s.vnc_limit = cfg->best_val_no_change;
+  u64 cr_le; int cr_none;
+  if (cfg->dtype == NLS_F64) crossover_threshold<double>(cfg->crossover_prob, &cr_le, &cr_none);
+  else crossover_threshold<float>(cfg->crossover_prob, &cr_le, &cr_none);
+  s.cr_le = cr_le; s.cr_none = cr_none;
+
+  const size_t row_bytes = size_t(P) * s.stride * de->elem;
+  int rc;
+  void *x0_dev = nullptr;
+#define NLS_ALLOC(ptr, bytes) if ((rc = de->mem.alloc(reinterpret_cast<void **>(&(ptr)), (bytes))) != NLS_OK) return rc
+  NLS_ALLOC(s.buf[0], row_bytes);
+  NLS_ALLOC(s.buf[1], row_bytes);
+  NLS_ALLOC(s.where, P);
+  NLS_ALLOC(s.score, P * de->elem);
+  NLS_ALLOC(s.tscore, P * de->elem);
+  NLS_ALLOC(s.acc, P);
+  NLS_ALLOC(s.fin, P * sizeof(uint16_t));
+  NLS_ALLOC(s.dec, P * sizeof(uint4));
+  NLS_ALLOC(s.rej, P * sizeof(uint32_t));
+  NLS_ALLOC(s.list, P * sizeof(uint32_t));
+  NLS_ALLOC(s.ctrl, sizeof(DECtrl));
+  NLS_ALLOC(s.part_min, de->g.reduce_blocks * sizeof(double));
+  NLS_ALLOC(s.part_idx, de->g.reduce_blocks * sizeof(unsigned long long));
+  NLS_ALLOC(s.part_mom, de->g.reduce_blocks * sizeof(Moments));
+  if (cfg->flags & NLS_FLAG_RECORD_MASKS) NLS_ALLOC(s.masks, P * d);
+  NLS_ALLOC(de->record, nls_record_bytes(cfg->dtype, d));
+  de->staging_bytes = std::min<size_t>(size_t(P) * d * de->elem, size_t(256) << 20);
+  NLS_ALLOC(de->staging, de->staging_bytes);
+  NLS_ALLOC(x0_dev, d * de->elem);
+#undef NLS_ALLOC
+  cudaStream_t st = ctx->stream;
+  NLS_CUDA(cudaMemsetAsync(s.ctrl, 0, sizeof(DECtrl), st));
+  NLS_CUDA(cudaMemsetAsync(s.fin, 0, P * sizeof(uint16_t), st));
+  NLS_CUDA(cudaMemsetAsync(s.dec, 0, P * sizeof(uint4), st));
+  NLS_CUDA(cudaMemsetAsync(s.rej, 0, P * sizeof(uint32_t), st));
+  if (s.masks) NLS_CUDA(cudaMemsetAsync(s.masks, 0, P * d, st));
+  NLS_CUDA(cudaMemcpyAsync(x0_dev, x0_host, d * de->elem, cudaMemcpyHostToDevice, st));
+  NLS_CUDA(de->ops->init(s, x0_dev, de->g, st));
+  NLS_CUDA(cudaStreamSynchronize(st));
+  return NLS_OK;
+}
+
+int nls_de_create(nls_ctx *ctx, const nls_de_cfg *cfg, const void *x0_host, nls_de **out) {
+  if (!ctx || !cfg || !x0_host || !out) return fail(NLS_ERR_INVALID, "nls_de_create: NULL argument");
+  *out = nullptr;
+  int rc = de_validate(cfg);
+  if (rc != NLS_OK) return rc;
+  NLS_CUDA(cudaSetDevice(ctx->device));
+  nls_de *de = new nls_de();
+  rc = de_build(ctx, cfg, x0_host, de);
+  if (rc != NLS_OK) { de->mem.release(); delete de; return rc; }
+  *out = de;
+  return NLS_OK;
+}
+
+int nls_de_step(nls_de *de, uint64_t n_generations) {
+  if (!de) return fail(NLS_ERR_INVALID, "nls_de_step: NULL handle");
+  NLS_CUDA(cudaSetDevice(de->ctx->device));
+  for (uint64_t g = 0; g < n_generations; g++) NLS_CUDA(de->ops->generation(de->s, de->g, de->ctx->stream));
+  return NLS_OK;
+}
+
+static int de_status(nls_de *de, nls_status *status) {
+  DECtrl c;
+  NLS_CUDA(cudaMemcpyAsync(&c, de->s.ctrl, sizeof(c), cudaMemcpyDeviceToHost, de->ctx->stream));
+  NLS_CUDA(cudaStreamSynchronize(de->ctx->stream));
+  if (c.error) return fail(NLS_ERR_INTERNAL, "DE in-place repair did not converge");
+  if (status) {
+    std::memset(status, 0, sizeof(*status));
+    status->f_value = c.best_value;
+    status->iterations = c.iter;
+    status->function_calls = de->s.P * (c.iter + 1);
+    status->best_index = c.best_id;
+    status->val_no_change = c.vnc;
+    status->stopped = c.stop;
+    status->stop_reason = c.stop_reason;
+    status->best_valid = 1;
+    status->std_err = c.std_err;
+    status->repair_reruns = c.reruns;
+    status->repair_rounds = c.rounds;
+    status->accepted_total = c.accepted;
+  }
+  return NLS_OK;
+}
+
+int nls_de_sync(nls_de *de, nls_status *status) {
+  if (!de) return fail(NLS_ERR_INVALID, "nls_de_sync: NULL handle");
+  NLS_CUDA(cudaSetDevice(de->ctx->device));
+  return de_status(de, status);
+}
+
+static int de_read_rows(nls_de *de, u64 first, u64 count, void *host) {
+  const size_t row = de->s.d * de->elem;
+  const u64 per_chunk = std::max<u64>(1, de->staging_bytes / row);
+  char *dst = static_cast<char *>(host);
+  for (u64 off = 0; off < count; off += per_chunk) {
+    const u64 n = std::min(per_chunk, count - off);
+    NLS_CUDA(de->ops->gather_rows(de->s, first + off, n, de->staging, de->ctx->stream));
+    NLS_CUDA(cudaMemcpyAsync(dst + off * row, de->staging, n * row, cudaMemcpyDeviceToHost, de->ctx->stream));
+    NLS_CUDA(cudaStreamSynchronize(de->ctx->stream));
+  }
+  return NLS_OK;
+}
+
+int nls_de_read_best(nls_de *de, void *x_host) {
+  if (!de || !x_host) return fail(NLS_ERR_INVALID, "nls_de_read_best: NULL argument");
+  NLS_CUDA(cudaSetDevice(de->ctx->device));
+  nls_status st;
+  int rc = de_status(de, &st);
+  if (rc != NLS_OK) return rc;
+  return de_read_rows(de, st.best_index, 1, x_host);
+}
+
+int nls_de_read_population(nls_de *de, void *rows_host) {
+  if (!de || !rows_host) return fail(NLS_ERR_INVALID, "nls_de_read_population: NULL argument");
+  NLS_CUDA(cudaSetDevice(de->ctx->device));
+  NLS_CUDA(cudaStreamSynchronize(de->ctx->stream));
+  return de_read_rows(de, 0, de->s.P, rows_host);
+}
+
+int nls_de_read_scores(nls_de *de, void *scores_host) {
+  if (!de || !scores_host) return fail(NLS_ERR_INVALID, "nls_de_read_scores: NULL argument");
+  NLS_CUDA(cudaSetDevice(de->ctx->device));
+  NLS_CUDA(cudaMemcpyAsync(scores_host, de->s.score, de->s.P * de->elem, cudaMemcpyDeviceToHost, de->ctx->stream));
+  NLS_CUDA(cudaStreamSynchronize(de->ctx->stream));
+  return NLS_OK;
+}
+
+int nls_de_read_decisions(nls_de *de, uint32_t *donors, uint32_t *dim_idx, uint32_t *rejects, uint8_t *accepted,
+                          void *trial_scores, uint8_t *masks) {
+  if (!de) return fail(NLS_ERR_INVALID, "nls_de_read_decisions: NULL handle");
+  NLS_CUDA(cudaSetDevice(de->ctx->device));
+  cudaStream_t st = de->ctx->stream;
+  const u64 P = de->s.P;
+  if (donors || dim_idx) {
+    std::vector<uint4> dec(P);
+    NLS_CUDA(cudaMemcpyAsync(dec.data(), de->s.dec, P * sizeof(uint4), cudaMemcpyDeviceToHost, st));
+    NLS_CUDA(cudaStreamSynchronize(st));
+    for (u64 i = 0; i < P; i++) {
+      if (donors) { donors[3 * i] = dec[i].x; donors[3 * i + 1] = dec[i].y; donors[3 * i + 2] = dec[i].z; }
+      if (dim_idx) dim_idx[i] = dec[i].w;
+    }
+  }
+  if (rejects) NLS_CUDA(cudaMemcpyAsync(rejects, de->s.rej, P * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+  if (accepted) NLS_CUDA(cudaMemcpyAsync(accepted, de->s.acc, P, cudaMemcpyDeviceToHost, st));
+  if (trial_scores) NLS_CUDA(cudaMemcpyAsync(trial_scores, de->s.tscore, P * de->elem, cudaMemcpyDeviceToHost, st));
+  if (masks) {
+    if (!de->s.masks) return fail(NLS_ERR_STATE, "masks were not recorded: create the handle with NLS_FLAG_RECORD_MASKS");
+    NLS_CUDA(cudaMemcpyAsync(masks, de->s.masks, P * de->s.d, cudaMemcpyDeviceToHost, st));
+  }
+  NLS_CUDA(cudaStreamSynchronize(st));
+  return NLS_OK;
+}
+
+int nls_de_export_best(nls_de *de, void *record_dev) {
+  if (!de || !record_dev) return fail(NLS_ERR_INVALID, "nls_de_export_best: NULL argument");
+  NLS_CUDA(cudaSetDevice(de->ctx->device));
+  NLS_CUDA(de->ops->export_best(de->s, record_dev, de->ctx->stream));
+  return NLS_OK;
+}
+int nls_de_export_top(nls_de *de, uint64_t k, void *rows_dev, void *scores_dev) {
+  if (!de || !rows_dev || !scores_dev) return fail(NLS_ERR_INVALID, "nls_de_export_top: NULL argument");
+  if (k < 1 || k > de->s.P) return fail(NLS_ERR_INVALID, "nls_de_export_top: k out of range");
+  NLS_CUDA(cudaSetDevice(de->ctx->device));
+  NLS_CUDA(de->ops->migrate(de->s, +1, k, rows_dev, scores_dev, de->g, de->ctx->stream));
+  return NLS_OK;
+}
+int nls_de_import_migrants(nls_de *de, uint64_t k, const void *rows_dev, const void *scores_dev) {
+  if (!de || !rows_dev || !scores_dev) return fail(NLS_ERR_INVALID, "nls_de_import_migrants: NULL argument");
+  if (k < 1 || k > de->s.P) return fail(NLS_ERR_INVALID, "nls_de_import_migrants: k out of range");
+  NLS_CUDA(cudaSetDevice(de->ctx->device));
+  NLS_CUDA(de->ops->migrate(de->s, -1, k, const_cast<void *>(rows_dev), const_cast<void *>(scores_dev), de->g,
+                            de->ctx->stream));
+  return NLS_OK;
+}
+
+int nls_de_solve(nls_ctx *ctx, const nls_de_cfg *cfg, const void *x0_host, void *x_best_host, nls_status *status) {
+  if (!x_best_host) return fail(NLS_ERR_INVALID, "nls_de_solve: x_best_host is NULL");
+  nls_de *de = nullptr;
+  int rc = nls_de_create(ctx, cfg, x0_host, &de);
+  if (rc != NLS_OK) return rc;
+  nls_status st;
+  rc = nls_de_sync(de, &st);
+  // generations past the stop rule are no-ops on the device, so batches only bound the host's polling interval
+  uint64_t batch = 4;
+  while (rc == NLS_OK && !st.stopped) {
+    const uint64_t left = cfg->max_iter > st.iterations ? cfg->max_iter - st.iterations : 1;
+    rc = nls_de_step(de, std::min<uint64_t>(batch, left));
+    if (rc == NLS_OK) rc = nls_de_sync(de, &st);
+    if (batch < 64) batch *= 2;
+  }
+  if (rc == NLS_OK) rc = nls_de_read_best(de, x_best_host);
+  if (rc == NLS_OK && status) *status = st;
+  nls_de_destroy(de);
+  return rc;
+}
+
+/* ================================================================ PSO ======================================== */
+
+static int pso_validate(const nls_pso_cfg *c) {
+  if (c->dtype != NLS_F32 && c->dtype != NLS_F64) return fail(NLS_ERR_INVALID, "PSO: unknown dtype %d", c->dtype);
+  if (c->objective < 0 || c->objective > NLS_ROSENBROCK_EX) return fail(NLS_ERR_INVALID, "PSO: unknown objective %d", c->objective);
+  if (c->pso_type != NLS_PSO_VANILLA && c->pso_type != NLS_PSO_ACCELERATED) return fail(NLS_ERR_INVALID, "PSO: unknown type %d", c->pso_type);
+  if (c->n_particles < 1 || c->dim < 1) return fail(NLS_ERR_INVALID, "PSO: n_particles and dim must be >= 1");
+  const u64 pg = c->n_particles_global ? c->n_particles_global : c->n_particles;
+  if (c->particle_offset + c->n_particles > pg) return fail(NLS_ERR_INVALID, "PSO: shard exceeds the global swarm");
+  if (c->pso_type == NLS_PSO_VANILLA && !(c->flags & NLS_FLAG_SOCIAL_INDEX_J) && pg > c->dim)
+    return fail(NLS_ERR_INVALID,
+                "vanilla PSO with n_particles > dim reads swarm_best_position out of bounds in the reference "
+                "(nlsolver.h:2674); pass NLS_FLAG_SOCIAL_INDEX_J for the corrected social term");
+  return NLS_OK;
+}
+
+int nls_pso_destroy(nls_pso *pso) {
+  if (!pso) return NLS_OK;
+  cudaSetDevice(pso->ctx->device);
+  cudaStreamSynchronize(pso->ctx->stream);
+  pso->mem.release();
+  delete pso;
+  return NLS_OK;
+}
+
+static int pso_build(nls_ctx *ctx, const nls_pso_cfg *cfg, const void *lower, const void *upper, nls_pso *p) {
+  const u64 P = cfg->n_particles, d = cfg->dim;
+  p->ctx = ctx;
+  p->cfg = *cfg;
+  p->elem = elem_size(cfg->dtype);
+  p->ops = cfg->dtype == NLS_F64 ? pso_ops_f64() : pso_ops_f32();
+  p->g = make_geom(ctx, P);
+  p->enqueued = 0;
+  PSOState &s = p->s;
+  std::memset(&s, 0, sizeof(s));
+  s.P = P; s.d = d; s.stride = round_up(d, 32 / p->elem);
+  s.P_global = cfg->n_particles_global ? cfg->n_particles_global : P;
+  s.seed = cfg->seed; s.offset = cfg->particle_offset;
+  s.pso_type = cfg->pso_type; s.objective = cfg->objective; s.constrained = cfg->constrained;
+  s.social_j = (cfg->flags & NLS_FLAG_SOCIAL_INDEX_J) ? 1 : 0;
+  s.init_inertia = cfg->inertia; s.cog = cfg->cognitive_coef; s.soc = cfg->social_coef;
+  s.fm = cfg->minimize ? 1.0 : -1.0; s.eps = cfg->eps;
+  s.max_iter = cfg->max_iter; s.vnc_limit = cfg->best_val_no_change;
+  p->record_bytes = nls_record_bytes(cfg->dtype, d);
+  const size_t row_bytes = size_t(P) * s.stride * p->elem;
+  int rc;
+#define NLS_ALLOC(ptr, bytes) if ((rc = p->mem.alloc(reinterpret_cast<void **>(&(ptr)), (bytes))) != NLS_OK) return rc
+  NLS_ALLOC(s.pos, row_bytes);
+  if (cfg->pso_type == NLS_PSO_VANILLA) NLS_ALLOC(s.vel, row_bytes);
+  NLS_ALLOC(s.pbest, P * p->elem);
+  NLS_ALLOC(s.last, P * p->elem);
+  NLS_ALLOC(s.sbest, s.stride * p->elem);
+  NLS_ALLOC(s.lower, d * p->elem);
+  NLS_ALLOC(s.upper, d * p->elem);
+  NLS_ALLOC(s.ctrl, sizeof(PSOCtrl));
+  NLS_ALLOC(s.part_min, p->g.reduce_blocks * sizeof(double));
+  NLS_ALLOC(s.part_idx, p->g.reduce_blocks * sizeof(unsigned long long));
+  NLS_ALLOC(s.part_mom, p->g.reduce_blocks * sizeof(Moments));
+  NLS_ALLOC(p->record, p->record_bytes);
+#undef NLS_ALLOC
+  cudaStream_t st = ctx->stream;
+  PSOCtrl c0;
+  std::memset(&c0, 0, sizeof(c0));
+  c0.best_value = 100000.0;                          // swarm_best_value, nlsolver.h:2631
+  NLS_CUDA(cudaMemcpyAsync(s.ctrl, &c0, sizeof(c0), cudaMemcpyHostToDevice, st));
+  NLS_CUDA(cudaMemsetAsync(s.sbest, 0, s.stride * p->elem, st));
+  NLS_CUDA(cudaMemsetAsync(p->record, 0, p->record_bytes, st));
+  NLS_CUDA(cudaMemcpyAsync(s.lower, lower, d * p->elem, cudaMemcpyHostToDevice, st));
+  NLS_CUDA(cudaMemcpyAsync(s.upper, upper, d * p->elem, cudaMemcpyHostToDevice, st));
+  NLS_CUDA(cudaStreamSynchronize(st));               // c0 lives on this stack frame
+  NLS_CUDA(p->ops->init(s, p->g, st));
+  NLS_CUDA(p->ops->candidate(s, p->record, p->g, st));
+  p->first_apply_pending = true;
+  if (s.P_global == P) {                              // single-GPU swarm: finish update_best_positions here
+    NLS_CUDA(p->ops->apply(s, p->record, 1, p->record_bytes, 1, st));
+    p->first_apply_pending = false;
+  }
+  NLS_CUDA(cudaStreamSynchronize(st));
+  return NLS_OK;
+}
+
+int nls_pso_create(nls_ctx *ctx, const nls_pso_cfg *cfg, const void *lower_host, const void *upper_host,
+                   nls_pso **out) {
+  if (!ctx || !cfg || !lower_host || !upper_host || !out) return fail(NLS_ERR_INVALID, "nls_pso_create: NULL argument");
+  *out = nullptr;
+  int rc = pso_validate(cfg);
+  if (rc != NLS_OK) return rc;
+  NLS_CUDA(cudaSetDevice(ctx->device));
+  nls_pso *p = new nls_pso();
+  rc = pso_build(ctx, cfg, lower_host, upper_host, p);
+  if (rc != NLS_OK) { p->mem.release(); delete p; return rc; }
+  *out = p;
+  return NLS_OK;
+}
+
+// inertia the reference would hold while moving in iteration `iter` (nlsolver.h:2613; vanilla keeps the ctor value)
+static double pso_inertia(const nls_pso *p, u64 iter) {
+  if (p->cfg.pso_type == NLS_PSO_VANILLA) return p->cfg.inertia;
+  if (p->cfg.dtype == NLS_F64) return std::pow(p->cfg.inertia, static_cast<double>(iter));
+  return static_cast<double>(static_cast<float>(std::pow(static_cast<double>(static_cast<float>(p->cfg.inertia)),
+                                                         static_cast<double>(iter))));
+}
+
+int nls_pso_step_local(nls_pso *p, void *record_dev) {
+  if (!p) return fail(NLS_ERR_INVALID, "nls_pso_step_local: NULL handle");
+  if (p->first_apply_pending) return fail(NLS_ERR_STATE, "sharded swarm: apply the initial candidates before stepping");
+  NLS_CUDA(cudaSetDevice(p->ctx->device));
+  cudaStream_t st = p->ctx->stream;
+  NLS_CUDA(p->ops->move(p->s, pso_inertia(p, p->enqueued), p->g, st));
+  NLS_CUDA(p->ops->candidate(p->s, p->record, p->g, st));
+  p->enqueued++;
+  if (record_dev) NLS_CUDA(cudaMemcpyAsync(record_dev, p->record, p->record_bytes, cudaMemcpyDeviceToDevice, st));
+  return NLS_OK;
+}
+
+int nls_pso_export_candidate(nls_pso *p, void *record_dev) {
+  if (!p || !record_dev) return fail(NLS_ERR_INVALID, "nls_pso_export_candidate: NULL argument");
+  NLS_CUDA(cudaSetDevice(p->ctx->device));
+  NLS_CUDA(cudaMemcpyAsync(record_dev, p->record, p->record_bytes, cudaMemcpyDeviceToDevice, p->ctx->stream));
+  return NLS_OK;
+}
+
+int nls_pso_apply_candidates(nls_pso *p, const void *records_dev, uint64_t n_records) {
+  if (!p || !records_dev || n_records < 1) return fail(NLS_ERR_INVALID, "nls_pso_apply_candidates: bad argument");
+  NLS_CUDA(cudaSetDevice(p->ctx->device));
+  NLS_CUDA(p->ops->apply(p->s, records_dev, n_records, p->record_bytes, p->first_apply_pending ? 1 : 0, p->ctx->stream));
+  p->first_apply_pending = false;
+  return NLS_OK;
+}
+
+int nls_pso_step(nls_pso *p, uint64_t n_generations) {
+  if (!p) return fail(NLS_ERR_INVALID, "nls_pso_step: NULL handle");
+  if (p->s.P_global != p->s.P) return fail(NLS_ERR_STATE, "nls_pso_step is for a single-GPU swarm; a shard uses step_local / apply_candidates");
+  for (uint64_t g = 0; g < n_generations; g++) {
+    int rc = nls_pso_step_local(p, nullptr);
+    if (rc != NLS_OK) return rc;
+    rc = nls_pso_apply_candidates(p, p->record, 1);
+    if (rc != NLS_OK) return rc;
+  }
+  return NLS_OK;
+}
+
+int nls_pso_sync(nls_pso *p, nls_status *status) {
+  if (!p) return fail(NLS_ERR_INVALID, "nls_pso_sync: NULL handle");
+  NLS_CUDA(cudaSetDevice(p->ctx->device));
+  PSOCtrl c;
+  NLS_CUDA(cudaMemcpyAsync(&c, p->s.ctrl, sizeof(c), cudaMemcpyDeviceToHost, p->ctx->stream));
+  NLS_CUDA(cudaStreamSynchronize(p->ctx->stream));
+  // a stop rule that fired on the device turned the generations enqueued after it into no-ops; until then every
+  // enqueued generation ran, so the host count (which picks the accelerated inertia, nlsolver.h:2613) is exact
+  if (c.stop) p->enqueued = c.iter;
+  if (status) {
+    std::memset(status, 0, sizeof(*status));
+    status->f_value = c.best_value;
+    status->iterations = c.iter;
+    status->function_calls = p->s.P_global * (c.iter + 1);
+    status->best_index = c.best_index;
+    status->val_no_change = c.vnc;
+    status->stopped = c.stop;
+    status->stop_reason = c.stop_reason;
+    status->best_valid = c.best_valid;
+    status->std_err = c.std_err;
+  }
+  return NLS_OK;
+}
+
+static int pso_read(nls_pso *p, const void *dev, size_t bytes, void *host, const char *what) {
+  if (!p || !host) return fail(NLS_ERR_INVALID, "%s: NULL argument", what);
+  if (!dev) return fail(NLS_ERR_STATE, "%s: not available for this swarm type", what);
+  NLS_CUDA(cudaSetDevice(p->ctx->device));
+  NLS_CUDA(cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, p->ctx->stream));
+  NLS_CUDA(cudaStreamSynchronize(p->ctx->stream));
+  return NLS_OK;
+}
+static int pso_read_rows(nls_pso *p, const void *dev, void *host, const char *what) {
+  if (!p || !host) return fail(NLS_ERR_INVALID, "%s: NULL argument", what);
+  if (!dev) return fail(NLS_ERR_STATE, "%s: not available for this swarm type", what);
+  NLS_CUDA(cudaSetDevice(p->ctx->device));
+  NLS_CUDA(cudaMemcpy2DAsync(host, p->s.d * p->elem, dev, p->s.stride * p->elem, p->s.d * p->elem, p->s.P,
+                             cudaMemcpyDeviceToHost, p->ctx->stream));
+  NLS_CUDA(cudaStreamSynchronize(p->ctx->stream));
+  return NLS_OK;
+}
+int nls_pso_read_best(nls_pso *p, void *x_host) { return pso_read(p, p ? p->s.sbest : nullptr, p ? p->s.d * p->elem : 0, x_host, "nls_pso_read_best"); }
+int nls_pso_read_positions(nls_pso *p, void *rows_host) { return pso_read_rows(p, p ? p->s.pos : nullptr, rows_host, "nls_pso_read_positions"); }
+int nls_pso_read_velocities(nls_pso *p, void *rows_host) { return pso_read_rows(p, p ? p->s.vel : nullptr, rows_host, "nls_pso_read_velocities"); }
+int nls_pso_read_pbest_values(nls_pso *p, void *vals_host) { return pso_read(p, p ? p->s.pbest : nullptr, p ? p->s.P * p->elem : 0, vals_host, "nls_pso_read_pbest_values"); }
+int nls_pso_read_last_values(nls_pso *p, void *vals_host) { return pso_read(p, p ? p->s.last : nullptr, p ? p->s.P * p->elem : 0, vals_host, "nls_pso_read_last_values"); }
+
+int nls_pso_solve(nls_ctx *ctx, const nls_pso_cfg *cfg, const void *lower_host, const void *upper_host,
+                  void *x_best_host, nls_status *status) {
+  if (!x_best_host) return fail(NLS_ERR_INVALID, "nls_pso_solve: x_best_host is NULL");
+  nls_pso *p = nullptr;
+  int rc = nls_pso_create(ctx, cfg, lower_host, upper_host, &p);
+  if (rc != NLS_OK) return rc;
+  nls_status st;
+  rc = nls_pso_sync(p, &st);
+  uint64_t batch = 4;
+  while (rc == NLS_OK && !st.stopped) {
+    const uint64_t left = cfg->max_iter > st.iterations ? cfg->max_iter - st.iterations : 1;
+    rc = nls_pso_step(p, std::min<uint64_t>(batch, left));
+    if (rc == NLS_OK) rc = nls_pso_sync(p, &st);
+    if (batch < 64) batch *= 2;
+  }
+  if (rc == NLS_OK && st.best_valid) rc = nls_pso_read_best(p, x_best_host);
+  if (rc == NLS_OK && status) *status = st;
+  nls_pso_destroy(p);
+  return rc;
+}
+
+}  /* extern "C" */

@@ -1,0 +1,488 @@
+// de_impl.cuh — the DE generation on B200.  One warp owns one agent; rows live agent-major in HBM and are streamed
+// with 128-bit loads; the objective is a lane-strided sum closed by a warp butterfly.
+//
+// Reference semantics being reproduced (DE::solve, nlsolver.h:2413-2476): agents are processed sequentially and IN
+// PLACE — agent i reads donor r's row *after* r's own greedy selection when r < i and *before* it when r > i
+// (nlsolver.h:2466-2471 vs 2368-2372).  A synchronous double-buffered generation is a different algorithm
+// (SURVEY.md §7.3 item 1), so the generation is run as speculate + exact repair:
+//
+//   K2  de_generation_kernel : every agent builds and scores its trial against the PRE-generation rows (full HBM
+//                              bandwidth, no ordering), records donors / dim / rejects, accepts greedily; an accepted
+//                              trial is written to the agent's row in the OTHER buffer, so pre-generation rows stay.
+//   K2r de_repair_kernel     : cooperative kernel.  The "donor r < i" relation is a shallow DAG (depth ~17 at 2^20).
+//                              Round by round, an agent whose lower donors are all final becomes final; if any of
+//                              them was accepted, its trial is re-evaluated against the now-known rows.  Each agent
+//                              is therefore evaluated at most twice and the result equals the sequential loop.
+//   K3  de_commit_kernel     : commits accepted trials (score, row-location bit), then the population reduction:
+//                              min-loc with the reference's tie rule (nlsolver.h:2432-2437), the std_err statistic
+//                              (nlsolver.h:2037-2052) and the stop test (nlsolver.h:2439-2447), last block finalises.
+#pragma once
+#include <cooperative_groups.h>
+#include <math_constants.h>
+
+#include "objectives.cuh"
+#include "reduce.cuh"
+#include "launch.h"
+#include "state.h"
+
+namespace nls {
+namespace cg = cooperative_groups;
+
+
+// ------------------------------------------------------------------------------------------------ row pass
+template <class T, bool RESOLVED>
+__device__ __forceinline__ const T *de_row_of(const DEState &s, u64 r, u64 i) {
+  u32 w = s.where[r];
+  if (RESOLVED && r < i && s.acc[r]) w ^= 1u;   // a lower donor whose trial was accepted already holds its new row
+  return static_cast<const T *>(s.buf[w]) + r * s.stride;
+}
+
+// One sweep over the d coordinates of agent i's trial (propose_new_agent, nlsolver.h:2357-2375):
+//   trial[j] = mut ? A[r1][j] + F * (A[r2][j] - A[r3][j]) : A[r0][j],   mut = (draw_j < CR) || (j == dim)
+// EVAL accumulates the objective; WRITE stores the trial into `dst`.
+template <class T, int OBJ, bool EVAL, bool WRITE>
+__device__ __forceinline__ T de_sweep(const DEState &s, const T *p0, const T *p1, const T *p2, const T *p3, T *dst,
+                                      u64 sbase, u64 dim, u64 i, int lane) {
+  constexpr int V = Vec<T>::V;
+  constexpr int U = 2;                                 // steps in flight per lane: 2 x 4 x 16 B of loads
+  typedef Ar<T> A;
+  const u64 d = s.d;
+  const T F = static_cast<T>(s.F);
+  const u64 cr_le = s.cr_le;
+  const bool cr_any = !s.cr_none;
+  const u64 n_steps = (d + 32 * V - 1) / (32 * V);
+  Objective<T, OBJ> obj;
+  if (EVAL) obj.begin(lane, d);
+  for (u64 st0 = 0; st0 < n_steps; st0 += U) {
+    T x1[U][V], x2[U][V], x3[U][V], x0[U][V];
+    bool mut[U][V];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const u64 j0 = ((st0 + u) * 32 + lane) * V;
+      const bool in = j0 < d;
+      bool all_mut = true;
+#pragma unroll
+      for (int q = 0; q < V; q++) {
+        const u64 j = j0 + q;
+        mut[u][q] = (cr_any && mix64(sbase + kGolden * j) <= cr_le) || (j == dim);
+        all_mut &= mut[u][q];
+      }
+      if (in) {
+        ld_row(p1 + j0, x1[u]); ld_row(p2 + j0, x2[u]); ld_row(p3 + j0, x3[u]);
+        if (!all_mut) ld_row(p0 + j0, x0[u]);          // the base row is only touched where a coordinate keeps it
+        else {
+#pragma unroll
+          for (int q = 0; q < V; q++) x0[u][q] = T(0);
+        }
+      } else {
+#pragma unroll
+        for (int q = 0; q < V; q++) { x1[u][q] = T(0); x2[u][q] = T(0); x3[u][q] = T(0); x0[u][q] = T(0); }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const u64 j0 = ((st0 + u) * 32 + lane) * V;
+      T t[V];
+#pragma unroll
+      for (int q = 0; q < V; q++)
+        t[q] = mut[u][q] ? A::add(x1[u][q], A::mul(F, A::sub(x2[u][q], x3[u][q]))) : x0[u][q];
+      if (WRITE && j0 < d) st_row(dst + j0, t);
+      if (EVAL) {
+        if (st0 + u < n_steps) obj.step(t, j0, d, lane);
+        if (s.masks != nullptr) {
+#pragma unroll
+          for (int q = 0; q < V; q++)
+            if (j0 + q < d) s.masks[i * d + j0 + q] = mut[u][q];
+        }
+      }
+    }
+  }
+  return EVAL ? obj.finish(d) : T(0);
+}
+
+// Build, score and greedily select agent i's trial (loop body nlsolver.h:2459-2471).
+template <class T, int OBJ, bool RESOLVED>
+__device__ __forceinline__ void de_trial(const DEState &s, u64 i, u64 key, u64 r0, u64 r1, u64 r2, u64 r3, u64 dim,
+                                         u32 rej, int lane) {
+  const T *p0 = de_row_of<T, RESOLVED>(s, r0, i);
+  const T *p1 = de_row_of<T, RESOLVED>(s, r1, i);
+  const T *p2 = de_row_of<T, RESOLVED>(s, r2, i);
+  const T *p3 = de_row_of<T, RESOLVED>(s, r3, i);
+  T *dst = static_cast<T *>(s.buf[s.where[i] ^ 1u]) + i * s.stride;
+  const u64 sbase = tape_state(key, 4 + rej);           // draws 0..2+rej: indices, 3+rej: dim, then one per coordinate
+  const T raw = de_sweep<T, OBJ, true, false>(s, p0, p1, p2, p3, dst, sbase, dim, i, lane);
+  const T score = Ar<T>::mul(static_cast<T>(s.fm), raw);
+  const bool ok = score < static_cast<const T *>(s.score)[i];   // strict <, NaN never accepted (nlsolver.h:2466)
+  if (ok)   // re-stream the (L2-warm) donor rows and materialise the trial; ~a few % of agents
+    de_sweep<T, OBJ, false, true>(s, p0, p1, p2, p3, dst, sbase, dim, i, lane);
+  if (lane == 0) {
+    static_cast<T *>(s.tscore)[i] = score;
+    s.acc[i] = ok;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ K1 init
+// init_agents / generate_sequence + initial scoring (nlsolver.h:2302-2323, 2423-2425):
+//   agent[j] = (g() - 0.5) * x0[j]   evaluated in double even for T = float, like the reference expression
+template <class T, int OBJ>
+__global__ void __launch_bounds__(kBlock) de_init_kernel(DEState s, const T *__restrict__ x0) {
+  constexpr int V = Vec<T>::V;
+  const int lane = threadIdx.x & 31;
+  const u64 warp = (u64(blockIdx.x) * kBlock + threadIdx.x) >> 5, n_warps = (u64(gridDim.x) * kBlock) >> 5;
+  const u64 d = s.d, gen_key = tape_gen_key(s.seed, 0);
+  const u64 n_steps = (d + 32 * V - 1) / (32 * V);
+  for (u64 i = warp; i < s.P; i += n_warps) {
+    const u64 key = tape_key(gen_key, s.offset + i);
+    T *row = static_cast<T *>(s.buf[0]) + i * s.stride;
+    Objective<T, OBJ> obj;
+    obj.begin(lane, d);
+    for (u64 st = 0; st < n_steps; st++) {
+      const u64 j0 = (st * 32 + lane) * V;
+      T t[V];
+#pragma unroll
+      for (int q = 0; q < V; q++) {
+        const u64 j = j0 + q;
+        t[q] = T(0);
+        if (j < d)
+          t[q] = static_cast<T>(__dmul_rn(__dsub_rn(static_cast<double>(unit<T>(tape_draw(key, j))), 0.5),
+                                          static_cast<double>(x0[j])));
+      }
+      if (j0 < d) st_row(row + j0, t);
+      obj.step(t, j0, d, lane);
+    }
+    const T score = Ar<T>::mul(static_cast<T>(s.fm), obj.finish(d));
+    if (lane == 0) {
+      static_cast<T *>(s.score)[i] = score;
+      static_cast<T *>(s.tscore)[i] = score;
+      s.where[i] = 0;
+      s.acc[i] = 0;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ K2 generation
+// generate_indices (nlsolver.h:2331-2355): draw until three proposals differ from `fixed` and from each other.
+template <class T>
+__device__ __forceinline__ void de_select_donors(u64 key, u64 P, u64 fixed, u64 &r1, u64 &r2, u64 &r3, u32 &rej) {
+  u64 k = 0;
+  rej = 0;
+  for (;;) { r1 = index_from<T>(tape_draw(key, k++), P); if (r1 != fixed) break; rej++; }
+  for (;;) { r2 = index_from<T>(tape_draw(key, k++), P); if (r2 != fixed && r2 != r1) break; rej++; }
+  for (;;) { r3 = index_from<T>(tape_draw(key, k++), P); if (r3 != fixed && r3 != r1 && r3 != r2) break; rej++; }
+}
+
+template <class T, int OBJ>
+__global__ void __launch_bounds__(kBlock) de_generation_kernel(DEState s) {
+  const DECtrl *ctrl = s.ctrl;
+  if (ctrl->stop) return;
+  const int lane = threadIdx.x & 31;
+  const u64 warp = (u64(blockIdx.x) * kBlock + threadIdx.x) >> 5, n_warps = (u64(gridDim.x) * kBlock) >> 5;
+  const u64 gen_key = tape_gen_key(s.seed, ctrl->iter + 1), best_id = ctrl->best_id;
+  for (u64 i = warp; i < s.P; i += n_warps) {
+    const u64 key = tape_key(gen_key, s.offset + i);
+    const u64 fixed = s.strategy ? i : best_id;         // NLS_DE_RANDOM = 1: ids[0] = i; best: ids[0] = best_id
+    u64 r1, r2, r3;
+    u32 rej;
+    de_select_donors<T>(key, s.P, fixed, r1, r2, r3, rej);
+    const u64 dim = index_from<T>(tape_draw(key, 3 + rej), s.d);
+    if (lane == 0) {
+      s.dec[i] = make_uint4(u32(r1), u32(r2), u32(r3), u32(dim));
+      s.rej[i] = rej;
+      s.fin[i] = 0;
+    }
+    de_trial<T, OBJ, false>(s, i, key, fixed, r1, r2, r3, dim, rej, lane);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ K2r repair
+template <class T, int OBJ>
+__global__ void __launch_bounds__(kBlock) de_repair_kernel(DEState s) {
+  cg::grid_group grid = cg::this_grid();
+  DECtrl *ctrl = s.ctrl;
+  if (ctrl->stop) return;                                // uniform over the grid: only K3 changes it
+  const int lane = threadIdx.x & 31;
+  const u64 tid = u64(blockIdx.x) * kBlock + threadIdx.x, n_threads = u64(gridDim.x) * kBlock;
+  const u64 warp = tid >> 5, n_warps = n_threads >> 5;
+  const u64 gen_key = tape_gen_key(s.seed, ctrl->iter + 1), best_id = ctrl->best_id;
+  const bool best_mode = s.strategy == 0;
+  u32 reruns = 0, round = 1;
+  for (;; round++) {
+    const u32 par = round & 1u;
+    // phase A: classify the pending agents.  A donor is "final for this round" iff it was finalised in an EARLIER
+    // round (0 < fin < round), which makes the outcome independent of the order in which threads run.
+    u32 still = 0;
+    for (u64 base = warp * 32; base < s.P; base += n_threads) {
+      const u64 i = base + lane;
+      bool rerun = false;
+      if (i < s.P && s.fin[i] == 0) {
+        const uint4 dc = s.dec[i];
+        bool wait = false, dirty = false;
+        auto look = [&](u64 r) {
+          if (r < i) {
+            const u32 f = s.fin[r];
+            if (f == 0 || f >= round) wait = true;
+            else if (s.acc[r]) dirty = true;
+          }
+        };
+        look(dc.x); look(dc.y); look(dc.z);
+        if (best_mode) look(best_id);
+        if (wait) still++;
+        else { s.fin[i] = uint16_t(round); rerun = dirty; }
+      }
+      const u32 vote = __ballot_sync(kFull, rerun);
+      if (vote) {
+        u32 slot = 0;
+        if (lane == 0) slot = atomicAdd(&ctrl->list_count[par], __popc(vote));
+        slot = __shfl_sync(kFull, slot, 0);
+        if (rerun) s.list[slot + __popc(vote & ((1u << lane) - 1u))] = u32(i);
+      }
+    }
+    still = __reduce_add_sync(kFull, still);
+    if (lane == 0 && still) atomicAdd(&ctrl->pending[par], still);
+    grid.sync();
+    // every thread has now taken the previous round's exit decision, so the other parity's counters can be cleared
+    // for the next round's phase A (which starts after the second barrier below)
+    if (tid == 0) { ctrl->pending[par ^ 1u] = 0; ctrl->list_count[par ^ 1u] = 0; }
+    // phase B: re-evaluate the listed agents against rows that are now known
+    const u32 n_list = *reinterpret_cast<volatile unsigned int *>(&ctrl->list_count[par]);
+    for (u64 e = warp; e < n_list; e += n_warps) {
+      const u64 i = s.list[e];
+      const uint4 dc = s.dec[i];
+      const u64 key = tape_key(gen_key, s.offset + i);
+      de_trial<T, OBJ, true>(s, i, key, best_mode ? best_id : i, dc.x, dc.y, dc.z, dc.w, s.rej[i], lane);
+    }
+    if (warp == 0) reruns += n_list;
+    grid.sync();
+    const u32 pend = *reinterpret_cast<volatile unsigned int *>(&ctrl->pending[par]);
+    if (pend == 0) break;
+    if (round >= 65000u) { if (tid == 0) ctrl->error = 1; break; }
+  }
+  if (tid == 0) { ctrl->reruns += reruns; ctrl->rounds += round; }
+}
+
+// ------------------------------------------------------------------------------------------------ K3 commit + reduce
+template <class T>
+// mode 0: commit the generation in flight; 1: first scan after init; 2: re-scan after island migration (best only)
+__global__ void __launch_bounds__(kBlock) de_commit_kernel(DEState s, int mode) {
+  const bool initial = mode != 0;
+  DECtrl *ctrl = s.ctrl;
+  if (ctrl->stop) return;
+  T *score = static_cast<T *>(s.score);
+  const T *tscore = static_cast<const T *>(s.tscore);
+  u32 n_acc = 0;
+  auto item = [&](u64 i, double &for_min, double &for_moments) {
+    if (!initial && s.acc[i]) { score[i] = tscore[i]; s.where[i] ^= 1u; n_acc++; }
+    for_min = for_moments = static_cast<double>(score[i]);
+  };
+  auto fin = [&](MinLoc ml, Moments mo) {
+    if (!initial) ctrl->iter += 1;                        // nlsolver.h:2474
+    const u64 prev = ctrl->best_id;
+    bool not_updated = true;                              // best scan, nlsolver.h:2430-2437: the scan keeps best_id
+    if (ml.v < static_cast<double>(__ldcg(score + prev))) { ctrl->best_id = ml.i; not_updated = false; }
+    ctrl->best_value = static_cast<double>(__ldcg(score + ctrl->best_id));
+    ctrl->score_moments = mo;
+    if (mode == 2) { if (!not_updated) ctrl->vnc = 0; return; }
+    ctrl->vnc = not_updated ? ctrl->vnc + 1 : 0;          // nlsolver.h:2439
+    int reason = 0;                                       // nlsolver.h:2441-2443, same short-circuit order
+    if (ctrl->iter >= s.max_iter) reason = 1;
+    else if (ctrl->vnc >= s.vnc_limit) reason = 2;
+    else {
+      const T se = static_cast<T>(sqrt(mo.m2 / (mo.n - 1.0)));
+      ctrl->std_err = static_cast<double>(se);
+      if (se < static_cast<T>(s.eps)) reason = 3;
+    }
+    ctrl->accepted += ctrl->acc_partial;
+    ctrl->acc_partial = 0;
+    ctrl->pending[0] = ctrl->pending[1] = ctrl->list_count[0] = ctrl->list_count[1] = 0;
+    if (ctrl->error) reason = reason ? reason : 4;
+    ctrl->stop_reason = reason;
+    __threadfence();
+    ctrl->stop = reason != 0;
+  };
+  auto post = [&]() {
+    n_acc = __reduce_add_sync(kFull, n_acc);
+    if ((threadIdx.x & 31) == 0 && n_acc) atomicAdd(&ctrl->acc_partial, n_acc);
+  };
+  MinLoc ml;
+  Moments mo;
+  if (population_reduce(s.P, s.part_min, s.part_idx, s.part_mom, &ctrl->ticket, item, post, ml, mo) &&
+      threadIdx.x == 0)
+    fin(ml, mo);
+}
+
+// ------------------------------------------------------------------------------------------------ island hooks
+// (no reference counterpart — SURVEY.md §8e: each GPU runs a reference-exact DE on its island; these kernels export the
+//  island best, pick the k best emigrants and overwrite the k worst agents with immigrants, all deterministically.)
+template <class T>
+__global__ void __launch_bounds__(kBlock) de_export_best_kernel(DEState s, void *record) {
+  const DECtrl *ctrl = s.ctrl;
+  RecordHeader *h = static_cast<RecordHeader *>(record);
+  const u64 b = ctrl->best_id;
+  if (threadIdx.x == 0) {
+    h->value = ctrl->best_value; h->index = s.offset + b; h->moments = ctrl->score_moments; h->valid = 1; h->_pad = 0;
+  }
+  T *row = reinterpret_cast<T *>(h + 1);
+  const T *src = static_cast<const T *>(s.buf[s.where[b]]) + b * s.stride;
+  for (u64 j = threadIdx.x; j < s.d; j += kBlock) row[j] = __ldcg(src + j);
+}
+
+// One selection round: the next agent after the cursor (sel_value, sel_index) in the order
+//   best-first  (sign = +1): ascending score, ascending index on ties
+//   worst-first (sign = -1): descending score, descending index on ties
+// The last block stores the pick in list[slot] and advances the cursor.  `first` starts a new selection.
+template <class T>
+__global__ void __launch_bounds__(kBlock) de_select_kernel(DEState s, int sign, u32 slot, int first) {
+  DECtrl *ctrl = s.ctrl;
+  const T *score = static_cast<const T *>(s.score);
+  const double cv = ctrl->sel_value;
+  const u64 ci = ctrl->sel_index;
+  const u64 P = s.P;
+  auto item = [&](u64 i, double &for_min, double &for_moments) {
+    // keys: (sign * score, sign > 0 ? i : P - 1 - i); population_reduce walks i upward, so for the worst-first
+    // order the element visited is P - 1 - i, which keeps "lower visit index wins ties" == "higher agent index wins"
+    const u64 a = sign > 0 ? i : P - 1 - i;
+    const double v = sign * static_cast<double>(score[a]);
+    const bool beyond = first || v > cv || (v == cv && i > ci);
+    for_min = beyond ? v : CUDART_INF;
+    for_moments = 0.0;
+  };
+  MinLoc ml;
+  Moments mo;
+  if (population_reduce(P, s.part_min, s.part_idx, s.part_mom, &ctrl->ticket, item, [] {}, ml, mo) && threadIdx.x == 0) {
+    ctrl->sel_value = ml.v; ctrl->sel_index = ml.i;
+    s.list[slot] = ml.i == ~0ull ? 0xffffffffu : u32(sign > 0 ? ml.i : P - 1 - ml.i);
+  }
+}
+
+// copy the k selected rows / scores out (emigrants) ...
+template <class T>
+__global__ void __launch_bounds__(kBlock) de_gather_kernel(DEState s, u32 k, T *rows, T *scores) {
+  for (u32 e = blockIdx.x; e < k; e += gridDim.x) {
+    const u32 a = s.list[e];
+    if (a == 0xffffffffu) continue;
+    const T *src = static_cast<const T *>(s.buf[s.where[a]]) + u64(a) * s.stride;
+    for (u64 j = threadIdx.x; j < s.d; j += kBlock) rows[u64(e) * s.d + j] = __ldcg(src + j);
+    if (threadIdx.x == 0) scores[e] = static_cast<const T *>(s.score)[a];
+  }
+}
+// ... or overwrite the k selected agents (immigrants): row in place, score, and nothing else
+template <class T>
+__global__ void __launch_bounds__(kBlock) de_scatter_kernel(DEState s, u32 k, const T *rows, const T *scores) {
+  for (u32 e = blockIdx.x; e < k; e += gridDim.x) {
+    const u32 a = s.list[e];
+    if (a == 0xffffffffu) continue;
+    T *dst = static_cast<T *>(s.buf[s.where[a]]) + u64(a) * s.stride;
+    for (u64 j = threadIdx.x; j < s.d; j += kBlock) dst[j] = rows[u64(e) * s.d + j];
+    if (threadIdx.x == 0) static_cast<T *>(s.score)[a] = scores[e];
+  }
+}
+
+// compact rows [first, first + count) of the current population into `out` (host read-back path)
+template <class T>
+__global__ void __launch_bounds__(kBlock) de_gather_rows_kernel(DEState s, u64 first, u64 count, T *out) {
+  for (u64 e = blockIdx.x; e < count; e += gridDim.x) {
+    const u64 a = first + e;
+    const T *src = static_cast<const T *>(s.buf[s.where[a]]) + a * s.stride;
+    for (u64 j = threadIdx.x; j < s.d; j += kBlock) out[e * s.d + j] = __ldcg(src + j);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ host launchers
+template <class K>
+inline int blocks_per_sm(K kernel) {
+  int n = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, kBlock, 0);
+  return n < 1 ? 1 : n;
+}
+inline unsigned int clamp_grid(u64 want, u64 cap) {
+  const u64 g = want < cap ? want : cap;
+  return static_cast<unsigned int>(g < 1 ? 1 : g);
+}
+
+#define NLS_OBJ_SWITCH(obj, CALL)                      \
+  switch (obj) {                                       \
+    case OBJ_SPHERE: { CALL(OBJ_SPHERE); } break;      \
+    case OBJ_ROSENBROCK: { CALL(OBJ_ROSENBROCK); } break; \
+    case OBJ_RASTRIGIN: { CALL(OBJ_RASTRIGIN); } break; \
+    case OBJ_ACKLEY: { CALL(OBJ_ACKLEY); } break;      \
+    case OBJ_ROSENBROCK_EX: { CALL(OBJ_ROSENBROCK_EX); } break; \
+    default: return cudaErrorInvalidValue;             \
+  }
+
+template <class T>
+cudaError_t de_launch_commit(const DEState &s, int mode, const LaunchGeom &g, cudaStream_t st) {
+  de_commit_kernel<T><<<g.reduce_blocks, kBlock, 0, st>>>(s, mode);
+  return cudaGetLastError();
+}
+template <class T>
+cudaError_t de_launch_export_best(const DEState &s, void *record, cudaStream_t st) {
+  de_export_best_kernel<T><<<1, kBlock, 0, st>>>(s, record);
+  return cudaGetLastError();
+}
+// sign +1: export the k best into rows/scores; sign -1: overwrite the k worst with rows/scores, then re-scan the best
+template <class T>
+cudaError_t de_launch_migrate(const DEState &s, int sign, unsigned long long k, void *rows, void *scores,
+                              const LaunchGeom &g, cudaStream_t st) {
+  for (u32 e = 0; e < k; e++) de_select_kernel<T><<<g.reduce_blocks, kBlock, 0, st>>>(s, sign, e, e == 0);
+  const unsigned int grid = clamp_grid(k, 4096);
+  if (sign > 0) de_gather_kernel<T><<<grid, kBlock, 0, st>>>(s, u32(k), static_cast<T *>(rows), static_cast<T *>(scores));
+  else {
+    de_scatter_kernel<T><<<grid, kBlock, 0, st>>>(s, u32(k), static_cast<const T *>(rows), static_cast<const T *>(scores));
+    de_commit_kernel<T><<<g.reduce_blocks, kBlock, 0, st>>>(s, 2);
+  }
+  return cudaGetLastError();
+}
+
+template <class T>
+cudaError_t de_launch_init(const DEState &s, const void *x0_dev, const LaunchGeom &g, cudaStream_t st) {
+  const u64 want = (s.P + kWarpsPerBlock - 1) / kWarpsPerBlock;
+#define NLS_CALL(O)                                                                                       \
+  de_init_kernel<T, O><<<clamp_grid(want, u64(g.sm_count) * blocks_per_sm(de_init_kernel<T, O>)), kBlock, 0, st>>>( \
+      s, static_cast<const T *>(x0_dev))
+  NLS_OBJ_SWITCH(s.objective, NLS_CALL)
+#undef NLS_CALL
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  return de_launch_commit<T>(s, 1, g, st);
+}
+
+// one generation: K2, K2r (cooperative), K3
+template <class T>
+cudaError_t de_launch_generation(const DEState &s, const LaunchGeom &g, cudaStream_t st) {
+  const u64 want = (s.P + kWarpsPerBlock - 1) / kWarpsPerBlock;
+  cudaError_t e = cudaSuccess;
+#define NLS_CALL(O)                                                                                                 \
+  de_generation_kernel<T, O><<<clamp_grid(want, u64(g.sm_count) * blocks_per_sm(de_generation_kernel<T, O>)), kBlock, \
+                               0, st>>>(s);                                                                         \
+  e = cudaGetLastError();                                                                                           \
+  if (e != cudaSuccess) return e;                                                                                   \
+  {                                                                                                                 \
+    DEState arg = s;                                                                                                \
+    void *args[] = {&arg};                                                                                          \
+    const unsigned int grid = clamp_grid((s.P + kBlock - 1) / kBlock,                                               \
+                                         u64(g.sm_count) * blocks_per_sm(de_repair_kernel<T, O>));                  \
+    e = cudaLaunchCooperativeKernel(reinterpret_cast<void *>(de_repair_kernel<T, O>), dim3(grid), dim3(kBlock),     \
+                                    args, 0, st);                                                                   \
+  }
+  NLS_OBJ_SWITCH(s.objective, NLS_CALL)
+#undef NLS_CALL
+  if (e != cudaSuccess) return e;
+  return de_launch_commit<T>(s, 0, g, st);
+}
+
+
+template <class T>
+cudaError_t de_launch_gather_rows(const DEState &s, unsigned long long first, unsigned long long count, void *out,
+                                  cudaStream_t st) {
+  de_gather_rows_kernel<T><<<clamp_grid(count, 1u << 16), kBlock, 0, st>>>(s, first, count, static_cast<T *>(out));
+  return cudaGetLastError();
+}
+
+#define NLS_DEFINE_DE_OPS(T, NAME)                                                                        \
+  const DEOps *NAME() {                                                                                   \
+    static const DEOps ops = {de_launch_init<T>, de_launch_generation<T>, de_launch_export_best<T>,       \
+                              de_launch_migrate<T>, de_launch_gather_rows<T>};                            \
+    return &ops;                                                                                          \
+  }
+
+}  // namespace nls

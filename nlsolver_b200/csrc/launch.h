@@ -1,0 +1,28 @@
+// launch.h — host-callable launchers implemented by the per-dtype translation units (de_f64.cu, de_f32.cu,
+// pso_f64.cu, pso_f32.cu); api.cu picks the table that matches cfg.dtype.
+#pragma once
+#include "state.h"
+namespace nls {
+
+struct DEOps {
+  cudaError_t (*init)(const DEState &s, const void *x0_dev, const LaunchGeom &g, cudaStream_t st);
+  cudaError_t (*generation)(const DEState &s, const LaunchGeom &g, cudaStream_t st);
+  cudaError_t (*export_best)(const DEState &s, void *record, cudaStream_t st);
+  cudaError_t (*migrate)(const DEState &s, int sign, unsigned long long k, void *rows, void *scores,
+                         const LaunchGeom &g, cudaStream_t st);
+  cudaError_t (*gather_rows)(const DEState &s, unsigned long long first, unsigned long long count, void *out,
+                             cudaStream_t st);
+};
+struct PSOOps {
+  cudaError_t (*init)(const PSOState &s, const LaunchGeom &g, cudaStream_t st);
+  cudaError_t (*move)(const PSOState &s, double inertia, const LaunchGeom &g, cudaStream_t st);
+  cudaError_t (*candidate)(const PSOState &s, void *record, const LaunchGeom &g, cudaStream_t st);
+  cudaError_t (*apply)(const PSOState &s, const void *records, unsigned long long n, unsigned long long record_bytes,
+                       int initial, cudaStream_t st);
+};
+const DEOps *de_ops_f64();
+const DEOps *de_ops_f32();
+const PSOOps *pso_ops_f64();
+const PSOOps *pso_ops_f32();
+
+}  // namespace nls

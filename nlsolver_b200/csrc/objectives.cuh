@@ -1,0 +1,81 @@
+// objectives.cuh — device objective functors: one warp evaluates one agent.
+//
+// N-D forms of test_functions.h:51-92 (Sphere :55, Rosenbrock :63-66, Rastrigin :74-77, Ackley :85-90) and of the
+// example.cpp:41-48 Rosenbrock.  Each lane owns the coordinates j with (j / V) % 32 == lane and adds its terms in
+// increasing j; the 32 lane sums are combined by an xor-butterfly.  That order is the canonical summation order the
+// CPU oracle mirrors (oracle/popsolve_oracle.cpp `Lanes`), and each form is arranged so that at d = 2 it performs the
+// reference's own operations in the reference's order.
+#pragma once
+#include "common.cuh"
+
+namespace nls {
+
+enum { OBJ_SPHERE = 0, OBJ_ROSENBROCK = 1, OBJ_RASTRIGIN = 2, OBJ_ACKLEY = 3, OBJ_ROSENBROCK_EX = 4, OBJ_COUNT = 5 };
+
+template <class T, int OBJ>
+struct Objective {
+  static constexpr int V = Vec<T>::V;
+  static constexpr bool kPairwise = (OBJ == OBJ_ROSENBROCK || OBJ == OBJ_ROSENBROCK_EX);
+  typedef Ar<T> A;
+  T a, b, carry;
+
+  __device__ __forceinline__ void begin(int lane, u64 d) {
+    // Rastrigin's leading `2*10` (10*d in N-D) seeds lane 0's accumulator so that d = 2 gives (20 + t0) + t1
+    a = (OBJ == OBJ_RASTRIGIN && lane == 0) ? A::mul(T(10), T(d)) : T(0);
+    b = T(0);
+    carry = T(0);
+  }
+
+  // x[q] is coordinate j0 + q of the agent; coordinates >= d are padding and contribute nothing.
+  // Must be called by all 32 lanes (the pairwise forms shuffle).
+  __device__ __forceinline__ void step(const T (&x)[V], u64 j0, u64 d, int lane) {
+    T left = T(0);
+    if (kPairwise) {
+      left = __shfl_up_sync(kFull, x[V - 1], 1);          // x[j0 - 1] lives in the previous lane ...
+      if (lane == 0) left = carry;                        // ... or in lane 31 of the previous step
+      carry = __shfl_sync(kFull, x[V - 1], 31);
+    }
+#pragma unroll
+    for (int q = 0; q < V; q++) {
+      const u64 j = j0 + q;
+      const T xj = x[q];
+      if (kPairwise) {
+        const T xl = (q == 0) ? left : x[q == 0 ? 0 : q - 1];
+        if (j >= 1 && j < d) {
+          if (OBJ == OBJ_ROSENBROCK) {                     // 100*pow(x0*x0 - x1, 2) + pow(x0 - 1, 2)
+            const T p = A::sub(A::mul(xl, xl), xj), r = A::sub(xl, T(1));
+            a = A::add(a, A::add(A::mul(T(100), A::mul(p, p)), A::mul(r, r)));
+          } else {                                         // t1*t1 + 100*t2*t2, t1 = 1 - x0, t2 = x1 - x0*x0
+            const T t1 = A::sub(T(1), xl), t2 = A::sub(xj, A::mul(xl, xl));
+            a = A::add(a, A::add(A::mul(t1, t1), A::mul(A::mul(T(100), t2), t2)));
+          }
+        }
+      } else if (j < d) {
+        if (OBJ == OBJ_SPHERE) {
+          a = A::add(a, A::mul(xj, xj));
+        } else if (OBJ == OBJ_RASTRIGIN) {                 // x*x - 10*cos(2*pi*x)
+          const T c = t_cos<T>(A::mul(T(2 * 3.14159265358979323846), xj));
+          a = A::add(a, A::sub(A::mul(xj, xj), A::mul(T(10), c)));
+        } else if (OBJ == OBJ_ACKLEY) {
+          a = A::add(a, A::mul(xj, xj));
+          b = A::add(b, t_cos<T>(A::mul(T(2 * 3.14159265358979323846), xj)));
+        }
+      }
+    }
+  }
+
+  // every lane returns the objective value
+  __device__ __forceinline__ T finish(u64 d) {
+    a = warp_butterfly_add<T>(a);
+    if (OBJ == OBJ_ACKLEY) {
+      b = warp_butterfly_add<T>(b);
+      const T inv_d = T(1.0) / T(d);
+      const T ra = A::mul(T(-20), t_exp<T>(A::mul(T(-0.2), t_sqrt<T>(A::mul(inv_d, a)))));
+      const T rb = -t_exp<T>(A::mul(inv_d, b));
+      return A::add(A::add(A::add(ra, rb), T(2.718281828459045235360287)), T(20));
+    }
+    return a;
+  }
+};
+
+}  // namespace nls

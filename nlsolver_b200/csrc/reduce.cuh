@@ -1,0 +1,102 @@
+// reduce.cuh — the population reduction both solvers end a generation with (K3 / K7 in SURVEY.md §2.1):
+// a min-loc (lower value wins, lower index on ties — the outcome of the reference's sequential strict-< scans,
+// nlsolver.h:2432-2437 and 2723-2729) fused with the count / mean / M2 moments that std_err (nlsolver.h:2037-2052)
+// needs, block level first, then grid level: the last block to finish (ticket) combines the per-block partials in
+// index order, so the result does not depend on scheduling.
+#pragma once
+#include <math_constants.h>
+
+#include "common.cuh"
+#include "state.h"
+
+namespace nls {
+
+constexpr int kBlock = 256;
+constexpr int kWarpsPerBlock = kBlock / 32;
+
+struct MinLoc { double v; u64 i; };
+__device__ __forceinline__ MinLoc minloc_merge(MinLoc a, MinLoc b) {
+  return (b.v < a.v || (b.v == a.v && b.i < a.i)) ? b : a;
+}
+// Chan / Golub / LeVeque pairwise combination of (n, mean, M2)
+__host__ __device__ __forceinline__ Moments moments_merge(Moments a, Moments b) {
+  if (b.n == 0.0) return a;
+  if (a.n == 0.0) return b;
+  Moments r;
+  r.n = a.n + b.n;
+  const double delta = b.mean - a.mean;
+  r.mean = a.mean + delta * (b.n / r.n);
+  r.m2 = a.m2 + b.m2 + delta * delta * (a.n * b.n / r.n);
+  return r;
+}
+
+// block-wide combine; the result is valid in thread 0
+__device__ __forceinline__ void block_reduce(MinLoc &ml, Moments &mo, MinLoc *sm_ml, Moments *sm_mo) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    MinLoc o; o.v = __shfl_down_sync(kFull, ml.v, off); o.i = __shfl_down_sync(kFull, ml.i, off);
+    Moments p; p.n = __shfl_down_sync(kFull, mo.n, off); p.mean = __shfl_down_sync(kFull, mo.mean, off);
+    p.m2 = __shfl_down_sync(kFull, mo.m2, off);
+    ml = minloc_merge(ml, o); mo = moments_merge(mo, p);
+  }
+  if (lane == 0) { sm_ml[w] = ml; sm_mo[w] = mo; }
+  __syncthreads();
+  if (threadIdx.x == 0)
+    for (int k = 1; k < kWarpsPerBlock; k++) { ml = minloc_merge(ml, sm_ml[k]); mo = moments_merge(mo, sm_mo[k]); }
+  __syncthreads();
+}
+
+// item(i, for_min, for_moments) yields the two values of element i; post() runs once per thread after its sweep.
+// Returns true in every thread of the last block to finish, with the grid-wide result in (ml, mo).
+template <class PerItem, class PostSweep>
+__device__ __forceinline__ bool population_reduce(u64 n, double *part_min, unsigned long long *part_idx,
+                                                  Moments *part_mom, unsigned int *ticket, PerItem item,
+                                                  PostSweep post, MinLoc &ml, Moments &mo) {
+  __shared__ MinLoc sm_ml[kWarpsPerBlock];
+  __shared__ Moments sm_mo[kWarpsPerBlock];
+  __shared__ bool is_last;
+  ml.v = CUDART_INF; ml.i = ~0ull;
+  mo.n = 0.0; mo.mean = 0.0; mo.m2 = 0.0;
+  for (u64 i = u64(blockIdx.x) * kBlock + threadIdx.x; i < n; i += u64(gridDim.x) * kBlock) {
+    double v, w;
+    item(i, v, w);
+    if (v < ml.v) { ml.v = v; ml.i = i; }
+    mo.n += 1.0;
+    const double delta = w - mo.mean;
+    mo.mean += delta / mo.n;
+    mo.m2 += delta * (w - mo.mean);
+  }
+  post();   // per-thread side results (ordered before the election by the barrier inside block_reduce)
+  block_reduce(ml, mo, sm_ml, sm_mo);
+  if (threadIdx.x == 0) {
+    part_min[blockIdx.x] = ml.v; part_idx[blockIdx.x] = ml.i; part_mom[blockIdx.x] = mo;
+    __threadfence();
+    is_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!is_last) return false;
+  __threadfence();
+  ml.v = CUDART_INF; ml.i = ~0ull; mo.n = 0.0; mo.mean = 0.0; mo.m2 = 0.0;
+  for (u32 b = threadIdx.x; b < gridDim.x; b += kBlock) {
+    MinLoc o; o.v = __ldcg(part_min + b); o.i = __ldcg(part_idx + b);
+    Moments p; p.n = __ldcg(&part_mom[b].n); p.mean = __ldcg(&part_mom[b].mean); p.m2 = __ldcg(&part_mom[b].m2);
+    ml = minloc_merge(ml, o); mo = moments_merge(mo, p);
+  }
+  block_reduce(ml, mo, sm_ml, sm_mo);
+  if (threadIdx.x == 0) { *ticket = 0; sm_ml[0] = ml; sm_mo[0] = mo; }
+  __syncthreads();
+  ml = sm_ml[0]; mo = sm_mo[0];
+  return true;
+}
+
+// Exchange record (island best / sharded-swarm candidate): 48-byte header followed by one row of dim elements.
+struct RecordHeader {
+  double value;                 // candidate objective value (already multiplied by -1 when maximising)
+  unsigned long long index;     // global agent / particle index
+  Moments moments;              // moments of the shard's stop statistic (scores / particle_best_values)
+  int valid, _pad;              // 0: this shard has no candidate (all values NaN / +inf)
+};
+static_assert(sizeof(RecordHeader) == 48, "record header layout is part of the C ABI");
+
+}  // namespace nls

@@ -1,0 +1,77 @@
+// state.h — device-resident solver state shared between the host side of the C ABI (api.cu) and the kernels.
+// Plain structs, passed to kernels by value; element buffers are void* and reinterpreted by the kernel's dtype.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace nls {
+
+// Loop counters and stop flags of DE::solve (nlsolver.h:2426-2447), kept on the device so that generations can be
+// enqueued back to back: every kernel of a generation begins by reading `stop` and returns if a rule has fired.
+struct Moments {  // count / mean / sum of squared deviations (Chan et al. pairwise combination)
+  double n, mean, m2;
+};
+
+struct DECtrl {
+  unsigned long long iter, best_id, vnc;
+  unsigned long long reruns, rounds, accepted;
+  double best_value, std_err;
+  int stop, stop_reason, error, _pad;
+  unsigned int ticket;          // last-block election of the reduction
+  unsigned int acc_partial;     // accepted trials of the generation being committed
+  unsigned int pending[2];      // repair: agents still waiting on a lower donor, by round parity
+  unsigned int list_count[2];   // repair: agents to re-evaluate in this round, by round parity
+  Moments score_moments;        // moments of the scores at the last scan (island exchange record)
+  double sel_value; unsigned long long sel_index;   // cursor of the top-k / worst-k selection (island migration)
+};
+
+struct DEState {
+  void *buf[2];          // two agent-major row buffers [P][stride]; where[i] says which one holds agent i's row
+  uint8_t *where;        // [P]
+  void *score;           // [P] scores[i]
+  void *tscore;          // [P] trial score of the generation in flight
+  uint8_t *acc;          // [P] trial accepted (in flight) / decisions of the last generation
+  uint16_t *fin;         // [P] repair round in which the agent's outcome became final (0 = pending)
+  uint4 *dec;            // [P] {ids[1], ids[2], ids[3], dim}
+  uint32_t *rej;         // [P] rejected index proposals (draw offset of the crossover draws = 4 + rej)
+  uint8_t *masks;        // [P*d] crossover mask of the last generation, or NULL
+  uint32_t *list;        // [P] repair work list
+  DECtrl *ctrl;
+  // reduction partials [n_partials]
+  double *part_min; unsigned long long *part_idx; Moments *part_mom;
+  unsigned long long P, d, stride;
+  unsigned long long seed, offset;
+  unsigned long long cr_le;    // crossover: mutate iff raw draw <= cr_le (integer form of `unit(raw) < CR`)
+  int cr_none;                 // ... unless no raw draw satisfies it
+  int strategy, objective;
+  double F, fm, eps;
+  unsigned long long max_iter, vnc_limit;
+};
+
+struct PSOCtrl {
+  unsigned long long iter, vnc, best_index;   // best_index: global index of the particle that last set the swarm best
+  double best_value, std_err;
+  int stop, stop_reason, best_valid, error;
+  unsigned int ticket, _pad;
+};
+
+struct PSOState {
+  void *pos, *vel;          // [P][stride]
+  void *pbest, *last;       // [P] particle_best_values, values of the evaluation in flight
+  void *sbest;              // [stride] swarm_best_position
+  void *lower, *upper;      // [d]
+  PSOCtrl *ctrl;
+  double *part_min; unsigned long long *part_idx; Moments *part_mom;
+  unsigned long long P, d, stride, P_global;
+  unsigned long long seed, offset;
+  int pso_type, objective, constrained, social_j;
+  double init_inertia, cog, soc, fm, eps;
+  unsigned long long max_iter, vnc_limit;
+};
+
+struct LaunchGeom {
+  int sm_count;
+  int reduce_blocks;   // grid of the reduction kernels (= number of partials)
+};
+
+}  // namespace nls

@@ -1,0 +1,332 @@
+"""Host-side mirror of the reference's solver interface for the DE / PSO population loop, over the C ABI.
+
+Names, argument order, defaults and behaviour follow nlsolver::DE (nlsolver.h:2379-2410), nlsolver::PSO
+(nlsolver.h:2498-2589) and nlsolver::solver_status (nlsolver.h:2054-2097): `minimize(x)` / `maximize(x)` overwrite
+`x` with the best point and return a `SolverStatus`.  The objective is one of the device functors (`Sphere`,
+`Rosenbrock`, `Rastrigin`, `Ackley`, `RosenbrockExample`); the random generator is any callable returning floats in
+[0, 1] — two draws are taken from it per solve to seed the device draw tape, so it advances deterministically.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib as L
+
+Sphere, Rosenbrock, Rastrigin, Ackley, RosenbrockExample = (L.SPHERE, L.ROSENBROCK, L.RASTRIGIN, L.ACKLEY,
+                                                             L.ROSENBROCK_EX)
+
+
+class RecombinationStrategy:  # nlsolver.h:2377
+    best, random = L.DE_BEST, L.DE_RANDOM
+
+
+class PSOType:  # nlsolver.h:2496
+    Vanilla, Accelerated = L.PSO_VANILLA, L.PSO_ACCELERATED
+
+
+def np_dtype(dtype):
+    return np.float64 if dtype == L.F64 else np.float32
+
+
+def nls_dtype(scalar_t):
+    return L.F64 if np.dtype(scalar_t) == np.float64 else L.F32
+
+
+def seed_from_generator(generator):
+    """Two draws -> 64-bit tape seed (the same rule as include/nlsolver_b200.hpp)."""
+    hi = min(int(float(generator()) * 4294967296.0), 0xFFFFFFFF)
+    lo = min(int(float(generator()) * 4294967296.0), 0xFFFFFFFF)
+    return (hi << 32) | lo
+
+
+class SolverStatus:
+    """solver_status<scalar_t> (nlsolver.h:2054-2097)."""
+
+    def __init__(self, f_value, iteration, function_calls_used, gradient_evals_used=0, hessian_evals_used=0):
+        self.f_value = f_value
+        self.iteration = iteration
+        self.function_calls_used = function_calls_used
+        self.gradient_evals_used = gradient_evals_used
+        self.hessian_evals_used = hessian_evals_used
+
+    def print(self):
+        print(f"Function calls used: {self.function_calls_used}")
+        print(f"Algorithm iterations used: {self.iteration}")
+        if self.gradient_evals_used > 0:
+            print(f"Gradient evaluations used: {self.gradient_evals_used}")
+        if self.hessian_evals_used > 0:
+            print(f"Hessian evaluations used: {self.hessian_evals_used}")
+        print(f"With final function value of {self.f_value:g}")
+
+    def get_summary(self):
+        return (self.function_calls_used, self.iteration, self.f_value, self.gradient_evals_used,
+                self.hessian_evals_used)
+
+    def add(self, other):
+        calls, it, f, g, h = other.get_summary()
+        self.function_calls_used += calls
+        self.iteration += it
+        self.f_value = f
+        self.gradient_evals_used += g
+        self.hessian_evals_used += h
+
+
+class Context:
+    """One per (process, GPU). `stream` is a raw cudaStream_t (int) or None for a library-owned stream."""
+
+    def __init__(self, device=0, stream=None):
+        self._h = C.c_void_p()
+        L.check(L.lib().nls_ctx_create(device, C.c_void_p(stream) if stream else None, C.byref(self._h)))
+
+    @property
+    def handle(self):
+        return self._h
+
+    @property
+    def sm_count(self):
+        return L.lib().nls_ctx_sm_count(self._h)
+
+    def close(self):
+        if self._h:
+            L.lib().nls_ctx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+_default_ctx = {}
+
+
+def default_context(device=0):
+    if device not in _default_ctx:
+        _default_ctx[device] = Context(device)
+    return _default_ctx[device]
+
+
+class DEPopulation:
+    """Stepwise handle (nls_de_*): the DE loop cut at generation boundaries, population resident in HBM."""
+
+    def __init__(self, ctx, cfg, x0):
+        self.ctx, self.cfg = ctx, cfg
+        self.dt = np_dtype(cfg.dtype)
+        x0 = np.ascontiguousarray(x0, dtype=self.dt)
+        assert x0.size == cfg.dim
+        self._h = C.c_void_p()
+        L.check(L.lib().nls_de_create(ctx.handle, C.byref(cfg), x0.ctypes.data, C.byref(self._h)))
+
+    def step(self, n=1):
+        L.check(L.lib().nls_de_step(self._h, n))
+
+    def sync(self):
+        st = L.Status()
+        L.check(L.lib().nls_de_sync(self._h, C.byref(st)))
+        return st.as_dict()
+
+    def best(self):
+        x = np.zeros(self.cfg.dim, self.dt)
+        L.check(L.lib().nls_de_read_best(self._h, x.ctypes.data))
+        return x
+
+    def population(self):
+        rows = np.zeros((self.cfg.pop_size, self.cfg.dim), self.dt)
+        L.check(L.lib().nls_de_read_population(self._h, rows.ctypes.data))
+        return rows
+
+    def scores(self):
+        s = np.zeros(self.cfg.pop_size, self.dt)
+        L.check(L.lib().nls_de_read_scores(self._h, s.ctypes.data))
+        return s
+
+    def decisions(self, masks=False):
+        P, d = self.cfg.pop_size, self.cfg.dim
+        a = {"donors": np.zeros((P, 3), np.uint32), "dim_idx": np.zeros(P, np.uint32),
+             "rejects": np.zeros(P, np.uint32), "accepted": np.zeros(P, np.uint8),
+             "trial_scores": np.zeros(P, self.dt)}
+        m = np.zeros((P, d), np.uint8) if masks else None
+        L.check(L.lib().nls_de_read_decisions(self._h, a["donors"].ctypes.data, a["dim_idx"].ctypes.data,
+                                              a["rejects"].ctypes.data, a["accepted"].ctypes.data,
+                                              a["trial_scores"].ctypes.data, m.ctypes.data if masks else None))
+        if masks:
+            a["masks"] = m
+        return a
+
+    def export_best(self, record_ptr):
+        L.check(L.lib().nls_de_export_best(self._h, C.c_void_p(record_ptr)))
+
+    def export_top(self, k, rows_ptr, scores_ptr):
+        L.check(L.lib().nls_de_export_top(self._h, k, C.c_void_p(rows_ptr), C.c_void_p(scores_ptr)))
+
+    def import_migrants(self, k, rows_ptr, scores_ptr):
+        L.check(L.lib().nls_de_import_migrants(self._h, k, C.c_void_p(rows_ptr), C.c_void_p(scores_ptr)))
+
+    def close(self):
+        if self._h:
+            L.lib().nls_de_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class PSOSwarm:
+    """Stepwise handle (nls_pso_*)."""
+
+    def __init__(self, ctx, cfg, lower, upper):
+        self.ctx, self.cfg = ctx, cfg
+        self.dt = np_dtype(cfg.dtype)
+        lower = np.ascontiguousarray(lower, dtype=self.dt)
+        upper = np.ascontiguousarray(upper, dtype=self.dt)
+        assert lower.size == cfg.dim and upper.size == cfg.dim
+        self._h = C.c_void_p()
+        L.check(L.lib().nls_pso_create(ctx.handle, C.byref(cfg), lower.ctypes.data, upper.ctypes.data,
+                                       C.byref(self._h)))
+
+    def step(self, n=1):
+        L.check(L.lib().nls_pso_step(self._h, n))
+
+    def step_local(self, record_ptr=None):
+        L.check(L.lib().nls_pso_step_local(self._h, C.c_void_p(record_ptr) if record_ptr else None))
+
+    def export_candidate(self, record_ptr):
+        L.check(L.lib().nls_pso_export_candidate(self._h, C.c_void_p(record_ptr)))
+
+    def apply_candidates(self, records_ptr, n):
+        L.check(L.lib().nls_pso_apply_candidates(self._h, C.c_void_p(records_ptr), n))
+
+    def sync(self):
+        st = L.Status()
+        L.check(L.lib().nls_pso_sync(self._h, C.byref(st)))
+        return st.as_dict()
+
+    def _read(self, fn, shape):
+        a = np.zeros(shape, self.dt)
+        L.check(fn(self._h, a.ctypes.data))
+        return a
+
+    def best(self):
+        return self._read(L.lib().nls_pso_read_best, self.cfg.dim)
+
+    def positions(self):
+        return self._read(L.lib().nls_pso_read_positions, (self.cfg.n_particles, self.cfg.dim))
+
+    def velocities(self):
+        return self._read(L.lib().nls_pso_read_velocities, (self.cfg.n_particles, self.cfg.dim))
+
+    def pbest_values(self):
+        return self._read(L.lib().nls_pso_read_pbest_values, self.cfg.n_particles)
+
+    def last_values(self):
+        return self._read(L.lib().nls_pso_read_last_values, self.cfg.n_particles)
+
+    def close(self):
+        if self._h:
+            L.lib().nls_pso_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def de_cfg(dtype=L.F64, objective=L.SPHERE, strategy=L.DE_RANDOM, minimize=True, pop_size=50, dim=2,
+           crossover_prob=0.9, differential_weight=0.8, eps=10e-4, max_iter=1000, best_val_no_change=50, seed=0,
+           agent_offset=0, flags=0):
+    return L.DECfg(dtype, objective, strategy, int(minimize), pop_size, dim, crossover_prob, differential_weight, eps,
+                   max_iter, best_val_no_change, seed, agent_offset, flags, 0)
+
+
+def pso_cfg(dtype=L.F64, objective=L.SPHERE, pso_type=L.PSO_VANILLA, minimize=True, n_particles=10, dim=2,
+            inertia=0.8, cognitive_coef=1.8, social_coef=1.8, eps=10e-4, max_iter=5000, best_val_no_change=50,
+            constrained=False, flags=0, seed=0, particle_offset=0, n_particles_global=0):
+    return L.PSOCfg(dtype, objective, pso_type, int(minimize), n_particles, dim, inertia, cognitive_coef, social_coef,
+                    eps, max_iter, best_val_no_change, int(constrained), flags, seed, particle_offset,
+                    n_particles_global)
+
+
+class DE:
+    """nlsolver::DE<Callable, RNG, scalar_t, RecombinationType> (nlsolver.h:2379-2410)."""
+
+    def __init__(self, f, generator, crossover_prob=0.9, differential_weight=0.8, eps=10e-4, pop_size=50,
+                 max_iter=1000, best_val_no_change=50, scalar_t=np.float64,
+                 recombination=RecombinationStrategy.random, ctx=None):
+        self.f, self.generator = f, generator
+        self.crossover_prob, self.differential_weight, self.eps = crossover_prob, differential_weight, eps
+        self.pop_size, self.max_iter, self.best_val_no_change = pop_size, max_iter, best_val_no_change
+        self.scalar_t, self.recombination = scalar_t, recombination
+        self.ctx = ctx
+
+    def _solve(self, x, minimize):
+        ctx = self.ctx or default_context()
+        dt = np.dtype(self.scalar_t)
+        cfg = de_cfg(nls_dtype(dt), self.f, self.recombination, minimize, self.pop_size, len(x), self.crossover_prob,
+                     self.differential_weight, self.eps, self.max_iter, self.best_val_no_change,
+                     seed_from_generator(self.generator))
+        x0 = np.ascontiguousarray(x, dtype=dt)
+        out = np.zeros(len(x), dt)
+        st = L.Status()
+        L.check(L.lib().nls_de_solve(ctx.handle, C.byref(cfg), x0.ctypes.data, out.ctypes.data, C.byref(st)))
+        x[:] = out.tolist() if isinstance(x, list) else out
+        return SolverStatus(dt.type(st.f_value), st.iterations, st.function_calls)
+
+    def minimize(self, x):
+        return self._solve(x, True)
+
+    def maximize(self, x):
+        return self._solve(x, False)
+
+
+class PSO:
+    """nlsolver::PSO<Callable, RNG, scalar_t, Type> (nlsolver.h:2498-2589)."""
+
+    def __init__(self, f, generator, inertia=0.8, cognitive_coef=1.8, social_coef=1.8, n_particles=10, max_iter=5000,
+                 best_val_no_change=50, eps=10e-4, scalar_t=np.float64, pso_type=PSOType.Vanilla, ctx=None):
+        self.f, self.generator = f, generator
+        self.inertia, self.cognitive_coef, self.social_coef = inertia, cognitive_coef, social_coef
+        self.n_particles, self.max_iter, self.best_val_no_change, self.eps = (n_particles, max_iter,
+                                                                            best_val_no_change, eps)
+        self.scalar_t, self.pso_type = scalar_t, pso_type
+        self.ctx = ctx
+
+    def _solve(self, x, lower, upper, minimize):
+        ctx = self.ctx or default_context()
+        dt = np.dtype(self.scalar_t)
+        d = len(x)
+        constrained = lower is not None
+        if not constrained:   # nlsolver.h:2553-2563: lower = -|x|, upper = |x|, no clamping
+            upper = np.abs(np.asarray(x, dtype=dt))
+            lower = -upper
+        flags = 0
+        if self.pso_type == PSOType.Vanilla and self.n_particles > d:
+            flags |= L.FLAG_SOCIAL_INDEX_J   # the reference reads out of bounds here (nlsolver.h:2674)
+        cfg = pso_cfg(nls_dtype(dt), self.f, self.pso_type, minimize, self.n_particles, d, self.inertia,
+                      self.cognitive_coef, self.social_coef, self.eps, self.max_iter, self.best_val_no_change,
+                      constrained, flags, seed_from_generator(self.generator))
+        lo = np.ascontiguousarray(lower, dtype=dt)
+        up = np.ascontiguousarray(upper, dtype=dt)
+        out = np.zeros(d, dt)
+        st = L.Status()
+        L.check(L.lib().nls_pso_solve(ctx.handle, C.byref(cfg), lo.ctypes.data, up.ctypes.data, out.ctypes.data,
+                                      C.byref(st)))
+        if st.best_valid:
+            x[:] = out.tolist() if isinstance(x, list) else out
+        elif isinstance(x, list):
+            del x[:]          # the reference assigns an empty swarm_best_position (nlsolver.h:2601)
+        return SolverStatus(dt.type(st.f_value), st.iterations, st.function_calls)
+
+    def minimize(self, x, lower=None, upper=None):
+        return self._solve(x, lower, upper, True)
+
+    def maximize(self, x, lower=None, upper=None):
+        return self._solve(x, lower, upper, False)
+
+
+DESolver, PSOSolver = DE, PSO   # the names README.md:80,99 uses

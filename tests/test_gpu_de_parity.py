@@ -1,0 +1,182 @@
+"""DE on the B200 (through the C ABI) against the oracle on the same draw tape, generation by generation.
+
+Bit-exact: donor ids, dim, rejected proposals, crossover masks, accept flags, iteration / call counters, best index.
+Values: bit-exact for Sphere / Rosenbrock; <= 1e-12 relative (fp64) where libm is involved."""
+import os
+
+import numpy as np
+import pytest
+
+import nlsolver_b200 as nb
+from oracle import binding as B
+from tests.golden_util import golden_files, load_de
+from tests.gpu_util import bits, gpu_de, oracle_de, rel_close, tolerance
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = nb.Context(0)
+    yield c
+    c.close()
+
+
+def compare_generation(pop, st, so, ao, tol, g, check_decisions):
+    assert st["iterations"] == so["iterations"] == g
+    assert st["function_calls"] == so["function_calls"]
+    if check_decisions:
+        dec = pop.decisions(masks=True)
+        for k in ("donors", "dim_idx", "rejects", "masks"):
+            assert np.array_equal(dec[k], ao[k]), (g, k)
+        flips = np.nonzero(dec["accepted"] != ao["accepted"])[0]
+        assert flips.size == 0, (g, "accept flags differ at", flips[:10], dec["trial_scores"][flips[:10]],
+                                 ao["trial_scores"][flips[:10]])
+        if tol == 0.0:
+            assert np.array_equal(bits(dec["trial_scores"]), bits(ao["trial_scores"])), (g, "trial_scores")
+        else:
+            assert rel_close(dec["trial_scores"], ao["trial_scores"], tol), (g, "trial_scores")
+    rows, scores = pop.population(), pop.scores()
+    if tol == 0.0:
+        assert np.array_equal(bits(rows), bits(ao["rows"])), (g, "rows")
+        assert np.array_equal(bits(scores), bits(ao["scores"])), (g, "scores")
+        assert st["f_value"] == so["f_value"]
+    else:
+        assert rel_close(rows, ao["rows"], tol), (g, "rows")
+        assert rel_close(scores, ao["scores"], tol), (g, "scores")
+        assert rel_close(st["f_value"], so["f_value"], tol)
+    assert st["best_index"] == so["best_index"], g
+    assert np.array_equal(bits(pop.best()), bits(rows[so["best_index"]]))
+
+
+CASES = [
+    # dtype, objective, strategy, minimize, P, d, G, scale
+    (B.F64, B.SPHERE, B.DE_RANDOM, True, 50, 2, 12, 5.0),
+    (B.F64, B.SPHERE, B.DE_RANDOM, True, 1000, 16, 8, 10.24),
+    (B.F64, B.ROSENBROCK, B.DE_BEST, True, 64, 8, 30, 4.096),
+    (B.F64, B.ROSENBROCK, B.DE_BEST, True, 3000, 130, 5, 4.096),
+    (B.F64, B.ROSENBROCK_EX, B.DE_RANDOM, False, 40, 5, 6, 3.0),
+    (B.F64, B.RASTRIGIN, B.DE_RANDOM, True, 257, 33, 6, 10.24),
+    (B.F64, B.RASTRIGIN, B.DE_RANDOM, True, 512, 1000, 3, 10.24),     # the north-star row shape, small population
+    (B.F64, B.ACKLEY, B.DE_BEST, True, 128, 65, 6, 65.536),
+    (B.F64, B.RASTRIGIN, B.DE_RANDOM, True, 4, 1, 10, 10.24),         # smallest legal population, d = 1
+    (B.F64, B.SPHERE, B.DE_BEST, True, 5, 3, 10, 1.0),
+    (B.F64, B.SPHERE, B.DE_RANDOM, True, 20000, 8, 4, 10.24),         # deep "donor r < i" DAG, many repair rounds
+    (B.F64, B.SPHERE, B.DE_RANDOM, True, 333, 64, 5, 10.24),
+    (B.F32, B.SPHERE, B.DE_RANDOM, True, 300, 17, 6, 10.24),
+    (B.F32, B.ROSENBROCK, B.DE_BEST, True, 100, 12, 6, 4.096),
+    (B.F32, B.RASTRIGIN, B.DE_RANDOM, True, 64, 9, 5, 10.24),
+    (B.F32, B.SPHERE, B.DE_RANDOM, True, 2048, 64, 4, 10.24),
+]
+
+
+@pytest.mark.parametrize("dtype,obj,strategy,minimize,P,d,G,scale", CASES)
+def test_de_matches_oracle_every_generation(ctx, oracle_lib, dtype, obj, strategy, minimize, P, d, G, scale):
+    seed = 0xABCDEF0123456789 ^ (P * 1000003 + d)
+    x0 = np.full(d, scale)
+    tol = tolerance(dtype, obj)
+    pop = gpu_de(ctx, dtype, obj, strategy, minimize, P, d, seed, x0)
+    for g in range(G + 1):
+        if g:
+            pop.step(1)
+        st = pop.sync()
+        so, ao = oracle_de(oracle_lib, dtype, obj, strategy, minimize, P, d, g, seed, x0)
+        compare_generation(pop, st, so, ao, tol, g, check_decisions=g > 0)
+    assert st["repair_rounds"] >= G
+    pop.close()
+
+
+@pytest.mark.parametrize("path", golden_files("de_"), ids=os.path.basename)
+def test_de_matches_reference_fixture(ctx, path):
+    """Against what the UNMODIFIED reference produced (tests/golden, written by tests/golden/make_golden.py)."""
+    cfg, x0, z = load_de(path)
+    tol = tolerance(cfg.dtype, cfg.objective)
+    pop = gpu_de(ctx, cfg.dtype, cfg.objective, cfg.strategy, bool(cfg.minimize), cfg.pop_size, cfg.dim, cfg.seed, x0,
+                 max_iter=cfg.max_iter)
+    pop.step(cfg.max_iter)
+    st = pop.sync()
+    assert st["stopped"] and st["stop_reason"] == 1
+    assert st["iterations"] == z["iterations"].item() and st["function_calls"] == z["function_calls"].item()
+    assert st["best_index"] == z["best_index"].item()
+    dec = pop.decisions(masks=True)
+    for k in ("donors", "dim_idx", "rejects", "masks", "accepted"):
+        assert np.array_equal(dec[k], z[k]), k
+    if tol == 0.0:
+        assert np.array_equal(bits(pop.population()), bits(z["rows"]))
+        assert np.array_equal(bits(pop.best()), bits(z["x_best"]))
+        assert st["f_value"] == z["f_value"].item()
+    else:
+        assert rel_close(pop.population(), z["rows"], tol) and rel_close(st["f_value"], z["f_value"].item(), tol)
+    pop.close()
+
+
+def test_de_batched_steps_equal_single_steps(ctx, oracle_lib):
+    P, d, G, seed = 777, 24, 9, 5
+    x0 = np.full(d, 4.096)
+    a = gpu_de(ctx, B.F64, B.ROSENBROCK, B.DE_RANDOM, True, P, d, seed, x0, masks=False)
+    a.step(G)
+    so, ao = oracle_de(oracle_lib, B.F64, B.ROSENBROCK, B.DE_RANDOM, True, P, d, G, seed, x0, masks=False)
+    st = a.sync()
+    assert st["iterations"] == G and np.array_equal(bits(a.population()), bits(ao["rows"]))
+    a.close()
+
+
+def test_de_stop_rules_on_device(ctx, oracle_lib):
+    """Default stop rules (eps = 10e-4, best_val_no_change = 50) fire on the device in the reference's iteration."""
+    for obj, strategy, P, d, scale in ((B.ROSENBROCK, B.DE_BEST, 64, 8, 4.096), (B.SPHERE, B.DE_RANDOM, 50, 2, 1.0)):
+        cfg = B.de_cfg(objective=obj, strategy=strategy, pop_size=P, dim=d, seed=99)
+        so, ao = B.de_run(oracle_lib, cfg, np.full(d, scale))
+        x = np.full(d, scale)
+        ncfg = nb.de_cfg(objective=obj, strategy=strategy, pop_size=P, dim=d, seed=99)
+        pop = nb.DEPopulation(ctx, ncfg, x)
+        pop.step(so["iterations"] + 20)      # generations past the stop are no-ops
+        st = pop.sync()
+        assert st["stopped"] and st["stop_reason"] == so["stop_reason"]
+        assert st["iterations"] == so["iterations"] and st["function_calls"] == so["function_calls"]
+        assert st["f_value"] == so["f_value"]
+        assert np.array_equal(bits(pop.best()), bits(ao["x_best"]))
+        pop.close()
+
+
+def test_de_solve_one_shot_matches_oracle(ctx, oracle_lib):
+    import ctypes as C
+    from nlsolver_b200 import _lib as L
+    d = 6
+    cfg = nb.de_cfg(objective=nb.ROSENBROCK, strategy=nb.DE_BEST, pop_size=80, dim=d, seed=1234)
+    x0, out, st = np.full(d, 4.096), np.zeros(d), L.Status()
+    L.check(L.lib().nls_de_solve(ctx.handle, C.byref(cfg), x0.ctypes.data, out.ctypes.data, C.byref(st)))
+    so, ao = B.de_run(oracle_lib, B.de_cfg(objective=B.ROSENBROCK, strategy=B.DE_BEST, pop_size=80, dim=d, seed=1234), x0)
+    assert (st.iterations, st.function_calls, st.f_value) == (so["iterations"], so["function_calls"], so["f_value"])
+    assert np.array_equal(bits(out), bits(ao["x_best"]))
+
+
+def test_de_rejects_bad_arguments(ctx):
+    with pytest.raises(nb.NlsError):
+        nb.DEPopulation(ctx, nb.de_cfg(pop_size=3, dim=2), np.ones(2))      # the reference would loop forever
+    with pytest.raises(nb.NlsError):
+        nb.DEPopulation(ctx, nb.de_cfg(pop_size=10, dim=2, objective=17), np.ones(2))
+
+
+def test_de_large_population_properties(ctx):
+    """Size-independent properties at a population the oracle would take minutes for: greedy selection never
+    worsens a score, the reported best is the population minimum with the lowest index, counters add up."""
+    P, d = 1 << 17, 64
+    pop = gpu_de(ctx, B.F64, B.SPHERE, B.DE_RANDOM, True, P, d, 7, np.full(d, 10.24), masks=False)
+    prev = pop.scores()
+    for g in range(1, 4):
+        pop.step(1)
+        st = pop.sync()
+        cur = pop.scores()
+        assert np.all(cur <= prev) and st["iterations"] == g and st["function_calls"] == P * (g + 1)
+        dec = pop.decisions()
+        assert np.array_equal(dec["accepted"].astype(bool), cur < prev)
+        assert np.array_equal(np.where(dec["accepted"] == 1, dec["trial_scores"], prev), cur)
+        don = dec["donors"].astype(np.int64)
+        idx = np.arange(P)
+        assert np.all(don < P) and np.all(don != idx[:, None])
+        assert np.all(don[:, 0] != don[:, 1]) and np.all(don[:, 0] != don[:, 2]) and np.all(don[:, 1] != don[:, 2])
+        assert st["best_index"] == int(np.argmin(cur)) and st["f_value"] == cur.min()
+        rows = pop.population()
+        assert np.allclose((rows * rows).sum(1), cur, rtol=1e-12)
+        prev = cur
+    pop.close()

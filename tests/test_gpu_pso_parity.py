@@ -1,0 +1,156 @@
+"""PSO on the B200 (through the C ABI) against the oracle on the same draw tape, generation by generation."""
+import os
+
+import numpy as np
+import pytest
+
+import nlsolver_b200 as nb
+from oracle import binding as B
+from tests.golden_util import golden_files, load_pso
+from tests.gpu_util import bits, rel_close
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = nb.Context(0)
+    yield c
+    c.close()
+
+
+def pso_tol(dtype, obj, ptype):
+    # the accelerated move calls log / sqrt / cos per coordinate; vanilla with Sphere / Rosenbrock is + - * only
+    exact = ptype == B.PSO_VANILLA and obj in (B.SPHERE, B.ROSENBROCK, B.ROSENBROCK_EX)
+    if exact:
+        return 0.0
+    return 1e-12 if dtype == B.F64 else 2e-5
+
+
+CASES = [
+    # dtype, objective, type, minimize, constrained, P, d, G, bound
+    (B.F64, B.SPHERE, B.PSO_VANILLA, True, False, 8, 8, 25, 10.24),
+    (B.F64, B.ROSENBROCK, B.PSO_VANILLA, True, True, 6, 8, 25, 4.096),
+    (B.F64, B.SPHERE, B.PSO_VANILLA, True, False, 100, 130, 10, 5.12),
+    (B.F64, B.RASTRIGIN, B.PSO_VANILLA, True, False, 30, 33, 10, 5.12),
+    (B.F64, B.SPHERE, B.PSO_ACCELERATED, True, False, 40, 8, 20, 10.24),
+    (B.F64, B.ACKLEY, B.PSO_ACCELERATED, True, False, 1000, 32, 8, 32.768),
+    (B.F64, B.ACKLEY, B.PSO_ACCELERATED, True, False, 300, 256, 5, 32.768),     # config-3 row shape
+    (B.F64, B.RASTRIGIN, B.PSO_ACCELERATED, True, True, 40, 8, 30, 5.12),
+    (B.F64, B.ROSENBROCK_EX, B.PSO_ACCELERATED, False, True, 33, 5, 10, 2.0),
+    (B.F32, B.SPHERE, B.PSO_ACCELERATED, True, False, 100, 16, 8, 10.24),
+    (B.F32, B.SPHERE, B.PSO_VANILLA, True, True, 12, 16, 8, 10.24),
+]
+
+
+@pytest.mark.parametrize("dtype,obj,ptype,minimize,constrained,P,d,G,bound", CASES)
+def test_pso_matches_oracle_every_generation(ctx, oracle_lib, dtype, obj, ptype, minimize, constrained, P, d, G, bound):
+    seed = 42 + d * 7 + P
+    up = np.full(d, bound)
+    tol = pso_tol(dtype, obj, ptype)
+    cfg = nb.pso_cfg(dtype=dtype, objective=obj, pso_type=ptype, minimize=minimize, n_particles=P, dim=d, eps=0.0,
+                     max_iter=1 << 40, best_val_no_change=1 << 40, constrained=constrained, seed=seed)
+    swarm = nb.PSOSwarm(ctx, cfg, -up, up)
+    for g in range(G + 1):
+        if g:
+            swarm.step(1)
+        st = swarm.sync()
+        ocfg = B.pso_cfg(dtype=dtype, objective=obj, pso_type=ptype, minimize=minimize, n_particles=P, dim=d, eps=0.0,
+                         max_iter=g, best_val_no_change=1 << 40, constrained=constrained, seed=seed)
+        so, ao = B.pso_run(oracle_lib, ocfg, -up, up)
+        assert st["iterations"] == so["iterations"] == g and st["function_calls"] == so["function_calls"]
+        assert st["best_valid"] == so["best_valid"] and st["val_no_change"] == so["val_no_change"], g
+        got = {"positions": swarm.positions(), "pbest_values": swarm.pbest_values(), "last_values": swarm.last_values()}
+        if ptype == B.PSO_VANILLA:
+            got["velocities"] = swarm.velocities()
+        for k, v in got.items():
+            if tol == 0.0:
+                assert np.array_equal(bits(v), bits(ao[k])), (g, k)
+            else:
+                assert rel_close(v, ao[k], tol), (g, k, np.max(np.abs(v - ao[k])))
+        if so["best_valid"]:
+            assert st["best_index"] == so["best_index"], g
+            assert (np.array_equal(bits(swarm.best()), bits(ao["x_best"])) if tol == 0.0
+                    else rel_close(swarm.best(), ao["x_best"], tol))
+            assert st["f_value"] == so["f_value"] if tol == 0.0 else rel_close(st["f_value"], so["f_value"], tol)
+    swarm.close()
+
+
+@pytest.mark.parametrize("path", golden_files("pso_"), ids=os.path.basename)
+def test_pso_matches_reference_fixture(ctx, path):
+    cfg, up, z = load_pso(path)
+    tol = pso_tol(cfg.dtype, cfg.objective, cfg.pso_type)
+    ncfg = nb.pso_cfg(dtype=cfg.dtype, objective=cfg.objective, pso_type=cfg.pso_type, minimize=bool(cfg.minimize),
+                      n_particles=cfg.n_particles, dim=cfg.dim, eps=0.0, max_iter=cfg.max_iter,
+                      best_val_no_change=1 << 40, constrained=bool(cfg.constrained), seed=cfg.seed)
+    swarm = nb.PSOSwarm(ctx, ncfg, -up, up)
+    swarm.step(cfg.max_iter)
+    st = swarm.sync()
+    assert st["stopped"] and st["iterations"] == z["iterations"].item()
+    assert st["function_calls"] == z["function_calls"].item()
+    for k, v in (("positions", swarm.positions()), ("pbest_values", swarm.pbest_values()), ("x_best", swarm.best())):
+        assert (np.array_equal(bits(v), bits(z[k])) if tol == 0.0 else rel_close(v, z[k], tol)), k
+    assert st["f_value"] == z["f_value"].item() if tol == 0.0 else rel_close(st["f_value"], z["f_value"].item(), tol)
+    swarm.close()
+
+
+def test_pso_stop_rules_on_device(ctx, oracle_lib):
+    for ptype, P, d in ((B.PSO_VANILLA, 8, 8),):
+        up = np.full(d, 3.0)
+        so, ao = B.pso_run(oracle_lib, B.pso_cfg(objective=B.SPHERE, pso_type=ptype, n_particles=P, dim=d, seed=5), -up, up)
+        swarm = nb.PSOSwarm(ctx, nb.pso_cfg(objective=nb.SPHERE, pso_type=ptype, n_particles=P, dim=d, seed=5), -up, up)
+        swarm.step(so["iterations"] + 10)
+        st = swarm.sync()
+        assert st["stopped"] and st["stop_reason"] == so["stop_reason"] and st["iterations"] == so["iterations"]
+        assert st["f_value"] == so["f_value"] and np.array_equal(bits(swarm.best()), bits(ao["x_best"]))
+        swarm.close()
+
+
+def test_pso_vanilla_more_particles_than_dims_needs_corrected_flag(ctx, oracle_lib):
+    up = np.full(4, 2.0)
+    with pytest.raises(nb.NlsError):    # the reference reads out of bounds here (nlsolver.h:2674)
+        nb.PSOSwarm(ctx, nb.pso_cfg(n_particles=10, dim=4), -up, up)
+    cfg = nb.pso_cfg(n_particles=10, dim=4, flags=nb.FLAG_SOCIAL_INDEX_J, eps=0.0, max_iter=1 << 40,
+                     best_val_no_change=1 << 40, seed=3)
+    swarm = nb.PSOSwarm(ctx, cfg, -up, up)
+    swarm.step(15)
+    st = swarm.sync()
+    so, ao = B.pso_run(oracle_lib, B.pso_cfg(n_particles=10, dim=4, social_index_j=True, eps=0.0, max_iter=15,
+                                             best_val_no_change=1 << 40, seed=3), -up, up)
+    assert st["iterations"] == 15 and np.array_equal(bits(swarm.positions()), bits(ao["positions"]))
+    swarm.close()
+
+
+def test_sharded_swarm_equals_single_swarm(ctx):
+    """Two shards on one GPU exchanging candidate records (what the multi-GPU path all-gathers) == one swarm."""
+    import torch
+    P, d, G = 600, 48, 6
+    up = np.full(d, 32.768)
+    kw = dict(objective=nb.ACKLEY, pso_type=nb.PSO_ACCELERATED, dim=d, eps=0.0, max_iter=1 << 40,
+              best_val_no_change=1 << 40, seed=77)
+    whole = nb.PSOSwarm(ctx, nb.pso_cfg(n_particles=P, **kw), -up, up)
+    cut = 250
+    shards = [nb.PSOSwarm(ctx, nb.pso_cfg(n_particles=cut, particle_offset=0, n_particles_global=P, **kw), -up, up),
+              nb.PSOSwarm(ctx, nb.pso_cfg(n_particles=P - cut, particle_offset=cut, n_particles_global=P, **kw), -up, up)]
+    rb = nb.lib().nls_record_bytes(nb.F64, d)
+    rec = torch.zeros(2 * rb, dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()     # torch filled `rec` on its own stream; the context stream is independent of it
+    for k, s in enumerate(shards):
+        s.export_candidate(rec.data_ptr() + k * rb)
+    for s in shards:
+        s.apply_candidates(rec.data_ptr(), 2)
+    for g in range(G):
+        whole.step(1)
+        for k, s in enumerate(shards):
+            s.step_local(rec.data_ptr() + k * rb)
+        for s in shards:
+            s.sync()
+        for s in shards:
+            s.apply_candidates(rec.data_ptr(), 2)
+    sw = whole.sync()
+    for s in shards:
+        ss = s.sync()
+        for k in ("f_value", "iterations", "function_calls", "best_index", "val_no_change", "std_err"):
+            assert ss[k] == sw[k], k
+        assert np.array_equal(bits(s.best()), bits(whole.best()))
+    assert np.array_equal(bits(np.concatenate([s.positions() for s in shards])), bits(whole.positions()))
