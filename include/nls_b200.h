@@ -137,6 +137,11 @@ NLS_API int nls_de_read_scores(nls_de *de, void *scores_host);      /* scores, p
 NLS_API int nls_de_read_decisions(nls_de *de, uint32_t *donors, uint32_t *dim_idx, uint32_t *rejects, uint8_t *accepted,
                           void *trial_scores, uint8_t *masks);
 NLS_API int nls_de_destroy(nls_de *de);
+/* measurement hook: when enabled, CUDA events bracket the three kernels of every generation enqueued afterwards;
+ * nls_de_kernel_times waits for them and returns the accumulated device milliseconds and the generation count
+ * since the last call (ms[0] K2 generation pass, ms[1] K2r repair, ms[2] K3 commit + reduce). */
+NLS_API int nls_de_enable_kernel_timing(nls_de *de, int enable);
+NLS_API int nls_de_kernel_times(nls_de *de, double ms[3], uint64_t *generations);
 
 /* island-model hooks (device pointers, enqueued on the context stream; no reference counterpart) */
 /* record = [f_value (double), best global id (uint64), row (dim elements of dtype, padded to 8 bytes)] */

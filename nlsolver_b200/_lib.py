@@ -6,7 +6,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libnls_b200.so")
+# NLS_B200_LIB selects an alternative build of the same library (kernel tuning experiments, tools/build_variants.sh)
+LIB_PATH = os.environ.get("NLS_B200_LIB") or os.path.join(HERE, "libnls_b200.so")
 
 F32, F64 = 0, 1
 SPHERE, ROSENBROCK, RASTRIGIN, ACKLEY, ROSENBROCK_EX = range(5)
@@ -69,6 +70,8 @@ SYMBOLS = {
     "nls_de_read_scores": (C.c_int, [P, P]),
     "nls_de_read_decisions": (C.c_int, [P, P, P, P, P, P, P]),
     "nls_de_destroy": (C.c_int, [P]),
+    "nls_de_enable_kernel_timing": (C.c_int, [P, C.c_int]),
+    "nls_de_kernel_times": (C.c_int, [P, C.POINTER(f64), C.POINTER(u64)]),
     "nls_record_bytes": (u64, [i32, u64]),
     "nls_de_export_best": (C.c_int, [P, P]),
     "nls_de_export_top": (C.c_int, [P, u64, P, P]),

@@ -104,6 +104,10 @@ struct nls_de {
   void *staging;      // read-back staging
   size_t staging_bytes;
   size_t elem;
+  bool timing;                          // measurement hook (nls_de_enable_kernel_timing)
+  std::vector<cudaEvent_t> events;      // 4 per timed generation
+  double timed_ms[3];
+  u64 timed_generations;
 };
 
 struct nls_pso {
@@ -181,6 +185,7 @@ int nls_de_destroy(nls_de *de) {
   if (!de) return NLS_OK;
   cudaSetDevice(de->ctx->device);
   cudaStreamSynchronize(de->ctx->stream);
+  for (cudaEvent_t e : de->events) cudaEventDestroy(e);
   de->mem.release();
   delete de;
   return NLS_OK;
@@ -190,6 +195,9 @@ static int de_build(nls_ctx *ctx, const nls_de_cfg *cfg, const void *x0_host, nl
   const u64 P = cfg->pop_size, d = cfg->dim;
   de->ctx = ctx;
   de->cfg = *cfg;
+  de->timing = false;
+  de->timed_ms[0] = de->timed_ms[1] = de->timed_ms[2] = 0.0;
+  de->timed_generations = 0;
   de->elem = elem_size(cfg->dtype);
   de->ops = cfg->dtype == NLS_F64 ? de_ops_f64() : de_ops_f32();
   de->g = make_geom(ctx, P);
@@ -258,7 +266,50 @@ int nls_de_create(nls_ctx *ctx, const nls_de_cfg *cfg, const void *x0_host, nls_
 int nls_de_step(nls_de *de, uint64_t n_generations) {
   if (!de) return fail(NLS_ERR_INVALID, "nls_de_step: NULL handle");
   NLS_CUDA(cudaSetDevice(de->ctx->device));
-  for (uint64_t g = 0; g < n_generations; g++) NLS_CUDA(de->ops->generation(de->s, de->g, de->ctx->stream));
+  for (uint64_t g = 0; g < n_generations; g++) {
+    cudaEvent_t *ev = nullptr;
+    if (de->timing) {
+      const size_t base = de->events.size();
+      de->events.resize(base + 4);
+      for (int k = 0; k < 4; k++) NLS_CUDA(cudaEventCreate(&de->events[base + k]));
+      ev = &de->events[base];
+    }
+    NLS_CUDA(de->ops->generation(de->s, de->g, de->ctx->stream, ev));
+  }
+  return NLS_OK;
+}
+
+static int de_drain_events(nls_de *de) {
+  for (size_t b = 0; b + 4 <= de->events.size(); b += 4) {
+    NLS_CUDA(cudaEventSynchronize(de->events[b + 3]));
+    for (int k = 0; k < 3; k++) {
+      float ms = 0.f;
+      NLS_CUDA(cudaEventElapsedTime(&ms, de->events[b + k], de->events[b + k + 1]));
+      de->timed_ms[k] += ms;
+    }
+    de->timed_generations++;
+    for (int k = 0; k < 4; k++) cudaEventDestroy(de->events[b + k]);
+  }
+  de->events.clear();
+  return NLS_OK;
+}
+
+int nls_de_enable_kernel_timing(nls_de *de, int enable) {
+  if (!de) return fail(NLS_ERR_INVALID, "nls_de_enable_kernel_timing: NULL handle");
+  NLS_CUDA(cudaSetDevice(de->ctx->device));
+  int rc = de_drain_events(de);
+  de->timing = enable != 0;
+  return rc;
+}
+
+int nls_de_kernel_times(nls_de *de, double ms[3], uint64_t *generations) {
+  if (!de || !ms || !generations) return fail(NLS_ERR_INVALID, "nls_de_kernel_times: NULL argument");
+  NLS_CUDA(cudaSetDevice(de->ctx->device));
+  int rc = de_drain_events(de);
+  if (rc != NLS_OK) return rc;
+  for (int k = 0; k < 3; k++) { ms[k] = de->timed_ms[k]; de->timed_ms[k] = 0.0; }
+  *generations = de->timed_generations;
+  de->timed_generations = 0;
   return NLS_OK;
 }
 

@@ -87,6 +87,38 @@ template <class T> __device__ __forceinline__ T warp_butterfly_add(T a) {
   return a;
 }
 
+// cos(2*pi*x) for the Rastrigin / Ackley terms.  fp64: exact reduction r = x - rint(x) (|x| < 2^51), fold |r| > 1/4
+// onto 1/2 - |r| with a sign flip, then a degree-8 polynomial in r^2 (Chebyshev fit of cos(2*pi*sqrt(t)) on
+// [0, 1/16], absolute error < 2.5e-16).  This evaluates the same function as the reference's cos(2*M_PI*x)
+// (test_functions.h:75, 88) without libdevice's table loads and Payne-Hanek path; the two differ by the rounding of
+// 2*M_PI*x in the reference expression (<= 4e-15 per term for |x| <= 5.12), far inside the 1e-12 tolerance.
+template <class T> __device__ __forceinline__ T cos2pi(T x);
+template <> __device__ __forceinline__ double cos2pi<double>(double x) {
+#ifdef NLS_LIBM_COS
+  return cos(__dmul_rn(2 * 3.14159265358979323846, x));
+#else
+  const double magic = 6755399441055744.0;                 // 1.5 * 2^52: (x + magic) - magic == rint(x)
+  const double r = x - (__dadd_rn(x, magic) - magic);      // exact, in [-1/2, 1/2]
+  double a = fabs(r);
+  const bool fold = a > 0.25;
+  a = fold ? 0.5 - a : a;                                  // exact
+  const double t = a * a;
+  double p = 0x1.1678f9078a9b3p-2;
+  p = fma(p, t, -0x1.b6957b54dd389p+0);
+  p = fma(p, t, 0x1.f9d254582ac30p+2);
+  p = fma(p, t, -0x1.a6d1efc8c38bep+4);
+  p = fma(p, t, 0x1.e1f506813a321p+5);
+  p = fma(p, t, -0x1.55d3c7e3bfbf5p+6);
+  p = fma(p, t, 0x1.03c1f081b5992p+6);
+  p = fma(p, t, -0x1.3bd3cc9be45dbp+4);
+  p = fma(p, t, 1.0);
+  return fold ? -p : p;
+#endif
+}
+template <> __device__ __forceinline__ float cos2pi<float>(float x) {
+  return cosf(__fmul_rn(static_cast<float>(2 * 3.14159265358979323846), x));
+}
+
 template <class T> __device__ __forceinline__ T t_cos(T x);
 template <> __device__ __forceinline__ double t_cos<double>(double x) { return cos(x); }
 template <> __device__ __forceinline__ float t_cos<float>(float x) { return cosf(x); }

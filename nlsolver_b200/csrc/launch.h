@@ -6,7 +6,8 @@ namespace nls {
 
 struct DEOps {
   cudaError_t (*init)(const DEState &s, const void *x0_dev, const LaunchGeom &g, cudaStream_t st);
-  cudaError_t (*generation)(const DEState &s, const LaunchGeom &g, cudaStream_t st);
+  // ev: NULL, or 4 events recorded before K2, between K2/K2r, between K2r/K3 and after K3
+  cudaError_t (*generation)(const DEState &s, const LaunchGeom &g, cudaStream_t st, cudaEvent_t *ev);
   cudaError_t (*export_best)(const DEState &s, void *record, cudaStream_t st);
   cudaError_t (*migrate)(const DEState &s, int sign, unsigned long long k, void *rows, void *scores,
                          const LaunchGeom &g, cudaStream_t st);

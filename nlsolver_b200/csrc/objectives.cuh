@@ -19,7 +19,7 @@ struct Objective {
   typedef Ar<T> A;
   T a, b, carry;
 
-  __device__ __forceinline__ void begin(int lane, u64 d) {
+  __device__ __forceinline__ void begin(int lane, u32 d) {
     // Rastrigin's leading `2*10` (10*d in N-D) seeds lane 0's accumulator so that d = 2 gives (20 + t0) + t1
     a = (OBJ == OBJ_RASTRIGIN && lane == 0) ? A::mul(T(10), T(d)) : T(0);
     b = T(0);
@@ -28,7 +28,7 @@ struct Objective {
 
   // x[q] is coordinate j0 + q of the agent; coordinates >= d are padding and contribute nothing.
   // Must be called by all 32 lanes (the pairwise forms shuffle).
-  __device__ __forceinline__ void step(const T (&x)[V], u64 j0, u64 d, int lane) {
+  __device__ __forceinline__ void step(const T (&x)[V], u32 j0, u32 d, int lane) {
     T left = T(0);
     if (kPairwise) {
       left = __shfl_up_sync(kFull, x[V - 1], 1);          // x[j0 - 1] lives in the previous lane ...
@@ -37,7 +37,7 @@ struct Objective {
     }
 #pragma unroll
     for (int q = 0; q < V; q++) {
-      const u64 j = j0 + q;
+      const u32 j = j0 + q;
       const T xj = x[q];
       if (kPairwise) {
         const T xl = (q == 0) ? left : x[q == 0 ? 0 : q - 1];
@@ -54,18 +54,17 @@ struct Objective {
         if (OBJ == OBJ_SPHERE) {
           a = A::add(a, A::mul(xj, xj));
         } else if (OBJ == OBJ_RASTRIGIN) {                 // x*x - 10*cos(2*pi*x)
-          const T c = t_cos<T>(A::mul(T(2 * 3.14159265358979323846), xj));
-          a = A::add(a, A::sub(A::mul(xj, xj), A::mul(T(10), c)));
+          a = A::add(a, A::sub(A::mul(xj, xj), A::mul(T(10), cos2pi<T>(xj))));
         } else if (OBJ == OBJ_ACKLEY) {
           a = A::add(a, A::mul(xj, xj));
-          b = A::add(b, t_cos<T>(A::mul(T(2 * 3.14159265358979323846), xj)));
+          b = A::add(b, cos2pi<T>(xj));
         }
       }
     }
   }
 
   // every lane returns the objective value
-  __device__ __forceinline__ T finish(u64 d) {
+  __device__ __forceinline__ T finish(u32 d) {
     a = warp_butterfly_add<T>(a);
     if (OBJ == OBJ_ACKLEY) {
       b = warp_butterfly_add<T>(b);

@@ -19,6 +19,8 @@ struct DECtrl {
   int stop, stop_reason, error, _pad;
   unsigned int ticket;          // last-block election of the reduction
   unsigned int acc_partial;     // accepted trials of the generation being committed
+  unsigned int spec_accepted;   // trials accepted by the speculative pass K2 (0 => nothing to repair)
+  unsigned int _pad2;
   unsigned int pending[2];      // repair: agents still waiting on a lower donor, by round parity
   unsigned int list_count[2];   // repair: agents to re-evaluate in this round, by round parity
   Moments score_moments;        // moments of the scores at the last scan (island exchange record)

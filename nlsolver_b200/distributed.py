@@ -1,0 +1,232 @@
+"""Multi-GPU layer: one process per GPU, torch.distributed for the plumbing (NCCL on GPUs, gloo in the CPU tests).
+
+What shards:
+  * PSO (both types) shards exactly: particles only interact through the previous generation's swarm best, so each
+    rank owns a contiguous slice of GLOBAL particle ids (draw streams are keyed by the global id) and a generation is
+    `step_local` -> all-gather of one candidate record per rank -> `apply_candidates`.  Results are identical to the
+    single-GPU swarm.  The all-gather + lowest-index-wins select is the min-loc all-reduce NCCL does not have natively.
+  * DE does not shard one population (every agent gathers three uniformly random rows and the in-place order spans the
+    whole population), so large DE runs as islands: each rank runs a reference-exact DE on its own population; every
+    generation the island bests are all-gathered (global status), and every `migrate_every` generations the `migrants`
+    best rows travel around the ring rank -> rank + 1 and overwrite the receiver's worst rows.
+
+The pure functions at the top (slices, ring, record select) are the host logic the world_size-2 gloo tests cover; the
+compute behind `engine` is any object with the small interface used below (the CUDA handles on GPUs).
+"""
+import struct
+
+import numpy as np
+
+HEADER_BYTES = 48   # RecordHeader: value f64, index u64, moments 3 x f64, valid i32, pad i32 (csrc/reduce.cuh)
+
+
+# ------------------------------------------------------------------ pure host logic -------------------------------
+def slice_bounds(n_global, world_size, rank):
+    """Contiguous slice [begin, end) of rank: the first n_global % world_size ranks hold one extra element."""
+    base, extra = divmod(n_global, world_size)
+    begin = rank * base + min(rank, extra)
+    return begin, begin + base + (1 if rank < extra else 0)
+
+
+def ring_neighbors(rank, world_size):
+    """(destination, source) of the migration ring."""
+    return (rank + 1) % world_size, (rank - 1) % world_size
+
+
+def record_bytes(elem_size, dim):
+    return HEADER_BYTES + (dim * elem_size + 7) // 8 * 8
+
+
+def parse_record(buf):
+    """Header of one exchange record (bytes-like) -> dict."""
+    value, index, n, mean, m2, valid, _ = struct.unpack_from("<dQdddii", bytes(buf[:HEADER_BYTES]))
+    return {"value": value, "index": index, "n": n, "mean": mean, "m2": m2, "valid": valid}
+
+
+def select_best(records, running_best=float("inf")):
+    """Index of the record that wins a strict-< scan in rank order against `running_best`, or -1.
+    Ranks hold ascending index ranges, so this is the reference's sequential scan (nlsolver.h:2723-2729)."""
+    win, best = -1, running_best
+    for r, rec in enumerate(records):
+        if rec["valid"] and rec["value"] < best:
+            best, win = rec["value"], r
+    return win
+
+
+def migration_due(generation, migrate_every):
+    """Migration happens after generations migrate_every, 2*migrate_every, ... (generation counts from 1)."""
+    return migrate_every > 0 and generation > 0 and generation % migrate_every == 0
+
+
+# ------------------------------------------------------------------ process group ---------------------------------
+def init_from_env(backend=None):
+    """Join the process group torchrun describes (RANK / WORLD_SIZE / LOCAL_RANK / MASTER_*). Returns (rank, world)."""
+    import os
+
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    if world > 1 and not dist.is_initialized():
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        kw = {}
+        if backend == "nccl":
+            local = int(os.environ.get("LOCAL_RANK", "0"))
+            torch.cuda.set_device(local)
+            kw["device_id"] = torch.device("cuda", local)
+        dist.init_process_group(backend=backend, rank=rank, world_size=world, **kw)
+    return rank, world
+
+
+class _Comm:
+    """all_gather / ring exchange of byte tensors on the tensors' own device (NCCL for cuda, gloo for cpu)."""
+
+    def __init__(self, group=None):
+        import torch.distributed as dist
+        self.dist = dist
+        self.group = group
+        self.active = dist.is_available() and dist.is_initialized()
+        self.rank = dist.get_rank(group) if self.active else 0
+        self.world = dist.get_world_size(group) if self.active else 1
+
+    def all_gather(self, out, inp):
+        if self.world == 1:
+            out.copy_(inp)
+        else:
+            self.dist.all_gather_into_tensor(out, inp, group=self.group)
+
+    def ring_exchange(self, send, recv):
+        """send -> rank + 1, recv <- rank - 1."""
+        if self.world == 1:
+            recv.copy_(send)
+            return
+        dst, src = ring_neighbors(self.rank, self.world)
+        ops = [self.dist.P2POp(self.dist.isend, send, dst, self.group),
+               self.dist.P2POp(self.dist.irecv, recv, src, self.group)]
+        for w in self.dist.batch_isend_irecv(ops):
+            w.wait()
+
+
+# ------------------------------------------------------------------ sharded PSO -----------------------------------
+class ShardedPSO:
+    """A global swarm of `cfg.n_particles` particles split across the ranks of `group`."""
+
+    def __init__(self, cfg, lower, upper, device=0, group=None, stream=None):
+        import torch
+
+        from . import _lib as L
+        from .solvers import Context, PSOSwarm, pso_cfg
+        self.torch = torch
+        self.comm = _Comm(group)
+        n_global = cfg.n_particles
+        begin, end = slice_bounds(n_global, self.comm.world, self.comm.rank)
+        self.stream = stream or torch.cuda.Stream(device)
+        self.ctx = Context(device, self.stream.cuda_stream)
+        local = pso_cfg(cfg.dtype, cfg.objective, cfg.pso_type, bool(cfg.minimize), end - begin, cfg.dim, cfg.inertia,
+                        cfg.cognitive_coef, cfg.social_coef, cfg.eps, cfg.max_iter, cfg.best_val_no_change,
+                        bool(cfg.constrained), cfg.flags, cfg.seed, begin, n_global)
+        self.n_local, self.n_global = end - begin, n_global
+        self.swarm = PSOSwarm(self.ctx, local, lower, upper)
+        self.rb = L.lib().nls_record_bytes(cfg.dtype, cfg.dim)
+        with torch.cuda.stream(self.stream):
+            self.mine = torch.zeros(self.rb, dtype=torch.uint8, device=f"cuda:{device}")
+            self.all = torch.zeros(self.rb * self.comm.world, dtype=torch.uint8, device=f"cuda:{device}")
+            if self.comm.world > 1:   # finish the first update_best_positions across shards (nlsolver.h:2595)
+                self.swarm.export_candidate(self.mine.data_ptr())
+                self.comm.all_gather(self.all, self.mine)
+                self.swarm.apply_candidates(self.all.data_ptr(), self.comm.world)
+
+    def step(self, n=1):
+        with self.torch.cuda.stream(self.stream):
+            if self.comm.world == 1:
+                self.swarm.step(n)
+                return
+            for _ in range(n):
+                self.swarm.step_local(self.mine.data_ptr())
+                self.comm.all_gather(self.all, self.mine)
+                self.swarm.apply_candidates(self.all.data_ptr(), self.comm.world)
+
+    def sync(self):
+        return self.swarm.sync()
+
+    def best(self):
+        return self.swarm.best()
+
+    def close(self):
+        self.swarm.close()
+        self.ctx.close()
+
+
+# ------------------------------------------------------------------ island DE -------------------------------------
+class IslandDE:
+    """One reference-exact DE island per rank; global best by all-gather, ring migration every `migrate_every`."""
+
+    def __init__(self, cfg, x0, device=0, group=None, migrate_every=10, migrants=64, stream=None):
+        import torch
+
+        from . import _lib as L
+        from .solvers import Context, DEPopulation, de_cfg
+        self.torch = torch
+        self.comm = _Comm(group)
+        self.migrate_every, self.k = migrate_every, min(migrants, cfg.pop_size)
+        self.stream = stream or torch.cuda.Stream(device)
+        self.ctx = Context(device, self.stream.cuda_stream)
+        # islands draw from disjoint streams: global agent ids rank * P + i
+        local = de_cfg(cfg.dtype, cfg.objective, cfg.strategy, bool(cfg.minimize), cfg.pop_size, cfg.dim,
+                       cfg.crossover_prob, cfg.differential_weight, cfg.eps, cfg.max_iter, cfg.best_val_no_change,
+                       cfg.seed, cfg.agent_offset + self.comm.rank * cfg.pop_size, cfg.flags)
+        self.cfg = local
+        self.island = DEPopulation(self.ctx, local, x0)
+        self.generation = 0
+        self.rb = L.lib().nls_record_bytes(cfg.dtype, cfg.dim)
+        es = 8 if cfg.dtype == L.F64 else 4
+        tdt = torch.float64 if cfg.dtype == L.F64 else torch.float32
+        dev = f"cuda:{device}"
+        with torch.cuda.stream(self.stream):
+            self.mine = torch.zeros(self.rb, dtype=torch.uint8, device=dev)
+            self.all = torch.zeros(self.rb * self.comm.world, dtype=torch.uint8, device=dev)
+            self.out_rows = torch.zeros(self.k * cfg.dim, dtype=tdt, device=dev)
+            self.out_scores = torch.zeros(self.k, dtype=tdt, device=dev)
+            self.in_rows = torch.zeros_like(self.out_rows)
+            self.in_scores = torch.zeros_like(self.out_scores)
+        self.launches = 0
+        del es
+
+    def step(self, n=1):
+        with self.torch.cuda.stream(self.stream):
+            for _ in range(n):
+                self.island.step(1)
+                self.generation += 1
+                self.launches += 3
+                self.island.export_best(self.mine.data_ptr())
+                self.launches += 1
+                self.comm.all_gather(self.all, self.mine)
+                if migration_due(self.generation, self.migrate_every) and self.comm.world > 1:
+                    self.island.export_top(self.k, self.out_rows.data_ptr(), self.out_scores.data_ptr())
+                    self.comm.ring_exchange(self.out_rows, self.in_rows)
+                    self.comm.ring_exchange(self.out_scores, self.in_scores)
+                    self.island.import_migrants(self.k, self.in_rows.data_ptr(), self.in_scores.data_ptr())
+                    self.launches += 2 * self.k + 3
+
+    def sync(self):
+        """Local island status plus the global best over the last all-gather."""
+        st = self.island.sync()
+        self.stream.synchronize()
+        recs = self.all.cpu().numpy()
+        heads = [parse_record(recs[r * self.rb:r * self.rb + HEADER_BYTES]) for r in range(self.comm.world)]
+        win = select_best(heads)
+        st["global_best_value"] = heads[win]["value"] if win >= 0 else st["f_value"]
+        st["global_best_rank"] = win
+        return st
+
+    def global_best_row(self):
+        st = self.sync()
+        r = max(st["global_best_rank"], 0)
+        dt = np.float64 if self.cfg.dtype == 1 else np.float32
+        raw = self.all.cpu().numpy()[r * self.rb + HEADER_BYTES:(r + 1) * self.rb]
+        return raw.view(dt)[:self.cfg.dim].copy()
+
+    def close(self):
+        self.island.close()
+        self.ctx.close()

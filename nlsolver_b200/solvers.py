@@ -154,6 +154,15 @@ class DEPopulation:
             a["masks"] = m
         return a
 
+    def enable_kernel_timing(self, enable=True):
+        L.check(L.lib().nls_de_enable_kernel_timing(self._h, int(enable)))
+
+    def kernel_times(self):
+        """(ms per kernel [K2 generation pass, K2r repair, K3 commit+reduce], generations) since the last call."""
+        ms, n = (L.f64 * 3)(), L.u64()
+        L.check(L.lib().nls_de_kernel_times(self._h, ms, C.byref(n)))
+        return list(ms), n.value
+
     def export_best(self, record_ptr):
         L.check(L.lib().nls_de_export_best(self._h, C.c_void_p(record_ptr)))
 

@@ -82,7 +82,6 @@ def test_de_matches_oracle_every_generation(ctx, oracle_lib, dtype, obj, strateg
         st = pop.sync()
         so, ao = oracle_de(oracle_lib, dtype, obj, strategy, minimize, P, d, g, seed, x0)
         compare_generation(pop, st, so, ao, tol, g, check_decisions=g > 0)
-    assert st["repair_rounds"] >= G
     pop.close()
 
 

@@ -150,7 +150,9 @@ def test_sharded_swarm_equals_single_swarm(ctx):
     sw = whole.sync()
     for s in shards:
         ss = s.sync()
-        for k in ("f_value", "iterations", "function_calls", "best_index", "val_no_change", "std_err"):
-            assert ss[k] == sw[k], k
+        for k in ("f_value", "iterations", "function_calls", "best_index", "val_no_change"):
+            assert ss[k] == sw[k], (k, ss[k], sw[k])
+        # the stop statistic merges per-shard moments in a different order than the single swarm's block tree
+        assert abs(ss["std_err"] - sw["std_err"]) <= 1e-12 * abs(sw["std_err"])
         assert np.array_equal(bits(s.best()), bits(whole.best()))
     assert np.array_equal(bits(np.concatenate([s.positions() for s in shards])), bits(whole.positions()))
