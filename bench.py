@@ -211,7 +211,7 @@ def run_b200_arm(args, rank, world):
     island = IslandDE(cfg, x0, device=local, migrate_every=MIGRATE_EVERY, migrants=MIGRANTS, stream=stream)
     island.step(W)
     st0 = island.sync()
-    island.island.enable_kernel_timing(True)
+    island.engine.pop.enable_kernel_timing(True)
     launches0 = island.launches
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sampler = ClockSampler(local)
@@ -226,8 +226,8 @@ def run_b200_arm(args, rank, world):
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     total_ms = float(ms.item())
-    kernel_ms, timed_gens = island.island.kernel_times()
-    island.island.enable_kernel_timing(False)
+    kernel_ms, timed_gens = island.engine.pop.kernel_times()
+    island.engine.pop.enable_kernel_timing(False)
     st1 = island.sync()
     assert st1["iterations"] - st0["iterations"] == K and timed_gens == K
     launches = island.launches - launches0

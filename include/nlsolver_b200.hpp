@@ -1,0 +1,360 @@
+// nlsolver_b200.hpp — drop-in C++17 header for the DE / PSO part of JSzitas/nlsolver, backed by the B200 engine.
+//
+// Same names, template parameter lists, constructor defaults and method signatures as the reference
+// (nlsolver.h:2377-2477 DE, 2496-2742 PSO, 2054-2097 solver_status, 1263-1288 / 1343-1381 the generators), so call
+// sites like example.cpp:184-215 or README.md:94-110 compile unchanged apart from the objective type: `Callable`
+// must be one of the device functor tags below (test_functions.h:51-92 names), because the objective runs on the
+// GPU.  Everything here is plain host C++ over the C ABI in nls_b200.h — no CUDA headers, link with -lnls_b200.
+//
+// What differs from the reference, by design:
+//   * the population loop runs on the GPU; there is no CPU fallback (an error from the C ABI becomes
+//     std::runtime_error);
+//   * the user's generator is advanced by exactly TWO draws per minimize()/maximize() call — they seed the device
+//     draw tape (DESIGN.md "RNG tape"); callers that share one generator across solvers or reset() it between runs
+//     (test_functions.h:434-470, example.cpp:209) keep deterministic behaviour;
+//   * vanilla PSO with n_particles > dim uses swarm_best_position[j] in the social term; the reference indexes it
+//     with the particle number there and reads out of bounds (nlsolver.h:2674).
+#ifndef NLSOLVER_B200_HPP_
+#define NLSOLVER_B200_HPP_
+
+#include <array>
+#include <cmath>
+#include <cstdint>
+#include <cstdlib>
+#include <iostream>
+#include <stdexcept>
+#include <string>
+#include <tuple>
+#include <type_traits>
+#include <vector>
+
+#include "nls_b200.h"
+
+// nlsolver.h:49-55
+template <typename T>
+void print_vector(T x) {
+  for (auto &val : x) std::cout << val << ",";
+  std::cout << "\n";
+}
+
+namespace nlsolver {
+
+// ------------------------------------------------------------------------------------------------ generators
+namespace rng {
+namespace detail {
+inline uint64_t splitmix_out(uint64_t z) {   // output function of splitmix64
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+template <typename T>
+inline T to_unit(uint64_t u) { return static_cast<T>(u / static_cast<T>(18446744073709551615U)); }
+}  // namespace detail
+
+// nlsolver.h:1263-1288
+template <typename scalar_t = float>
+struct splitmix {
+  explicit splitmix() : s(12374563468ull) {}
+  scalar_t yield() { return detail::to_unit<scalar_t>(yield_init()); }
+  scalar_t operator()() { return yield(); }
+  uint64_t yield_init() { return detail::splitmix_out(s += 0x9E3779B97F4A7C15ull); }
+  void set_state(uint64_t seed) { s = seed; }
+  std::vector<scalar_t> get_state() const { return {static_cast<scalar_t>(s)}; }
+
+ private:
+  uint64_t s;
+};
+
+// nlsolver.h:1343-1381 — xorshift128+ (23 / 18 / 5), default-seeded from splitmix
+template <typename scalar_t = float>
+struct xorshift {
+  xorshift() { reset(); }
+  scalar_t yield() {
+    uint64_t t = x[0];
+    const uint64_t s = x[1];
+    x[0] = s;
+    t ^= t << 23;
+    t ^= t >> 18;
+    t ^= s ^ (s >> 5);
+    x[1] = t;
+    return detail::to_unit<scalar_t>(t + s);
+  }
+  scalar_t operator()() { return yield(); }
+  void reset() {
+    splitmix<scalar_t> gn;
+    x[0] = gn.yield_init();
+    x[1] = x[0] >> 32;
+  }
+  void set_state(uint64_t y, uint64_t z) { x[0] = y; x[1] = z; }
+  std::vector<scalar_t> get_state() const { return {static_cast<scalar_t>(x[0]), static_cast<scalar_t>(x[1])}; }
+
+ private:
+  uint64_t x[2]{};
+};
+}  // namespace rng
+
+// ------------------------------------------------------------------------------------------------ objectives
+// Device functor tags.  operator() evaluates the same N-D form on the host, in the device's summation order, so a
+// caller can re-evaluate the returned point; the solvers never call it.
+namespace test_functions {
+namespace detail {
+template <typename T, typename Term>
+T lane_sum(size_t first_j, size_t d, T lane0_init, Term term) {
+  constexpr size_t V = 16 / sizeof(T);
+  T acc[32] = {};
+  acc[0] = lane0_init;
+  for (size_t j = first_j; j < d; j++) { T &a = acc[(j / V) % 32]; a = a + term(j); }
+  for (int off = 16; off >= 1; off >>= 1) {
+    T nxt[32];
+    for (int l = 0; l < 32; l++) nxt[l] = acc[l] + acc[l ^ off];
+    for (int l = 0; l < 32; l++) acc[l] = nxt[l];
+  }
+  return acc[0];
+}
+}  // namespace detail
+
+template <typename T> struct Sphere {                      // test_functions.h:51-57
+  static constexpr int nls_objective = NLS_SPHERE;
+  static constexpr size_t input_size() { return 2; }
+  T operator()(const std::vector<T> &x) const {
+    return detail::lane_sum<T>(0, x.size(), T(0), [&](size_t j) { return x[j] * x[j]; });
+  }
+  std::vector<T> minimum() const { return {0.0, 0.0}; }
+};
+template <typename T> struct Rosenbrock {                  // test_functions.h:59-68
+  static constexpr int nls_objective = NLS_ROSENBROCK;
+  static constexpr size_t input_size() { return 2; }
+  T operator()(const std::vector<T> &x) const {
+    return detail::lane_sum<T>(1, x.size(), T(0), [&](size_t j) {
+      const T p = x[j - 1] * x[j - 1] - x[j], q = x[j - 1] - 1;
+      return static_cast<T>(100.0) * (p * p) + q * q;
+    });
+  }
+  std::vector<T> minimum() const { return {1.0, 1.0}; }
+};
+template <typename T> struct Rastrigin {                   // test_functions.h:70-79
+  static constexpr int nls_objective = NLS_RASTRIGIN;
+  static constexpr size_t input_size() { return 2; }
+  T operator()(const std::vector<T> &x) const {
+    const T two_pi = static_cast<T>(2 * 3.14159265358979323846);
+    return detail::lane_sum<T>(0, x.size(), static_cast<T>(10) * static_cast<T>(x.size()),
+                               [&](size_t j) { return x[j] * x[j] - static_cast<T>(10) * std::cos(two_pi * x[j]); });
+  }
+  std::vector<T> minimum() const { return {0.0, 0.0}; }
+};
+template <typename T> struct Ackley {                      // test_functions.h:81-92
+  static constexpr int nls_objective = NLS_ACKLEY;
+  static constexpr size_t input_size() { return 2; }
+  T operator()(const std::vector<T> &x) const {
+    const T two_pi = static_cast<T>(2 * 3.14159265358979323846);
+    const T sq = detail::lane_sum<T>(0, x.size(), T(0), [&](size_t j) { return x[j] * x[j]; });
+    const T cs = detail::lane_sum<T>(0, x.size(), T(0), [&](size_t j) { return std::cos(two_pi * x[j]); });
+    const T inv_d = static_cast<T>(1.0) / static_cast<T>(x.size());
+    const T a = static_cast<T>(-20) * std::exp(static_cast<T>(-0.2) * std::sqrt(inv_d * sq));
+    const T b = -std::exp(inv_d * cs);
+    return a + b + static_cast<T>(std::exp(1.0)) + static_cast<T>(20);
+  }
+  std::vector<T> minimum() const { return {0.0, 0.0}; }
+};
+// the Rosenbrock variant of example.cpp:41-48 and README.md:83-90
+template <typename T> struct RosenbrockExample {
+  static constexpr int nls_objective = NLS_ROSENBROCK_EX;
+  static constexpr size_t input_size() { return 2; }
+  T operator()(const std::vector<T> &x) const {
+    return detail::lane_sum<T>(1, x.size(), T(0), [&](size_t j) {
+      const T t1 = 1 - x[j - 1], t2 = x[j] - x[j - 1] * x[j - 1];
+      return t1 * t1 + static_cast<T>(100) * t2 * t2;
+    });
+  }
+  std::vector<T> minimum() const { return {1.0, 1.0}; }
+};
+}  // namespace test_functions
+
+namespace b200 {
+template <typename C, typename = void> struct objective_of : std::integral_constant<int, -1> {};
+template <typename C>
+struct objective_of<C, std::void_t<decltype(C::nls_objective)>> : std::integral_constant<int, C::nls_objective> {};
+template <typename T> constexpr int dtype_of() {
+  static_assert(std::is_same<T, double>::value || std::is_same<T, float>::value, "scalar_t must be float or double");
+  return std::is_same<T, double>::value ? NLS_F64 : NLS_F32;
+}
+inline void check(int rc) {
+  if (rc != NLS_OK) throw std::runtime_error(std::string("nls_b200: ") + nls_last_error());
+}
+// one context per process, created on first use on device $NLS_B200_DEVICE (default 0)
+inline nls_ctx *default_context() {
+  struct Holder {
+    nls_ctx *ctx = nullptr;
+    Holder() {
+      const char *dev = std::getenv("NLS_B200_DEVICE");
+      check(nls_ctx_create(dev ? std::atoi(dev) : 0, nullptr, &ctx));
+    }
+    ~Holder() { nls_ctx_destroy(ctx); }
+  };
+  static Holder h;
+  return h.ctx;
+}
+// two draws of the user's generator -> 64-bit tape seed (hi word first)
+template <typename RNG>
+uint64_t seed_from(RNG &generator) {
+  auto word = [&]() {
+    const double v = static_cast<double>(generator()) * 4294967296.0;
+    return v >= 4294967295.0 ? 0xFFFFFFFFull : (v <= 0.0 ? 0ull : static_cast<uint64_t>(v));
+  };
+  const uint64_t hi = word();
+  const uint64_t lo = word();
+  return (hi << 32) | lo;
+}
+}  // namespace b200
+
+// ------------------------------------------------------------------------------------------------ solver_status
+// nlsolver.h:2054-2097
+template <typename scalar_t = double>
+struct solver_status {
+  solver_status(const scalar_t f_val, const size_t iter_used, const size_t f_calls_used,
+                const size_t grad_evals_used = 0ul, const size_t hess_evals_used = 0ul)
+      : f_value(f_val), iteration(iter_used), function_calls_used(f_calls_used),
+        gradient_evals_used(grad_evals_used), hessian_evals_used(hess_evals_used) {}
+  void print() const {
+    std::cout << "Function calls used: " << function_calls_used << std::endl;
+    std::cout << "Algorithm iterations used: " << iteration << std::endl;
+    if (gradient_evals_used > 0) std::cout << "Gradient evaluations used: " << gradient_evals_used << std::endl;
+    if (hessian_evals_used > 0) std::cout << "Hessian evaluations used: " << hessian_evals_used << std::endl;
+    std::cout << "With final function value of " << f_value << std::endl;
+  }
+  std::tuple<size_t, size_t, scalar_t, size_t, size_t> get_summary() const {
+    return std::make_tuple(function_calls_used, iteration, f_value, gradient_evals_used, hessian_evals_used);
+  }
+  void add(const solver_status<scalar_t> &more) {
+    const auto o = more.get_summary();
+    function_calls_used += std::get<0>(o);
+    iteration += std::get<1>(o);
+    f_value = std::get<2>(o);
+    gradient_evals_used += std::get<3>(o);
+    hessian_evals_used += std::get<4>(o);
+  }
+
+ private:
+  scalar_t f_value;
+  size_t iteration, function_calls_used, gradient_evals_used, hessian_evals_used;
+};
+
+// ------------------------------------------------------------------------------------------------ DE
+enum RecombinationStrategy { best, random };   // nlsolver.h:2377
+
+// nlsolver.h:2379-2477
+template <typename Callable, typename RNG, typename scalar_t = double,
+          RecombinationStrategy RecombinationType = random>
+class DE {
+  static_assert(b200::objective_of<Callable>::value >= 0,
+                "nlsolver_b200: Callable must be a device objective tag (nlsolver::test_functions::Sphere, "
+                "Rosenbrock, Rastrigin, Ackley, RosenbrockExample); host functors cannot run on the GPU");
+
+ public:
+  DE(Callable &f, RNG &generator, const scalar_t crossover_prob = 0.9, const scalar_t differential_weight = 0.8,
+     const scalar_t eps = 10e-4, const size_t pop_size = 50, const size_t max_iter = 1000,
+     const size_t best_val_no_change = 50)
+      : f(f), generator(generator), crossover_prob(crossover_prob), differential_weight(differential_weight),
+        eps(eps), pop_size(pop_size), max_iter(max_iter), best_value_no_change(best_val_no_change) {}
+  solver_status<scalar_t> minimize(std::vector<scalar_t> &x) { return solve(x, true); }
+  solver_status<scalar_t> maximize(std::vector<scalar_t> &x) { return solve(x, false); }
+
+ private:
+  solver_status<scalar_t> solve(std::vector<scalar_t> &x, bool minimize) {
+    nls_de_cfg cfg{};
+    cfg.dtype = b200::dtype_of<scalar_t>();
+    cfg.objective = b200::objective_of<Callable>::value;
+    cfg.strategy = RecombinationType == random ? NLS_DE_RANDOM : NLS_DE_BEST;
+    cfg.minimize = minimize ? 1 : 0;
+    cfg.pop_size = pop_size;
+    cfg.dim = x.size();
+    cfg.crossover_prob = crossover_prob;
+    cfg.differential_weight = differential_weight;
+    cfg.eps = eps;
+    cfg.max_iter = max_iter;
+    cfg.best_val_no_change = best_value_no_change;
+    cfg.seed = b200::seed_from(generator);
+    std::vector<scalar_t> best_row(x.size());
+    nls_status st{};
+    b200::check(nls_de_solve(b200::default_context(), &cfg, x.data(), best_row.data(), &st));
+    x = best_row;                                              // nlsolver.h:2444
+    return solver_status<scalar_t>(static_cast<scalar_t>(st.f_value), st.iterations, st.function_calls);
+  }
+  Callable &f;
+  RNG &generator;
+  const scalar_t crossover_prob, differential_weight, eps;
+  const size_t pop_size, max_iter, best_value_no_change;
+};
+
+// ------------------------------------------------------------------------------------------------ PSO
+enum PSOType { Vanilla, Accelerated };   // nlsolver.h:2496
+
+// nlsolver.h:2498-2742
+template <typename Callable, typename RNG, typename scalar_t = double, PSOType Type = Vanilla>
+class PSO {
+  static_assert(b200::objective_of<Callable>::value >= 0,
+                "nlsolver_b200: Callable must be a device objective tag (see nlsolver::test_functions)");
+
+ public:
+  PSO(Callable &f, RNG &generator, const scalar_t inertia = 0.8, const scalar_t cognitive_coef = 1.8,
+      const scalar_t social_coef = 1.8, const size_t n_particles = 10, const size_t max_iter = 5000,
+      const size_t best_val_no_change = 50, const scalar_t eps = 10e-4)
+      : generator(generator), f(f), inertia(inertia), cognitive_coef(cognitive_coef), social_coef(social_coef),
+        n_particles(n_particles), max_iter(max_iter), best_val_no_change(best_val_no_change), eps(eps) {}
+  // unbounded: lower = -|x|, upper = |x| seed the swarm, positions are never clamped (nlsolver.h:2553-2575)
+  solver_status<scalar_t> minimize(std::vector<scalar_t> &x) { return unbounded(x, true); }
+  solver_status<scalar_t> maximize(std::vector<scalar_t> &x) { return unbounded(x, false); }
+  // bounded: positions are clamped to [lower, upper] every generation (nlsolver.h:2577-2589)
+  solver_status<scalar_t> minimize(std::vector<scalar_t> &x, const std::vector<scalar_t> &lower,
+                                   const std::vector<scalar_t> &upper) { return solve(x, lower, upper, true, true); }
+  solver_status<scalar_t> maximize(std::vector<scalar_t> &x, const std::vector<scalar_t> &lower,
+                                   const std::vector<scalar_t> &upper) { return solve(x, lower, upper, false, true); }
+
+ private:
+  solver_status<scalar_t> unbounded(std::vector<scalar_t> &x, bool minimize) {
+    std::vector<scalar_t> lower(x.size()), upper(x.size());
+    for (size_t i = 0; i < x.size(); i++) { upper[i] = std::abs(x[i]); lower[i] = -upper[i]; }
+    return solve(x, lower, upper, minimize, false);
+  }
+  solver_status<scalar_t> solve(std::vector<scalar_t> &x, const std::vector<scalar_t> &lower,
+                                const std::vector<scalar_t> &upper, bool minimize, bool constrained) {
+    if (lower.size() != upper.size()) throw std::invalid_argument("nlsolver_b200: lower / upper sizes differ");
+    nls_pso_cfg cfg{};
+    cfg.dtype = b200::dtype_of<scalar_t>();
+    cfg.objective = b200::objective_of<Callable>::value;
+    cfg.pso_type = Type == Vanilla ? NLS_PSO_VANILLA : NLS_PSO_ACCELERATED;
+    cfg.minimize = minimize ? 1 : 0;
+    cfg.n_particles = n_particles;
+    cfg.dim = lower.size();
+    cfg.inertia = inertia;
+    cfg.cognitive_coef = cognitive_coef;
+    cfg.social_coef = social_coef;
+    cfg.eps = eps;
+    cfg.max_iter = max_iter;
+    cfg.best_val_no_change = best_val_no_change;
+    cfg.constrained = constrained ? 1 : 0;
+    cfg.flags = (Type == Vanilla && n_particles > lower.size()) ? NLS_FLAG_SOCIAL_INDEX_J : 0u;
+    cfg.seed = b200::seed_from(generator);
+    std::vector<scalar_t> best_row(lower.size());
+    nls_status st{};
+    b200::check(nls_pso_solve(b200::default_context(), &cfg, lower.data(), upper.data(), best_row.data(), &st));
+    if (st.best_valid) x = best_row;
+    else x.clear();   // the reference assigns a never-filled swarm_best_position (nlsolver.h:2601)
+    return solver_status<scalar_t>(static_cast<scalar_t>(st.f_value), st.iterations, st.function_calls);
+  }
+  RNG &generator;
+  Callable &f;
+  const scalar_t inertia, cognitive_coef, social_coef;
+  const size_t n_particles, max_iter, best_val_no_change;
+  const scalar_t eps;
+};
+
+// the names README.md:80,99 uses
+template <typename Callable, typename RNG, typename scalar_t = double,
+          RecombinationStrategy RecombinationType = random>
+using DESolver = DE<Callable, RNG, scalar_t, RecombinationType>;
+template <typename Callable, typename RNG, typename scalar_t = double, PSOType Type = Vanilla>
+using PSOSolver = PSO<Callable, RNG, scalar_t, Type>;
+
+}  // namespace nlsolver
+#endif  // NLSOLVER_B200_HPP_

@@ -108,44 +108,101 @@ class _Comm:
             w.wait()
 
 
-# ------------------------------------------------------------------ sharded PSO -----------------------------------
-class ShardedPSO:
-    """A global swarm of `cfg.n_particles` particles split across the ranks of `group`."""
+def merge_moments(parts):
+    """Chan / Golub / LeVeque combination of (n, mean, m2) triples in the given order -> (n, mean, m2)."""
+    n, mean, m2 = 0.0, 0.0, 0.0
+    for pn, pmean, pm2 in parts:
+        if pn == 0.0:
+            continue
+        if n == 0.0:
+            n, mean, m2 = pn, pmean, pm2
+            continue
+        tot = n + pn
+        delta = pmean - mean
+        mean, m2, n = mean + delta * (pn / tot), m2 + pm2 + delta * delta * (n * pn / tot), tot
+    return n, mean, m2
 
-    def __init__(self, cfg, lower, upper, device=0, group=None, stream=None):
+
+def std_err_from_moments(n, mean, m2):
+    """std_err (nlsolver.h:2037-2052) from merged moments: sqrt(sum((x - mean)^2) / (n - 1))."""
+    return float(np.sqrt(m2 / (n - 1.0))) if n > 1.0 else float("nan")
+
+
+def pack_record(value, index, moments, row, valid=True):
+    """Build one exchange record (numpy uint8) — the layout the CUDA kernels write (csrc/reduce.cuh RecordHeader)."""
+    row = np.ascontiguousarray(row)
+    body = row.tobytes()
+    body += b"\0" * (-len(body) % 8)
+    head = struct.pack("<dQdddii", float(value), int(index) & 0xFFFFFFFFFFFFFFFF, *[float(m) for m in moments],
+                       int(bool(valid)), 0)
+    return np.frombuffer(head + body, dtype=np.uint8).copy()
+
+
+# ------------------------------------------------------------------ engines ---------------------------------------
+class CudaDEEngine:
+    """The CUDA island: nls_de_* behind the interface IslandDE drives (tensors in, raw device pointers out)."""
+
+    def __init__(self, cfg, x0, device, stream):
         import torch
 
-        from . import _lib as L
-        from .solvers import Context, PSOSwarm, pso_cfg
+        from .solvers import Context, DEPopulation
         self.torch = torch
-        self.comm = _Comm(group)
-        n_global = cfg.n_particles
-        begin, end = slice_bounds(n_global, self.comm.world, self.comm.rank)
-        self.stream = stream or torch.cuda.Stream(device)
-        self.ctx = Context(device, self.stream.cuda_stream)
-        local = pso_cfg(cfg.dtype, cfg.objective, cfg.pso_type, bool(cfg.minimize), end - begin, cfg.dim, cfg.inertia,
-                        cfg.cognitive_coef, cfg.social_coef, cfg.eps, cfg.max_iter, cfg.best_val_no_change,
-                        bool(cfg.constrained), cfg.flags, cfg.seed, begin, n_global)
-        self.n_local, self.n_global = end - begin, n_global
-        self.swarm = PSOSwarm(self.ctx, local, lower, upper)
-        self.rb = L.lib().nls_record_bytes(cfg.dtype, cfg.dim)
-        with torch.cuda.stream(self.stream):
-            self.mine = torch.zeros(self.rb, dtype=torch.uint8, device=f"cuda:{device}")
-            self.all = torch.zeros(self.rb * self.comm.world, dtype=torch.uint8, device=f"cuda:{device}")
-            if self.comm.world > 1:   # finish the first update_best_positions across shards (nlsolver.h:2595)
-                self.swarm.export_candidate(self.mine.data_ptr())
-                self.comm.all_gather(self.all, self.mine)
-                self.swarm.apply_candidates(self.all.data_ptr(), self.comm.world)
+        self.ctx = Context(device, stream.cuda_stream)
+        self.pop = DEPopulation(self.ctx, cfg, x0)
+        self.device = f"cuda:{device}"
+        self.kernel_launches = 0
 
-    def step(self, n=1):
-        with self.torch.cuda.stream(self.stream):
-            if self.comm.world == 1:
-                self.swarm.step(n)
-                return
-            for _ in range(n):
-                self.swarm.step_local(self.mine.data_ptr())
-                self.comm.all_gather(self.all, self.mine)
-                self.swarm.apply_candidates(self.all.data_ptr(), self.comm.world)
+    def tensor(self, n, dtype):
+        return self.torch.zeros(n, dtype=dtype, device=self.device)
+
+    def step(self, n):
+        self.pop.step(n)
+        self.kernel_launches += 3 * n
+
+    def export_best(self, record):
+        self.pop.export_best(record.data_ptr())
+        self.kernel_launches += 1
+
+    def export_top(self, k, rows, scores):
+        self.pop.export_top(k, rows.data_ptr(), scores.data_ptr())
+        self.kernel_launches += k + 1
+
+    def import_migrants(self, k, rows, scores):
+        self.pop.import_migrants(k, rows.data_ptr(), scores.data_ptr())
+        self.kernel_launches += k + 2
+
+    def sync(self):
+        return self.pop.sync()
+
+    def close(self):
+        self.pop.close()
+        self.ctx.close()
+
+
+class CudaPSOEngine:
+    def __init__(self, cfg, lower, upper, device, stream):
+        import torch
+
+        from .solvers import Context, PSOSwarm
+        self.torch = torch
+        self.ctx = Context(device, stream.cuda_stream)
+        self.swarm = PSOSwarm(self.ctx, cfg, lower, upper)
+        self.device = f"cuda:{device}"
+
+    def tensor(self, n, dtype):
+        return self.torch.zeros(n, dtype=dtype, device=self.device)
+
+    def export_candidate(self, record):
+        self.swarm.export_candidate(record.data_ptr())
+
+    def step_local(self, record):
+        self.swarm.step_local(record.data_ptr())
+
+    def step(self, n):
+        self.swarm.step(n)
+
+    def apply_candidates(self, records, n):
+        self.swarm.apply_candidates(records.data_ptr(), n)
 
     def sync(self):
         return self.swarm.sync()
@@ -158,60 +215,129 @@ class ShardedPSO:
         self.ctx.close()
 
 
+class _NullStream:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+    def synchronize(self):
+        pass
+
+
+# ------------------------------------------------------------------ sharded PSO -----------------------------------
+class ShardedPSO:
+    """A global swarm of `cfg.n_particles` particles split across the ranks of `group`."""
+
+    def __init__(self, cfg, lower, upper, device=0, group=None, stream=None, engine_factory=None):
+        import torch
+
+        from . import _lib as L
+        from .solvers import pso_cfg
+        self.torch = torch
+        self.comm = _Comm(group)
+        n_global = cfg.n_particles
+        begin, end = slice_bounds(n_global, self.comm.world, self.comm.rank)
+        local = pso_cfg(cfg.dtype, cfg.objective, cfg.pso_type, bool(cfg.minimize), end - begin, cfg.dim, cfg.inertia,
+                        cfg.cognitive_coef, cfg.social_coef, cfg.eps, cfg.max_iter, cfg.best_val_no_change,
+                        bool(cfg.constrained), cfg.flags, cfg.seed, begin, n_global)
+        self.n_local, self.n_global = end - begin, n_global
+        if engine_factory is None:
+            self.stream = stream or torch.cuda.Stream(device)
+            self._scope = lambda: torch.cuda.stream(self.stream)
+            self.engine = CudaPSOEngine(local, lower, upper, device, self.stream)
+        else:
+            self.stream = _NullStream()
+            self._scope = lambda: self.stream
+            self.engine = engine_factory(local, lower, upper)
+        self.rb = record_bytes(8 if cfg.dtype == L.F64 else 4, cfg.dim)
+        with self._scope():
+            self.mine = self.engine.tensor(self.rb, torch.uint8)
+            self.all = self.engine.tensor(self.rb * self.comm.world, torch.uint8)
+            if self.comm.world > 1:   # finish the first update_best_positions across shards (nlsolver.h:2595)
+                self.engine.export_candidate(self.mine)
+                self.comm.all_gather(self.all, self.mine)
+                self.engine.apply_candidates(self.all, self.comm.world)
+
+    def step(self, n=1):
+        with self._scope():
+            if self.comm.world == 1:
+                self.engine.step(n)
+                return
+            for _ in range(n):
+                self.engine.step_local(self.mine)
+                self.comm.all_gather(self.all, self.mine)
+                self.engine.apply_candidates(self.all, self.comm.world)
+
+    def sync(self):
+        return self.engine.sync()
+
+    def best(self):
+        return self.engine.best()
+
+    def close(self):
+        self.engine.close()
+
+
 # ------------------------------------------------------------------ island DE -------------------------------------
 class IslandDE:
     """One reference-exact DE island per rank; global best by all-gather, ring migration every `migrate_every`."""
 
-    def __init__(self, cfg, x0, device=0, group=None, migrate_every=10, migrants=64, stream=None):
+    def __init__(self, cfg, x0, device=0, group=None, migrate_every=10, migrants=64, stream=None,
+                 engine_factory=None):
         import torch
 
         from . import _lib as L
-        from .solvers import Context, DEPopulation, de_cfg
+        from .solvers import de_cfg
         self.torch = torch
         self.comm = _Comm(group)
         self.migrate_every, self.k = migrate_every, min(migrants, cfg.pop_size)
-        self.stream = stream or torch.cuda.Stream(device)
-        self.ctx = Context(device, self.stream.cuda_stream)
         # islands draw from disjoint streams: global agent ids rank * P + i
         local = de_cfg(cfg.dtype, cfg.objective, cfg.strategy, bool(cfg.minimize), cfg.pop_size, cfg.dim,
                        cfg.crossover_prob, cfg.differential_weight, cfg.eps, cfg.max_iter, cfg.best_val_no_change,
                        cfg.seed, cfg.agent_offset + self.comm.rank * cfg.pop_size, cfg.flags)
         self.cfg = local
-        self.island = DEPopulation(self.ctx, local, x0)
+        if engine_factory is None:
+            self.stream = stream or torch.cuda.Stream(device)
+            self._scope = lambda: torch.cuda.stream(self.stream)
+            self.engine = CudaDEEngine(local, x0, device, self.stream)
+        else:
+            self.stream = _NullStream()
+            self._scope = lambda: self.stream
+            self.engine = engine_factory(local, x0)
+        self.island = getattr(self.engine, "pop", None)
         self.generation = 0
-        self.rb = L.lib().nls_record_bytes(cfg.dtype, cfg.dim)
-        es = 8 if cfg.dtype == L.F64 else 4
+        self.rb = record_bytes(8 if cfg.dtype == L.F64 else 4, cfg.dim)
         tdt = torch.float64 if cfg.dtype == L.F64 else torch.float32
-        dev = f"cuda:{device}"
-        with torch.cuda.stream(self.stream):
-            self.mine = torch.zeros(self.rb, dtype=torch.uint8, device=dev)
-            self.all = torch.zeros(self.rb * self.comm.world, dtype=torch.uint8, device=dev)
-            self.out_rows = torch.zeros(self.k * cfg.dim, dtype=tdt, device=dev)
-            self.out_scores = torch.zeros(self.k, dtype=tdt, device=dev)
-            self.in_rows = torch.zeros_like(self.out_rows)
-            self.in_scores = torch.zeros_like(self.out_scores)
-        self.launches = 0
-        del es
+        with self._scope():
+            self.mine = self.engine.tensor(self.rb, torch.uint8)
+            self.all = self.engine.tensor(self.rb * self.comm.world, torch.uint8)
+            self.out_rows = self.engine.tensor(self.k * cfg.dim, tdt)
+            self.out_scores = self.engine.tensor(self.k, tdt)
+            self.in_rows = self.engine.tensor(self.k * cfg.dim, tdt)
+            self.in_scores = self.engine.tensor(self.k, tdt)
+
+    @property
+    def launches(self):
+        return getattr(self.engine, "kernel_launches", 0)
 
     def step(self, n=1):
-        with self.torch.cuda.stream(self.stream):
+        with self._scope():
             for _ in range(n):
-                self.island.step(1)
+                self.engine.step(1)
                 self.generation += 1
-                self.launches += 3
-                self.island.export_best(self.mine.data_ptr())
-                self.launches += 1
+                self.engine.export_best(self.mine)
                 self.comm.all_gather(self.all, self.mine)
                 if migration_due(self.generation, self.migrate_every) and self.comm.world > 1:
-                    self.island.export_top(self.k, self.out_rows.data_ptr(), self.out_scores.data_ptr())
+                    self.engine.export_top(self.k, self.out_rows, self.out_scores)
                     self.comm.ring_exchange(self.out_rows, self.in_rows)
                     self.comm.ring_exchange(self.out_scores, self.in_scores)
-                    self.island.import_migrants(self.k, self.in_rows.data_ptr(), self.in_scores.data_ptr())
-                    self.launches += 2 * self.k + 3
+                    self.engine.import_migrants(self.k, self.in_rows, self.in_scores)
 
     def sync(self):
         """Local island status plus the global best over the last all-gather."""
-        st = self.island.sync()
+        st = self.engine.sync()
         self.stream.synchronize()
         recs = self.all.cpu().numpy()
         heads = [parse_record(recs[r * self.rb:r * self.rb + HEADER_BYTES]) for r in range(self.comm.world)]
@@ -228,5 +354,4 @@ class IslandDE:
         return raw.view(dt)[:self.cfg.dim].copy()
 
     def close(self):
-        self.island.close()
-        self.ctx.close()
+        self.engine.close()

@@ -178,3 +178,109 @@ def pso_run(lib, cfg, lower, upper, prefix=None):
 def objective(dtype, obj_id, x):
     x = np.ascontiguousarray(x, dtype=np_dtype(dtype))
     return oracle().oracle_objective(dtype, obj_id, x.ctypes.data, x.size)
+
+
+# ------------------------------------------------------------------ stepwise handles (fp64, tape) -----------------
+def _step_api(lib):
+    if getattr(lib, "_step_api_ready", False):
+        return lib
+    P = C.c_void_p
+    lib.oracle_de_open.argtypes = [C.POINTER(DECfg), P]
+    lib.oracle_de_open.restype = P
+    lib.oracle_de_advance.argtypes = [P, u64]
+    lib.oracle_de_report.argtypes = [P, C.POINTER(DEOut), C.POINTER(Status)]
+    lib.oracle_de_export_top.argtypes = [P, u64, P, P]
+    lib.oracle_de_import_migrants.argtypes = [P, u64, P, P]
+    lib.oracle_de_close.argtypes = [P]
+    lib.oracle_pso_open.argtypes = [C.POINTER(PSOCfg), P, P]
+    lib.oracle_pso_open.restype = P
+    lib.oracle_pso_evaluate.argtypes = [P, C.POINTER(f64), C.POINTER(u64)]
+    lib.oracle_pso_evaluate.restype = C.c_int
+    lib.oracle_pso_row.argtypes = [P, u64]
+    lib.oracle_pso_row.restype = C.POINTER(f64)
+    lib.oracle_pso_pbest.argtypes = [P]
+    lib.oracle_pso_pbest.restype = C.POINTER(f64)
+    lib.oracle_pso_adopt.argtypes = [P, C.c_int, f64, u64, P, u64, f64, C.c_int]
+    lib.oracle_pso_adopt.restype = C.c_int
+    lib.oracle_pso_move.argtypes = [P]
+    lib.oracle_pso_report.argtypes = [P, C.POINTER(PSOOut), C.POINTER(Status)]
+    lib.oracle_pso_close.argtypes = [P]
+    lib._step_api_ready = True
+    return lib
+
+
+class DEStepper:
+    """Generation-by-generation DE on the oracle (island tests): advance / report / export_top / import_migrants."""
+
+    def __init__(self, cfg, x0):
+        self.lib, self.cfg = _step_api(oracle()), cfg
+        x0 = np.ascontiguousarray(x0, dtype=np.float64)
+        self.h = self.lib.oracle_de_open(C.byref(cfg), x0.ctypes.data)
+        assert self.h, "oracle_de_open: fp64 tape configurations only"
+
+    def advance(self, n=1):
+        self.lib.oracle_de_advance(self.h, n)
+
+    def report(self):
+        P, d = self.cfg.pop_size, self.cfg.dim
+        a = {"x_best": np.zeros(d), "rows": np.zeros((P, d)), "scores": np.zeros(P)}
+        out = DEOut(**{k: v.ctypes.data for k, v in a.items()})
+        st = Status()
+        self.lib.oracle_de_report(self.h, C.byref(out), C.byref(st))
+        return st.as_dict(), a
+
+    def export_top(self, k):
+        rows, scores = np.zeros((k, self.cfg.dim)), np.zeros(k)
+        self.lib.oracle_de_export_top(self.h, k, rows.ctypes.data, scores.ctypes.data)
+        return rows, scores
+
+    def import_migrants(self, rows, scores):
+        rows, scores = np.ascontiguousarray(rows, np.float64), np.ascontiguousarray(scores, np.float64)
+        self.lib.oracle_de_import_migrants(self.h, scores.size, rows.ctypes.data, scores.ctypes.data)
+
+    def close(self):
+        if self.h:
+            self.lib.oracle_de_close(self.h)
+            self.h = None
+
+
+class PSOStepper:
+    """Phase-by-phase PSO shard on the oracle: evaluate -> (exchange) -> adopt -> move."""
+
+    def __init__(self, cfg, lower, upper):
+        self.lib, self.cfg = _step_api(oracle()), cfg
+        lower = np.ascontiguousarray(lower, dtype=np.float64)
+        upper = np.ascontiguousarray(upper, dtype=np.float64)
+        self.h = self.lib.oracle_pso_open(C.byref(cfg), lower.ctypes.data, upper.ctypes.data)
+        assert self.h, "oracle_pso_open: fp64 tape configurations only"
+
+    def evaluate(self):
+        """-> (has_candidate, value, local_index, row copy, pbest copy)."""
+        v, i = f64(), u64()
+        any_ = self.lib.oracle_pso_evaluate(self.h, C.byref(v), C.byref(i))
+        d, P = self.cfg.dim, self.cfg.n_particles
+        row = np.ctypeslib.as_array(self.lib.oracle_pso_row(self.h, i.value), shape=(d,)).copy()
+        pbest = np.ctypeslib.as_array(self.lib.oracle_pso_pbest(self.h), shape=(P,)).copy()
+        return bool(any_), v.value, i.value, row, pbest
+
+    def adopt(self, have, value, global_index, row, n_global, std_err_all, initial):
+        row = np.ascontiguousarray(row, np.float64)
+        return bool(self.lib.oracle_pso_adopt(self.h, int(have), value, global_index, row.ctypes.data, n_global,
+                                              std_err_all, int(initial)))
+
+    def move(self):
+        self.lib.oracle_pso_move(self.h)
+
+    def report(self):
+        P, d = self.cfg.n_particles, self.cfg.dim
+        a = {"x_best": np.zeros(d), "positions": np.zeros((P, d)), "pbest_values": np.zeros(P),
+             "last_values": np.zeros(P)}
+        out = PSOOut(**{k: v.ctypes.data for k, v in a.items()})
+        st = Status()
+        self.lib.oracle_pso_report(self.h, C.byref(out), C.byref(st))
+        return st.as_dict(), a
+
+    def close(self):
+        if self.h:
+            self.lib.oracle_pso_close(self.h)
+            self.h = None

@@ -15,9 +15,11 @@
  * Every function cites the reference lines it follows (paths are into /root/reference).
  * Build: g++ -std=c++17 -O2 -ffp-contract=off (FMA contraction changes result bits).
  */
+#include <algorithm>
 #include <cmath>
 #include <cstdint>
 #include <cstring>
+#include <limits>
 #include <vector>
 
 #include "oracle_abi.h"
@@ -165,40 +167,53 @@ size_t gen_index(T u, size_t max) {
 }
 
 /* ---------------------------------------------------------------- DE ------------------------------------- */
-
+/* DE::solve (nlsolver.h:2413-2476) cut at generation boundaries: `scan()` is the top of the while loop (best scan,
+ * val_no_change, stop test), `generation()` the body.  de_run() below strings them together exactly like the
+ * reference; the island tests call them one at a time and inject migrants in between. */
 template <class T, class Src>
-void de_run(const orc_de_cfg &c, const T *x0, Src &src, const orc_de_out *out, orc_status *st) {
-  const size_t P = c.pop_size, d = c.dim;
-  const T CR = static_cast<T>(c.crossover_prob), F = static_cast<T>(c.differential_weight);
-  const T eps = static_cast<T>(c.eps);
-  const T fm = c.minimize ? static_cast<T>(1.0) : static_cast<T>(-1.0);   /* nlsolver.h:2418 */
-  std::vector<T> A(P * d), scores(P), trial(d);
-
-  /* init_agents / generate_sequence, nlsolver.h:2302-2323: agent[j] = (g() - 0.5) * x0[j], agent-major */
-  for (size_t i = 0; i < P; i++) {
-    src.begin(0, i);
-    for (size_t j = 0; j < d; j++) A[i * d + j] = static_cast<T>((unit<T>(src.next()) - 0.5) * x0[j]);
-  }
-  for (size_t i = 0; i < P; i++) scores[i] = fm * objective<T>(c.objective, &A[i * d], d);   /* :2423-2425 */
-
-  u64 fcalls = P, iter = 0, best_id = 0, vnc = 0;
+struct DELoop {
+  const orc_de_cfg c;
+  Src src;
+  const size_t P, d;
+  const T CR, F, eps, fm;
+  std::vector<T> A, scores, trial, tscores;
+  std::vector<uint32_t> donors, dimv, rej;
+  std::vector<uint8_t> acc, masks;
+  u64 fcalls = 0, iter = 0, best_id = 0, vnc = 0;
   int stop_reason = 0;
   T se = 0;
-  std::vector<uint32_t> donors(P * 3), dimv(P), rej(P);
-  std::vector<uint8_t> acc(P), masks(out && out->masks ? P * d : 0);
-  std::vector<T> tscores(P);
 
-  while (true) {
-    bool not_updated = true;                      /* :2430-2439 */
+  DELoop(const orc_de_cfg &cfg, const T *x0, Src source, bool want_masks)
+      : c(cfg), src(source), P(cfg.pop_size), d(cfg.dim), CR(static_cast<T>(cfg.crossover_prob)),
+        F(static_cast<T>(cfg.differential_weight)), eps(static_cast<T>(cfg.eps)),
+        fm(cfg.minimize ? static_cast<T>(1.0) : static_cast<T>(-1.0)),   /* nlsolver.h:2418 */
+        A(P * d), scores(P), trial(d), tscores(P), donors(P * 3), dimv(P), rej(P), acc(P),
+        masks(want_masks ? P * d : 0) {
+    /* init_agents / generate_sequence, nlsolver.h:2302-2323: agent[j] = (g() - 0.5) * x0[j], agent-major */
+    for (size_t i = 0; i < P; i++) {
+      src.begin(0, i);
+      for (size_t j = 0; j < d; j++) A[i * d + j] = static_cast<T>((unit<T>(src.next()) - 0.5) * x0[j]);
+    }
+    for (size_t i = 0; i < P; i++) scores[i] = fm * objective<T>(c.objective, &A[i * d], d);   /* :2423-2425 */
+    fcalls = P;
+  }
+
+  /* top of the loop, nlsolver.h:2430-2447; returns true when a stop rule fires */
+  bool scan() {
+    bool not_updated = true;
     for (size_t i = 0; i < P; i++)
       if (scores[i] < scores[best_id]) { best_id = i; not_updated = false; }
     vnc = not_updated * (vnc + 1);
-    if (iter >= c.max_iter) stop_reason = 1;      /* :2441-2447, short-circuit order preserved */
+    stop_reason = 0;
+    if (iter >= c.max_iter) stop_reason = 1;      /* short-circuit order preserved */
     else if (vnc >= c.best_val_no_change) stop_reason = 2;
     else { se = std_err(scores); if (se < eps) stop_reason = 3; }
-    if (stop_reason) break;
+    return stop_reason != 0;
+  }
 
-    for (size_t i = 0; i < P; i++) {              /* :2449-2472, sequential and IN PLACE */
+  /* loop body, nlsolver.h:2449-2474: sequential and IN PLACE */
+  void generation() {
+    for (size_t i = 0; i < P; i++) {
       src.begin(iter + 1, i);
       const size_t fixed = (c.strategy == ORC_DE_RANDOM) ? i : best_id;   /* :2451-2457 */
       size_t ids[4] = {fixed, 0, 0, 0};
@@ -225,21 +240,58 @@ void de_run(const orc_de_cfg &c, const T *x0, Src &src, const orc_de_out *out, o
     iter++;
   }
 
-  if (st) {
-    st->f_value = scores[best_id]; st->iterations = iter; st->function_calls = fcalls;
-    st->best_index = best_id; st->val_no_change = vnc; st->draws_consumed = src.total;
-    st->best_valid = 1; st->stop_reason = stop_reason; st->std_err = se;
+  /* island hooks (no reference counterpart; mirror of the semantics in include/nls_b200.h):
+   * the k best agents, ascending score then ascending index ... */
+  void export_top(size_t k, T *rows, T *sc) const {
+    std::vector<size_t> order(P);
+    for (size_t i = 0; i < P; i++) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return scores[a] < scores[b]; });
+    for (size_t e = 0; e < k; e++) {
+      std::memcpy(rows + e * d, &A[order[e] * d], d * sizeof(T));
+      sc[e] = scores[order[e]];
+    }
   }
-  if (!out) return;
-  if (out->x_best) std::memcpy(out->x_best, &A[best_id * d], d * sizeof(T));
-  if (out->rows) std::memcpy(out->rows, A.data(), P * d * sizeof(T));
-  if (out->scores) std::memcpy(out->scores, scores.data(), P * sizeof(T));
-  if (out->trial_scores) std::memcpy(out->trial_scores, tscores.data(), P * sizeof(T));
-  if (out->donors) std::memcpy(out->donors, donors.data(), P * 3 * sizeof(uint32_t));
-  if (out->dim_idx) std::memcpy(out->dim_idx, dimv.data(), P * sizeof(uint32_t));
-  if (out->rejects) std::memcpy(out->rejects, rej.data(), P * sizeof(uint32_t));
-  if (out->accepted) std::memcpy(out->accepted, acc.data(), P);
-  if (out->masks) std::memcpy(out->masks, masks.data(), P * d);
+  /* ... replace the k worst (descending score, then descending index) and re-scan the best without touching the
+   * stop counters, except that an improved best resets val_no_change */
+  void import_migrants(size_t k, const T *rows, const T *sc) {
+    std::vector<size_t> order(P);
+    for (size_t i = 0; i < P; i++) order[i] = P - 1 - i;
+    std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return scores[a] > scores[b]; });
+    for (size_t e = 0; e < k; e++) {
+      std::memcpy(&A[order[e] * d], rows + e * d, d * sizeof(T));
+      scores[order[e]] = sc[e];
+    }
+    bool updated = false;
+    for (size_t i = 0; i < P; i++)
+      if (scores[i] < scores[best_id]) { best_id = i; updated = true; }
+    if (updated) vnc = 0;
+  }
+
+  void report(const orc_de_out *out, orc_status *st) const {
+    if (st) {
+      st->f_value = scores[best_id]; st->iterations = iter; st->function_calls = fcalls;
+      st->best_index = best_id; st->val_no_change = vnc; st->draws_consumed = src.total;
+      st->best_valid = 1; st->stop_reason = stop_reason; st->std_err = se;
+    }
+    if (!out) return;
+    if (out->x_best) std::memcpy(out->x_best, &A[best_id * d], d * sizeof(T));
+    if (out->rows) std::memcpy(out->rows, A.data(), P * d * sizeof(T));
+    if (out->scores) std::memcpy(out->scores, scores.data(), P * sizeof(T));
+    if (out->trial_scores) std::memcpy(out->trial_scores, tscores.data(), P * sizeof(T));
+    if (out->donors) std::memcpy(out->donors, donors.data(), P * 3 * sizeof(uint32_t));
+    if (out->dim_idx) std::memcpy(out->dim_idx, dimv.data(), P * sizeof(uint32_t));
+    if (out->rejects) std::memcpy(out->rejects, rej.data(), P * sizeof(uint32_t));
+    if (out->accepted) std::memcpy(out->accepted, acc.data(), P);
+    if (out->masks && !masks.empty()) std::memcpy(out->masks, masks.data(), P * d);
+  }
+};
+
+template <class T, class Src>
+void de_run(const orc_de_cfg &c, const T *x0, Src &src, const orc_de_out *out, orc_status *st) {
+  DELoop<T, Src> loop(c, x0, src, out && out->masks);
+  while (!loop.scan()) loop.generation();
+  loop.report(out, st);
+  src = loop.src;
 }
 
 /* ---------------------------------------------------------------- PSO ------------------------------------ */
@@ -254,55 +306,76 @@ T rnorm(T u_log, T u_cos) {
                         std::cos(static_cast<double>(2 * pi_ * u_cos)));
 }
 
+/* PSO::solve (nlsolver.h:2592-2624) cut into its phases.  A shard owns particles [offset, offset + P) of a global
+ * swarm: `evaluate()` is the per-particle part of update_best_positions and returns the shard's strict-< candidate,
+ * `adopt()` the swarm-level part (called with the winner over all shards), `move()` the position update. */
 template <class T, class Src>
-void pso_run(const orc_pso_cfg &c, const T *lower, const T *upper, Src &src, const orc_pso_out *out,
-             orc_status *st) {
-  const size_t P = c.n_particles, d = c.dim;
-  const bool vanilla = c.pso_type == ORC_PSO_VANILLA;
-  const T init_inertia = static_cast<T>(c.inertia);
-  T inertia = init_inertia;
-  const T cog = static_cast<T>(c.cognitive_coef), soc = static_cast<T>(c.social_coef);
-  const T eps = static_cast<T>(c.eps);
-  const T fm = c.minimize ? static_cast<T>(1.0) : static_cast<T>(-1.0);
-  std::vector<T> X(P * d), V(vanilla ? P * d : 0), pbest(P, static_cast<T>(10000)), last(P), sbest;
-  T sbest_val = static_cast<T>(100000.0);          /* init_solver_state, nlsolver.h:2626-2657 */
+struct PSOLoop {
+  const orc_pso_cfg c;
+  Src src;
+  const size_t P, d;
+  const bool vanilla;
+  const T init_inertia, cog, soc, eps, fm;
+  T inertia;
+  std::vector<T> lower, upper, X, V, pbest, last, sbest;
+  T sbest_val = static_cast<T>(100000.0);          /* init_solver_state, nlsolver.h:2631 */
   u64 f_evals = 0, vnc = 0, iter = 0, sbest_idx = 0;
-  for (size_t i = 0; i < P; i++) {
-    src.begin(0, i);
-    for (size_t j = 0; j < d; j++) {
-      const T temp = std::abs(upper[j] - lower[j]);
-      X[i * d + j] = lower[j] + ((upper[j] - lower[j]) * unit<T>(src.next()));
-      if (vanilla) V[i * d + j] = -temp + (unit<T>(src.next()) * temp);
+  int stop_reason = 0;
+  T se = 0;
+
+  PSOLoop(const orc_pso_cfg &cfg, const T *lo, const T *up, Src source)
+      : c(cfg), src(source), P(cfg.n_particles), d(cfg.dim), vanilla(cfg.pso_type == ORC_PSO_VANILLA),
+        init_inertia(static_cast<T>(cfg.inertia)), cog(static_cast<T>(cfg.cognitive_coef)),
+        soc(static_cast<T>(cfg.social_coef)), eps(static_cast<T>(cfg.eps)),
+        fm(cfg.minimize ? static_cast<T>(1.0) : static_cast<T>(-1.0)), inertia(init_inertia),
+        lower(lo, lo + d), upper(up, up + d), X(P * d), V(vanilla ? P * d : 0), pbest(P, static_cast<T>(10000)),
+        last(P) {
+    for (size_t i = 0; i < P; i++) {               /* init_solver_state, nlsolver.h:2626-2657 */
+      src.begin(0, i);
+      for (size_t j = 0; j < d; j++) {
+        const T temp = std::abs(upper[j] - lower[j]);
+        X[i * d + j] = lower[j] + ((upper[j] - lower[j]) * unit<T>(src.next()));
+        if (vanilla) V[i * d + j] = -temp + (unit<T>(src.next()) * temp);
+      }
     }
   }
-  auto update_best = [&]() {                        /* update_best_positions, :2716-2741 */
-    size_t best_index = 0;
-    bool update_happened = false;
+  /* per-particle part of update_best_positions, :2721-2733; candidate = lowest value, lowest index on ties */
+  bool evaluate(T *cand_value, size_t *cand_local) {
+    bool any = false;
     for (size_t i = 0; i < P; i++) {
       const T temp = fm * objective<T>(c.objective, &X[i * d], d);
       last[i] = temp;
-      if (temp < sbest_val) { sbest_val = temp; best_index = i; update_happened = true; }
       if (temp < pbest[i]) pbest[i] = temp;
+      if (!any ? temp < std::numeric_limits<T>::infinity() : temp < *cand_value) { *cand_value = temp; *cand_local = i; any = true; }
     }
-    f_evals += P;
-    if (update_happened) { sbest.assign(&X[best_index * d], &X[best_index * d] + d); sbest_idx = best_index; }
+    return any;
+  }
+  /* swarm-level part, :2723-2740: `value` / `global_index` / `row` describe the best candidate over all shards
+   * (have = false if no shard had one) */
+  void adopt(bool have, T value, u64 global_index, const T *row, size_t n_global) {
+    u64 best_index = 0;
+    if (have && value < sbest_val) { sbest_val = value; best_index = global_index; sbest.assign(row, row + d); sbest_idx = global_index; }
+    f_evals += n_global;
     vnc = (best_index == 0) * (vnc + 1);
-  };
-  update_best();                                    /* solve, :2592-2624 */
-  int stop_reason = 0;
-  T se = 0;
-  while (true) {
+  }
+  /* top of the loop, :2599-2600, with the std_err of ALL particle_best_values (moments supplied by the caller for a
+   * sharded swarm, computed here for a whole one) */
+  bool stop_test(T std_err_all) {
+    stop_reason = 0;
     if (iter >= c.max_iter) stop_reason = 1;
     else if (vnc >= c.best_val_no_change) stop_reason = 2;
-    else { se = std_err(pbest); if (se < eps) stop_reason = 3; }
-    if (stop_reason) break;
+    else { se = std_err_all; if (se < eps) stop_reason = 3; }
+    return stop_reason != 0;
+  }
+  void move() {
     if (vanilla) {                                  /* update_velocities, :2658-2677 (both quirks kept) */
       for (size_t i = 0; i < P; i++) {
         src.begin(iter + 1, i);
+        const size_t gi = c.particle_offset + i;
         for (size_t j = 0; j < d; j++) {
           const T r_p = unit<T>(src.next()), r_g = unit<T>(src.next());
           const T x = X[i * d + j];
-          const T sb = sbest.empty() ? static_cast<T>(0) : sbest[c.social_index_j ? j : i];
+          const T sb = sbest.empty() ? static_cast<T>(0) : sbest[c.social_index_j ? j : gi];
           V[i * d + j] = (inertia * V[i * d + j]) + cog * r_p * (x - x) + soc * r_g * (sb - x);
         }
       }
@@ -325,20 +398,39 @@ void pso_run(const orc_pso_cfg &c, const T *lower, const T *upper, Src &src, con
           p = p < lower[j] ? lower[j] : p;
           p = p > upper[j] ? upper[j] : p;
         }
+  }
+  void report(const orc_pso_out *out, orc_status *st) const {
+    if (st) {
+      st->f_value = sbest_val; st->iterations = iter; st->function_calls = f_evals;
+      st->best_index = sbest_idx; st->val_no_change = vnc; st->draws_consumed = src.total;
+      st->best_valid = !sbest.empty(); st->stop_reason = stop_reason; st->std_err = se;
+    }
+    if (!out) return;
+    if (out->x_best && !sbest.empty()) std::memcpy(out->x_best, sbest.data(), d * sizeof(T));
+    if (out->positions) std::memcpy(out->positions, X.data(), P * d * sizeof(T));
+    if (out->velocities && vanilla) std::memcpy(out->velocities, V.data(), P * d * sizeof(T));
+    if (out->pbest_values) std::memcpy(out->pbest_values, pbest.data(), P * sizeof(T));
+    if (out->last_values) std::memcpy(out->last_values, last.data(), P * sizeof(T));
+  }
+};
+
+template <class T, class Src>
+void pso_run(const orc_pso_cfg &c, const T *lower, const T *upper, Src &src, const orc_pso_out *out,
+             orc_status *st) {
+  PSOLoop<T, Src> loop(c, lower, upper, src);
+  auto update_best = [&]() {                        /* update_best_positions, :2716-2741 */
+    T v = 0; size_t i = 0;
+    const bool any = loop.evaluate(&v, &i);
+    loop.adopt(any, v, c.particle_offset + i, any ? &loop.X[i * loop.d] : nullptr, loop.P);
+  };
+  update_best();                                    /* solve, :2592-2624 */
+  while (!loop.stop_test(std_err(loop.pbest))) {
+    loop.move();
     update_best();
-    iter++;
+    loop.iter++;
   }
-  if (st) {
-    st->f_value = sbest_val; st->iterations = iter; st->function_calls = f_evals;
-    st->best_index = sbest_idx; st->val_no_change = vnc; st->draws_consumed = src.total;
-    st->best_valid = !sbest.empty(); st->stop_reason = stop_reason; st->std_err = se;
-  }
-  if (!out) return;
-  if (out->x_best && !sbest.empty()) std::memcpy(out->x_best, sbest.data(), d * sizeof(T));
-  if (out->positions) std::memcpy(out->positions, X.data(), P * d * sizeof(T));
-  if (out->velocities && vanilla) std::memcpy(out->velocities, V.data(), P * d * sizeof(T));
-  if (out->pbest_values) std::memcpy(out->pbest_values, pbest.data(), P * sizeof(T));
-  if (out->last_values) std::memcpy(out->last_values, last.data(), P * sizeof(T));
+  loop.report(out, st);
+  src = loop.src;
 }
 
 template <class T>
@@ -370,6 +462,51 @@ int oracle_pso_run(const orc_pso_cfg *c, const void *lower, const void *upper, c
                              : pso_dispatch<float>(c, lower, upper, out, st);
 }
 /* PSO::minimize(x) without bounds derives lower = -|x|, upper = |x| (nlsolver.h:2553-2563); callers do that. */
+
+/* ---- stepwise handles (fp64 tape only): what the world_size-2 CPU tests drive through nlsolver_b200.distributed ---- */
+typedef DELoop<double, TapeSource> DEHandle;
+typedef PSOLoop<double, TapeSource> PSOHandle;
+
+void *oracle_de_open(const orc_de_cfg *c, const double *x0) {
+  if (c->dtype != ORC_F64 || c->rng_mode != ORC_RNG_TAPE || c->pop_size < 4 || c->dim < 1) return nullptr;
+  DEHandle *h = new DEHandle(*c, x0, TapeSource(c->seed, c->agent_offset), false);
+  h->scan();
+  return h;
+}
+/* n generations, each followed by the next loop-top scan; stops early when a stop rule has fired */
+void oracle_de_advance(void *p, uint64_t n) {
+  DEHandle *h = static_cast<DEHandle *>(p);
+  for (uint64_t g = 0; g < n && !h->stop_reason; g++) { h->generation(); h->scan(); }
+}
+void oracle_de_report(void *p, const orc_de_out *out, orc_status *st) { static_cast<DEHandle *>(p)->report(out, st); }
+void oracle_de_export_top(void *p, uint64_t k, double *rows, double *scores) { static_cast<DEHandle *>(p)->export_top(k, rows, scores); }
+void oracle_de_import_migrants(void *p, uint64_t k, const double *rows, const double *scores) { static_cast<DEHandle *>(p)->import_migrants(k, rows, scores); }
+void oracle_de_close(void *p) { delete static_cast<DEHandle *>(p); }
+
+void *oracle_pso_open(const orc_pso_cfg *c, const double *lower, const double *upper) {
+  if (c->dtype != ORC_F64 || c->rng_mode != ORC_RNG_TAPE) return nullptr;
+  return new PSOHandle(*c, lower, upper, TapeSource(c->seed, c->particle_offset));
+}
+/* evaluate this shard; returns 1 and the candidate (value, local index) if it has one */
+int oracle_pso_evaluate(void *p, double *value, uint64_t *local_index) {
+  size_t i = 0;
+  const bool any = static_cast<PSOHandle *>(p)->evaluate(value, &i);
+  *local_index = i;
+  return any;
+}
+const double *oracle_pso_row(void *p, uint64_t local_index) { PSOHandle *h = static_cast<PSOHandle *>(p); return &h->X[local_index * h->d]; }
+const double *oracle_pso_pbest(void *p) { return static_cast<PSOHandle *>(p)->pbest.data(); }
+/* swarm-level update with the winner over all shards, then iter++ (unless initial) and the stop test */
+int oracle_pso_adopt(void *p, int have, double value, uint64_t global_index, const double *row, uint64_t n_global,
+                     double std_err_all, int initial) {
+  PSOHandle *h = static_cast<PSOHandle *>(p);
+  h->adopt(have != 0, value, global_index, row, n_global);
+  if (!initial) h->iter++;
+  return h->stop_test(std_err_all);
+}
+void oracle_pso_move(void *p) { static_cast<PSOHandle *>(p)->move(); }
+void oracle_pso_report(void *p, const orc_pso_out *out, orc_status *st) { static_cast<PSOHandle *>(p)->report(out, st); }
+void oracle_pso_close(void *p) { delete static_cast<PSOHandle *>(p); }
 
 double oracle_objective(int dtype, int id, const void *x, uint64_t d) {
   return dtype == ORC_F64 ? objective<double>(id, static_cast<const double *>(x), d)

@@ -1,0 +1,78 @@
+"""Island hooks on the GPU (export_best / export_top / import_migrants through the C ABI) against the oracle steppers:
+two islands on one GPU with an explicit ring exchange == the harness-level restatement."""
+import numpy as np
+import pytest
+
+import nlsolver_b200 as nb
+from nlsolver_b200 import distributed as D
+from oracle import binding as B
+from tests.cpu_engines import oracle_de_cfg
+from tests.gpu_util import bits
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("obj,strategy,P,d", [(nb.ROSENBROCK, nb.DE_BEST, 300, 12), (nb.SPHERE, nb.DE_RANDOM, 1000, 33)])
+def test_two_islands_with_ring_migration_match_restatement(obj, strategy, P, d):
+    import torch
+    world, every, k, gens = 2, 3, 5, 8
+    stream = torch.cuda.Stream()
+    ctx = nb.Context(0, stream.cuda_stream)
+    kw = dict(objective=obj, strategy=strategy, pop_size=P, dim=d, eps=0.0, max_iter=1 << 40,
+              best_val_no_change=1 << 40, seed=21)
+    x0 = np.full(d, 4.096)
+    gpu = [nb.DEPopulation(ctx, nb.de_cfg(**dict(kw, agent_offset=r * P)), x0) for r in range(world)]
+    cpu = [B.DEStepper(oracle_de_cfg(nb.de_cfg(**dict(kw, agent_offset=r * P))), x0) for r in range(world)]
+    with torch.cuda.stream(stream):
+        rows = [torch.zeros(k * d, dtype=torch.float64, device="cuda") for _ in range(world)]
+        scores = [torch.zeros(k, dtype=torch.float64, device="cuda") for _ in range(world)]
+        rec = torch.zeros(nb.lib().nls_record_bytes(nb.F64, d), dtype=torch.uint8, device="cuda")
+        for g in range(1, gens + 1):
+            for s in gpu:
+                s.step(1)
+            for s in cpu:
+                s.advance(1)
+            if D.migration_due(g, every):
+                for r in range(world):
+                    gpu[r].export_top(k, rows[r].data_ptr(), scores[r].data_ptr())
+                out = [s.export_top(k) for s in cpu]
+                for r in range(world):
+                    src = D.ring_neighbors(r, world)[1]
+                    assert np.array_equal(bits(rows[src].cpu().numpy().reshape(k, d)), bits(out[src][0]))
+                    assert np.array_equal(bits(scores[src].cpu().numpy()), bits(out[src][1]))
+                    gpu[r].import_migrants(k, rows[src].data_ptr(), scores[src].data_ptr())
+                    cpu[r].import_migrants(*out[src])
+            for r in range(world):
+                st = gpu[r].sync()
+                so, ao = cpu[r].report()
+                assert np.array_equal(bits(gpu[r].population()), bits(ao["rows"])), (g, r)
+                assert np.array_equal(bits(gpu[r].scores()), bits(ao["scores"])), (g, r)
+                for key in ("f_value", "iterations", "function_calls", "best_index", "val_no_change"):
+                    assert st[key] == so[key], (g, r, key, st[key], so[key])
+        # the exported record carries the island best
+        gpu[1].export_best(rec.data_ptr())
+        stream.synchronize()
+        raw = rec.cpu().numpy()
+        h = D.parse_record(raw)
+        so, ao = cpu[1].report()
+        assert h["valid"] == 1 and h["value"] == so["f_value"] and h["index"] == P + so["best_index"]
+        assert np.array_equal(bits(raw[D.HEADER_BYTES:].view(np.float64)[:d]), bits(ao["x_best"]))
+        assert h["n"] == P and abs(D.std_err_from_moments(h["n"], h["mean"], h["m2"]) - ao["scores"].std(ddof=1)) < 1e-9
+    for s in gpu:
+        s.close()
+    ctx.close()
+
+
+def test_island_de_single_rank_wrapper_runs():
+    """IslandDE at world size 1 (what bench.py drives at --gpus 1): plain DE plus the per-generation best export."""
+    d, P, gens = 40, 2000, 6
+    cfg = nb.de_cfg(objective=nb.RASTRIGIN, pop_size=P, dim=d, eps=0.0, max_iter=1 << 40, best_val_no_change=1 << 40, seed=9)
+    isl = D.IslandDE(cfg, np.full(d, 10.24), device=0, migrate_every=2, migrants=4)
+    isl.step(gens)
+    st = isl.sync()
+    so, ao = B.de_run(B.oracle(), B.de_cfg(objective=B.RASTRIGIN, pop_size=P, dim=d, eps=0.0, max_iter=gens,
+                                           best_val_no_change=1 << 40, seed=9), np.full(d, 10.24))
+    assert st["iterations"] == gens and st["best_index"] == so["best_index"]
+    assert abs(st["global_best_value"] - so["f_value"]) <= 1e-12 * abs(so["f_value"]) and st["global_best_rank"] == 0
+    assert np.allclose(isl.global_best_row(), ao["x_best"], rtol=1e-12, atol=0)
+    isl.close()
