@@ -317,6 +317,12 @@ class IslandDE:
             self.out_scores = self.engine.tensor(self.k, tdt)
             self.in_rows = self.engine.tensor(self.k * cfg.dim, tdt)
             self.in_scores = self.engine.tensor(self.k, tdt)
+            if self.comm.world > 1:
+                # NCCL builds its collective and point-to-point channels lazily (seconds): do it here, not in the
+                # first generation / first migration
+                self.comm.all_gather(self.all, self.mine)
+                self.comm.ring_exchange(self.out_rows, self.in_rows)
+                self.comm.ring_exchange(self.out_scores, self.in_scores)
 
     @property
     def launches(self):
