@@ -112,6 +112,9 @@ NLS_API int nls_version(void);
 /* stream: a cudaStream_t to enqueue on (e.g. torch's current stream), or NULL for a stream owned by the context */
 NLS_API int nls_ctx_create(int device, void *stream, nls_ctx **out);
 NLS_API int nls_ctx_destroy(nls_ctx *ctx);
+/* A context caches the device buffers of destroyed solver handles for the next solve of the same shape (allocating
+ * and freeing multi-GB populations costs hundreds of milliseconds); nls_ctx_trim returns them to the driver. */
+NLS_API int nls_ctx_trim(nls_ctx *ctx);
 NLS_API int nls_ctx_device(const nls_ctx *ctx);
 NLS_API int nls_ctx_sm_count(const nls_ctx *ctx);
 

@@ -58,6 +58,7 @@ SYMBOLS = {
     "nls_version": (C.c_int, []),
     "nls_ctx_create": (C.c_int, [C.c_int, P, C.POINTER(P)]),
     "nls_ctx_destroy": (C.c_int, [P]),
+    "nls_ctx_trim": (C.c_int, [P]),
     "nls_ctx_device": (C.c_int, [P]),
     "nls_ctx_sm_count": (C.c_int, [P]),
     "nls_de_solve": (C.c_int, [P, C.POINTER(DECfg), P, P, C.POINTER(Status)]),

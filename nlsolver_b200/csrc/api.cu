@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/nls_b200.h"
@@ -68,19 +69,48 @@ struct nls_ctx {
   cudaStream_t stream;
   bool own_stream;
   int sm_count;
+  // Device buffers released by destroyed solver handles, kept for the next solve of the same shape: cudaMalloc /
+  // cudaFree of multi-GB populations cost hundreds of milliseconds, which would dominate repeated minimize() calls.
+  std::vector<std::pair<void *, size_t>> pool;
+  size_t pool_bytes = 0;
 };
 
 namespace {
 
 struct DeviceBuffers {
-  std::vector<void *> ptrs;
+  nls_ctx *ctx = nullptr;
+  std::vector<std::pair<void *, size_t>> held;
   int alloc(void **out, size_t bytes) {
     *out = nullptr;
-    NLS_CUDA(cudaMalloc(out, bytes ? bytes : 1));
-    ptrs.push_back(*out);
+    bytes = bytes ? bytes : 1;
+    if (ctx)
+      for (size_t k = 0; k < ctx->pool.size(); k++)
+        if (ctx->pool[k].second == bytes) {
+          *out = ctx->pool[k].first;
+          ctx->pool_bytes -= bytes;
+          ctx->pool.erase(ctx->pool.begin() + k);
+          held.push_back({*out, bytes});
+          return NLS_OK;
+        }
+    cudaError_t e = cudaMalloc(out, bytes);
+    if (e == cudaErrorMemoryAllocation && ctx && !ctx->pool.empty()) {   // make room: drop the cached buffers, retry
+      cudaGetLastError();
+      for (auto &b : ctx->pool) cudaFree(b.first);
+      ctx->pool.clear();
+      ctx->pool_bytes = 0;
+      e = cudaMalloc(out, bytes);
+    }
+    NLS_CUDA(e);
+    held.push_back({*out, bytes});
     return NLS_OK;
   }
-  void release() { for (void *p : ptrs) cudaFree(p); ptrs.clear(); }
+  void release() {
+    for (auto &b : held) {
+      if (ctx) { ctx->pool.push_back(b); ctx->pool_bytes += b.second; }
+      else cudaFree(b.first);
+    }
+    held.clear();
+  }
 };
 
 LaunchGeom make_geom(const nls_ctx *ctx, u64 n) {
@@ -158,8 +188,18 @@ int nls_ctx_create(int device, void *stream, nls_ctx **out) {
 int nls_ctx_destroy(nls_ctx *ctx) {
   if (!ctx) return NLS_OK;
   cudaSetDevice(ctx->device);
+  for (auto &b : ctx->pool) cudaFree(b.first);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
+  return NLS_OK;
+}
+int nls_ctx_trim(nls_ctx *ctx) {
+  if (!ctx) return fail(NLS_ERR_INVALID, "nls_ctx_trim: NULL context");
+  NLS_CUDA(cudaSetDevice(ctx->device));
+  NLS_CUDA(cudaStreamSynchronize(ctx->stream));
+  for (auto &b : ctx->pool) cudaFree(b.first);
+  ctx->pool.clear();
+  ctx->pool_bytes = 0;
   return NLS_OK;
 }
 int nls_ctx_device(const nls_ctx *ctx) { return ctx ? ctx->device : -1; }
@@ -194,6 +234,7 @@ int nls_de_destroy(nls_de *de) {
 static int de_build(nls_ctx *ctx, const nls_de_cfg *cfg, const void *x0_host, nls_de *de) {
   const u64 P = cfg->pop_size, d = cfg->dim;
   de->ctx = ctx;
+  de->mem.ctx = ctx;
   de->cfg = *cfg;
   de->timing = false;
   de->timed_ms[0] = de->timed_ms[1] = de->timed_ms[2] = 0.0;
@@ -476,6 +517,7 @@ int nls_pso_destroy(nls_pso *pso) {
 static int pso_build(nls_ctx *ctx, const nls_pso_cfg *cfg, const void *lower, const void *upper, nls_pso *p) {
   const u64 P = cfg->n_particles, d = cfg->dim;
   p->ctx = ctx;
+  p->mem.ctx = ctx;
   p->cfg = *cfg;
   p->elem = elem_size(cfg->dtype);
   p->ops = cfg->dtype == NLS_F64 ? pso_ops_f64() : pso_ops_f32();

@@ -86,6 +86,10 @@ class Context:
     def sm_count(self):
         return L.lib().nls_ctx_sm_count(self._h)
 
+    def trim(self):
+        """Return the cached device buffers of finished solves to the driver."""
+        L.check(L.lib().nls_ctx_trim(self._h))
+
     def close(self):
         if self._h:
             L.lib().nls_ctx_destroy(self._h)
