@@ -542,8 +542,8 @@ static int pso_build(nls_ctx *ctx, const nls_pso_cfg *cfg, const void *lower, co
   NLS_ALLOC(s.pbest, P * p->elem);
   NLS_ALLOC(s.last, P * p->elem);
   NLS_ALLOC(s.sbest, s.stride * p->elem);
-  NLS_ALLOC(s.lower, d * p->elem);
-  NLS_ALLOC(s.upper, d * p->elem);
+  NLS_ALLOC(s.lower, s.stride * p->elem);   // padded like a row: the move kernel reads bounds with 128-bit loads
+  NLS_ALLOC(s.upper, s.stride * p->elem);
   NLS_ALLOC(s.ctrl, sizeof(PSOCtrl));
   NLS_ALLOC(s.part_min, p->g.reduce_blocks * sizeof(double));
   NLS_ALLOC(s.part_idx, p->g.reduce_blocks * sizeof(unsigned long long));
@@ -557,6 +557,8 @@ static int pso_build(nls_ctx *ctx, const nls_pso_cfg *cfg, const void *lower, co
   NLS_CUDA(cudaMemcpyAsync(s.ctrl, &c0, sizeof(c0), cudaMemcpyHostToDevice, st));
   NLS_CUDA(cudaMemsetAsync(s.sbest, 0, s.stride * p->elem, st));
   NLS_CUDA(cudaMemsetAsync(p->record, 0, p->record_bytes, st));
+  NLS_CUDA(cudaMemsetAsync(s.lower, 0, s.stride * p->elem, st));
+  NLS_CUDA(cudaMemsetAsync(s.upper, 0, s.stride * p->elem, st));
   NLS_CUDA(cudaMemcpyAsync(s.lower, lower, d * p->elem, cudaMemcpyHostToDevice, st));
   NLS_CUDA(cudaMemcpyAsync(s.upper, upper, d * p->elem, cudaMemcpyHostToDevice, st));
   NLS_CUDA(cudaStreamSynchronize(st));               // c0 lives on this stack frame
