@@ -269,6 +269,8 @@ static int de_build(nls_ctx *ctx, const nls_de_cfg *cfg, const void *x0_host, nl
   NLS_ALLOC(s.dec, P * sizeof(uint4));
   NLS_ALLOC(s.rej, P * sizeof(uint32_t));
   NLS_ALLOC(s.list, P * sizeof(uint32_t));
+  NLS_ALLOC(s.pend[0], P * sizeof(uint32_t));
+  NLS_ALLOC(s.pend[1], P * sizeof(uint32_t));
   NLS_ALLOC(s.ctrl, sizeof(DECtrl));
   NLS_ALLOC(s.part_min, de->g.reduce_blocks * sizeof(double));
   NLS_ALLOC(s.part_idx, de->g.reduce_blocks * sizeof(unsigned long long));

@@ -120,7 +120,6 @@ __device__ __forceinline__ void de_trial(const DEState &s, u64 i, u64 key, u64 r
   if (lane == 0) {
     static_cast<T *>(s.tscore)[i] = score;
     s.acc[i] = ok;
-    if (!RESOLVED && ok) atomicAdd(&s.ctrl->spec_accepted, 1u);   // a few % of agents at most
   }
 }
 
@@ -177,26 +176,96 @@ __device__ __forceinline__ void de_select_donors(u64 key, u64 P, u64 fixed, u64 
 #ifndef NLS_DE_MINBLOCKS
 #define NLS_DE_MINBLOCKS 4
 #endif
+// What the lane-parallel prologue hands to the cooperative part, one entry per agent of the tile (shared memory).
+struct __align__(16) DETileEntry {
+  unsigned long long key;      // draw stream of (generation, agent)
+  unsigned int r1, r2, r3;     // donors ids[1..3]
+  unsigned int dim;            // forced crossover coordinate
+  unsigned int rej;            // rejected index proposals
+  unsigned int wbits;          // where[] of ids[0], r1, r2, r3 and of the agent itself (bits 0..4)
+  double score;                // scores[i] (T widened)
+};
+
+// A warp owns a TILE of 32 consecutive agents:
+//   prologue  — one agent per lane: stream key, donor selection, forced coordinate, row-location bits, current score;
+//               the per-agent scalar work and its dependent loads run 32 agents wide instead of 32 times redundantly;
+//   body      — the 32 agents one after the other, all lanes streaming the rows of one agent (de_sweep);
+//   epilogue  — one agent per lane again: coalesced stores of trial score / accept flag.
+// The tile size (2^tile_shift <= 32 agents) is chosen by the launcher so that every warp gets many tiles: with 32-agent
+// tiles a population of 2^18 would give 1.7 tiles per resident warp and a 15 % tail.
 template <class T, int OBJ>
-__global__ void __launch_bounds__(kBlock, NLS_DE_MINBLOCKS) de_generation_kernel(DEState s) {
-  const DECtrl *ctrl = s.ctrl;
+__global__ void __launch_bounds__(kBlock, NLS_DE_MINBLOCKS) de_generation_kernel(DEState s, int tile_shift) {
+  __shared__ DETileEntry tile_mem[kWarpsPerBlock][32];
+  DECtrl *ctrl = s.ctrl;
   if (ctrl->stop) return;
   const int lane = threadIdx.x & 31;
+  DETileEntry *tile_entries = tile_mem[threadIdx.x >> 5];
   const u64 warp = (u64(blockIdx.x) * kBlock + threadIdx.x) >> 5, n_warps = (u64(gridDim.x) * kBlock) >> 5;
   const u64 gen_key = tape_gen_key(s.seed, ctrl->iter + 1), best_id = ctrl->best_id;
-  for (u64 i = warp; i < s.P; i += n_warps) {
-    const u64 key = tape_key(gen_key, s.offset + i);
-    const u64 fixed = s.strategy ? i : best_id;         // NLS_DE_RANDOM = 1: ids[0] = i; best: ids[0] = best_id
-    u64 r1, r2, r3;
-    u32 rej;
-    de_select_donors<T>(key, s.P, fixed, r1, r2, r3, rej);
-    const u32 dim = static_cast<u32>(index_from<T>(tape_draw(key, 3 + rej), s.d));
-    if (lane == 0) {
-      s.dec[i] = make_uint4(u32(r1), u32(r2), u32(r3), dim);
-      s.rej[i] = rej;
-      s.fin[i] = 0;
+  const bool random_mode = s.strategy != 0;             // NLS_DE_RANDOM = 1: ids[0] = i; best: ids[0] = best_id
+  const u64 P = s.P, tile_size = 1ull << tile_shift, n_tiles = (P + tile_size - 1) >> tile_shift;
+  const T *score = static_cast<const T *>(s.score);
+  for (u64 tile = warp; tile < n_tiles; tile += n_warps) {
+    const u64 first = tile << tile_shift, mine = first + lane;
+    const bool own = lane < int(tile_size) && mine < P;   // this lane carries an agent in the prologue / epilogue
+    // ---- prologue
+    bool level0 = true;
+    if (own) {
+      DETileEntry e;
+      e.key = tape_key(gen_key, s.offset + mine);
+      const u64 fixed = random_mode ? mine : best_id;
+      u64 r1, r2, r3;
+      de_select_donors<T>(e.key, P, fixed, r1, r2, r3, e.rej);
+      e.dim = static_cast<u32>(index_from<T>(tape_draw(e.key, 3 + e.rej), s.d));
+      e.r1 = u32(r1); e.r2 = u32(r2); e.r3 = u32(r3);
+      e.wbits = u32(s.where[fixed]) | (u32(s.where[r1]) << 1) | (u32(s.where[r2]) << 2) | (u32(s.where[r3]) << 3) |
+                (u32(s.where[mine]) << 4);
+      e.score = static_cast<double>(score[mine]);
+      tile_entries[lane] = e;
+      s.dec[mine] = make_uint4(e.r1, e.r2, e.r3, e.dim);
+      s.rej[mine] = e.rej;
+      // agents without a lower donor are final as they stand: repair round 1 is decided here
+      level0 = r1 > mine && r2 > mine && r3 > mine && (random_mode || best_id >= mine);
+      s.fin[mine] = level0 ? 1 : 0;
     }
-    de_trial<T, OBJ, false>(s, i, key, fixed, r1, r2, r3, dim, rej, lane);
+    {   // everybody else goes on the repair's first pending list (order is irrelevant)
+      const u32 vote = __ballot_sync(kFull, own && !level0);
+      if (vote) {
+        u32 slot = 0;
+        if (lane == 0) slot = atomicAdd(&ctrl->pending[1], __popc(vote));   // consumed by repair round 2
+        slot = __shfl_sync(kFull, slot, 0);
+        if (own && !level0) s.pend[0][slot + __popc(vote & ((1u << lane) - 1u))] = u32(mine);
+      }
+    }
+    __syncwarp();
+    // ---- body
+    const int n_here = (P - first) < tile_size ? int(P - first) : int(tile_size);
+    T my_score = T(0);
+    bool my_ok = false;
+    for (int a = 0; a < n_here; a++) {
+      const DETileEntry e = tile_entries[a];              // broadcast read
+      const u64 i = first + a;
+      const u64 r0 = random_mode ? i : best_id;
+      const T *p0 = static_cast<const T *>(s.buf[e.wbits & 1u]) + r0 * s.stride;
+      const T *p1 = static_cast<const T *>(s.buf[(e.wbits >> 1) & 1u]) + u64(e.r1) * s.stride;
+      const T *p2 = static_cast<const T *>(s.buf[(e.wbits >> 2) & 1u]) + u64(e.r2) * s.stride;
+      const T *p3 = static_cast<const T *>(s.buf[(e.wbits >> 3) & 1u]) + u64(e.r3) * s.stride;
+      T *dst = static_cast<T *>(s.buf[((e.wbits >> 4) & 1u) ^ 1u]) + i * s.stride;
+      const u64 sbase = tape_state(e.key, 4 + e.rej);
+      const T raw = de_sweep<T, OBJ, true, false>(s, p0, p1, p2, p3, dst, sbase, e.dim, i, lane);
+      const T sc = Ar<T>::mul(static_cast<T>(s.fm), raw);
+      const bool ok = sc < static_cast<T>(e.score);       // strict <, NaN never accepted (nlsolver.h:2466)
+      if (ok) de_sweep<T, OBJ, false, true>(s, p0, p1, p2, p3, dst, sbase, e.dim, i, lane);
+      if (lane == a) { my_score = sc; my_ok = ok; }
+    }
+    // ---- epilogue
+    if (own) {
+      static_cast<T *>(s.tscore)[mine] = my_score;
+      s.acc[mine] = my_ok;
+    }
+    const u32 n_ok = __popc(__ballot_sync(kFull, my_ok));
+    if (lane == 0 && n_ok) atomicAdd(&ctrl->spec_accepted, n_ok);
+    __syncwarp();                                          // tile_entries is rewritten by the next tile's prologue
   }
 }
 
@@ -206,26 +275,34 @@ __global__ void __launch_bounds__(kBlock) de_repair_kernel(DEState s) {
   cg::grid_group grid = cg::this_grid();
   DECtrl *ctrl = s.ctrl;
   if (ctrl->stop) return;                                // uniform over the grid: only K3 changes it
+  // If the speculative pass accepted nothing, no row changed and every speculative result already equals the
+  // sequential one (induction over the agent index) — nothing to repair.
+  if (*reinterpret_cast<volatile unsigned int *>(&ctrl->spec_accepted) == 0) return;
   const int lane = threadIdx.x & 31;
   const u64 tid = u64(blockIdx.x) * kBlock + threadIdx.x, n_threads = u64(gridDim.x) * kBlock;
   const u64 warp = tid >> 5, n_warps = n_threads >> 5;
   const u64 gen_key = tape_gen_key(s.seed, ctrl->iter + 1), best_id = ctrl->best_id;
   const bool best_mode = s.strategy == 0;
-  // If the speculative pass accepted nothing, no row changed and every speculative result already equals the
-  // sequential one (induction over the agent index) — nothing to repair.
-  if (*reinterpret_cast<volatile unsigned int *>(&ctrl->spec_accepted) == 0) return;
-  u32 reruns = 0, round = 1;
+  u32 reruns = 0, round = 2;                             // round 1 (agents without lower donors) was decided by K2
+  // Round r consumes the pending list produced by round r - 1 (buffer pend[r & 1], length pending[(r - 1) % 3]; K2
+  // produced the first one) and produces pend[(r & 1) ^ 1] / pending[r % 3] plus the re-evaluation list
+  // list / list_count[r % 3].  Three counter slots let thread 0 recycle slot (r + 1) % 3 between the two barriers of
+  // round r: its last reader finished a round ago, its next writer starts after the second barrier.
   for (;; round++) {
-    const u32 par = round & 1u;
+    const u32 cur = round % 3u, prev = (round + 2u) % 3u, nxt = (round + 1u) % 3u;
+    const u32 *pin = s.pend[round & 1u];
+    u32 *pout = s.pend[(round & 1u) ^ 1u];
     // phase A: classify the pending agents.  A donor is "final for this round" iff it was finalised in an EARLIER
     // round (0 < fin < round), which makes the outcome independent of the order in which threads run.
-    u32 still = 0;
-    for (u64 base = warp * 32; base < s.P; base += n_threads) {
-      const u64 i = base + lane;
-      bool rerun = false;
-      if (i < s.P && s.fin[i] == 0) {
+    const u32 n_in = *reinterpret_cast<volatile unsigned int *>(&ctrl->pending[prev]);
+    for (u64 base = warp * 32; base < n_in; base += n_threads) {
+      const u64 idx = base + lane;
+      bool rerun = false, wait = false;
+      u32 i = 0;
+      if (idx < n_in) {
+        i = pin[idx];
         const uint4 dc = s.dec[i];
-        bool wait = false, dirty = false;
+        bool dirty = false;
         auto look = [&](u64 r) {
           if (r < i) {
             const u32 f = s.fin[r];
@@ -235,25 +312,26 @@ __global__ void __launch_bounds__(kBlock) de_repair_kernel(DEState s) {
         };
         look(dc.x); look(dc.y); look(dc.z);
         if (best_mode) look(best_id);
-        if (wait) still++;
-        else { s.fin[i] = uint16_t(round); rerun = dirty; }
+        if (!wait) { s.fin[i] = uint16_t(round); rerun = dirty; }
       }
-      const u32 vote = __ballot_sync(kFull, rerun);
-      if (vote) {
-        u32 slot = 0;
-        if (lane == 0) slot = atomicAdd(&ctrl->list_count[par], __popc(vote));
-        slot = __shfl_sync(kFull, slot, 0);
-        if (rerun) s.list[slot + __popc(vote & ((1u << lane) - 1u))] = u32(i);
+      const u32 vote_w = __ballot_sync(kFull, wait), vote_r = __ballot_sync(kFull, rerun);
+      if (vote_w | vote_r) {
+        u32 slot_w = 0, slot_r = 0;
+        if (lane == 0) {
+          if (vote_w) slot_w = atomicAdd(&ctrl->pending[cur], __popc(vote_w));
+          if (vote_r) slot_r = atomicAdd(&ctrl->list_count[cur], __popc(vote_r));
+        }
+        slot_w = __shfl_sync(kFull, slot_w, 0);
+        slot_r = __shfl_sync(kFull, slot_r, 0);
+        const u32 below = (1u << lane) - 1u;
+        if (wait) pout[slot_w + __popc(vote_w & below)] = i;
+        if (rerun) s.list[slot_r + __popc(vote_r & below)] = i;
       }
     }
-    still = __reduce_add_sync(kFull, still);
-    if (lane == 0 && still) atomicAdd(&ctrl->pending[par], still);
     grid.sync();
-    // every thread has now taken the previous round's exit decision, so the other parity's counters can be cleared
-    // for the next round's phase A (which starts after the next barrier)
-    if (tid == 0) { ctrl->pending[par ^ 1u] = 0; ctrl->list_count[par ^ 1u] = 0; }
-    const u32 n_list = *reinterpret_cast<volatile unsigned int *>(&ctrl->list_count[par]);
-    const u32 pend = *reinterpret_cast<volatile unsigned int *>(&ctrl->pending[par]);
+    const u32 n_list = *reinterpret_cast<volatile unsigned int *>(&ctrl->list_count[cur]);
+    const u32 n_out = *reinterpret_cast<volatile unsigned int *>(&ctrl->pending[cur]);
+    if (tid == 0) { ctrl->pending[nxt] = 0; ctrl->list_count[nxt] = 0; }
     // phase B: re-evaluate the listed agents against rows that are now known
     for (u64 e = warp; e < n_list; e += n_warps) {
       const u64 i = s.list[e];
@@ -262,13 +340,11 @@ __global__ void __launch_bounds__(kBlock) de_repair_kernel(DEState s) {
       de_trial<T, OBJ, true>(s, i, key, best_mode ? best_id : i, dc.x, dc.y, dc.z, dc.w, s.rej[i], lane);
     }
     if (warp == 0) reruns += n_list;
-    if (pend == 0) break;
+    if (n_out == 0) break;
     if (round >= 65000u) { if (tid == 0) ctrl->error = 1; break; }
-    // the next round reads acc / rows written in phase B and the counters cleared above; with an empty list the
-    // barrier is still needed before phase A of round + 1 touches the cleared counters' parity again (round + 2)
-    grid.sync();
+    grid.sync();   // phase B's rows / accept flags and the recycled counters are visible to the next round
   }
-  if (tid == 0) { ctrl->reruns += reruns; ctrl->rounds += round; }
+  if (tid == 0) { ctrl->reruns += reruns; ctrl->rounds += round - 1; }
 }
 
 // ------------------------------------------------------------------------------------------------ K3 commit + reduce
@@ -305,7 +381,8 @@ __global__ void __launch_bounds__(kBlock) de_commit_kernel(DEState s, int mode) 
     ctrl->accepted += ctrl->acc_partial;
     ctrl->acc_partial = 0;
     ctrl->spec_accepted = 0;
-    ctrl->pending[0] = ctrl->pending[1] = ctrl->list_count[0] = ctrl->list_count[1] = 0;
+    ctrl->pending[0] = ctrl->pending[1] = ctrl->pending[2] = 0;
+    ctrl->list_count[0] = ctrl->list_count[1] = ctrl->list_count[2] = 0;
     if (ctrl->error) reason = reason ? reason : 4;
     ctrl->stop_reason = reason;
     __threadfence();
@@ -465,8 +542,12 @@ cudaError_t de_launch_generation(const DEState &s, const LaunchGeom &g, cudaStre
   cudaError_t e = cudaSuccess;
   if (ev) cudaEventRecord(ev[0], st);
 #define NLS_CALL(O)                                                                                                 \
-  de_generation_kernel<T, O><<<clamp_grid(want, u64(g.sm_count) * blocks_per_sm(de_generation_kernel<T, O>)), kBlock, \
-                               0, st>>>(s);                                                                         \
+  {                                                                                                                 \
+    const unsigned int grid = clamp_grid(want, u64(g.sm_count) * blocks_per_sm(de_generation_kernel<T, O>));        \
+    int shift = 5;                                     /* largest tile that still gives >= 8 tiles per warp */   \
+    while (shift > 0 && ((s.P + (1ull << shift) - 1) >> shift) < 8ull * grid * kWarpsPerBlock) shift--;             \
+    de_generation_kernel<T, O><<<grid, kBlock, 0, st>>>(s, shift);                                                  \
+  }                                                                                                                 \
   e = cudaGetLastError();                                                                                           \
   if (e != cudaSuccess) return e;                                                                                   \
   if (ev) cudaEventRecord(ev[1], st);                                                                               \

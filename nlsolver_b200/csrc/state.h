@@ -21,8 +21,8 @@ struct DECtrl {
   unsigned int acc_partial;     // accepted trials of the generation being committed
   unsigned int spec_accepted;   // trials accepted by the speculative pass K2 (0 => nothing to repair)
   unsigned int _pad2;
-  unsigned int pending[2];      // repair: agents still waiting on a lower donor, by round parity
-  unsigned int list_count[2];   // repair: agents to re-evaluate in this round, by round parity
+  unsigned int pending[3];      // repair: pending-list length produced in round r, slot r % 3 (K2 fills slot 1)
+  unsigned int list_count[3];   // repair: agents to re-evaluate in round r, slot r % 3
   Moments score_moments;        // moments of the scores at the last scan (island exchange record)
   double sel_value; unsigned long long sel_index;   // cursor of the top-k / worst-k selection (island migration)
 };
@@ -37,7 +37,8 @@ struct DEState {
   uint4 *dec;            // [P] {ids[1], ids[2], ids[3], dim}
   uint32_t *rej;         // [P] rejected index proposals (draw offset of the crossover draws = 4 + rej)
   uint8_t *masks;        // [P*d] crossover mask of the last generation, or NULL
-  uint32_t *list;        // [P] repair work list
+  uint32_t *list;        // [P] repair: agents to re-evaluate in the current round
+  uint32_t *pend[2];     // [P] each: ping-pong lists of agents whose outcome is not final yet
   DECtrl *ctrl;
   // reduction partials [n_partials]
   double *part_min; unsigned long long *part_idx; Moments *part_mom;
