@@ -81,9 +81,11 @@ __device__ __forceinline__ void st_row(float *p, const float (&x)[4]) {
 }
 
 // xor-butterfly sum: every lane ends with the same value (a + b is commutative, so both partners agree bit-wise)
-template <class T> __device__ __forceinline__ T warp_butterfly_add(T a) {
+// W < 32: the butterfly runs inside aligned groups of W lanes.  When only the first W accumulators of the canonical
+// 32 are non-zero (d <= W * V) this is bit-identical to the full butterfly, whose upper stages only add +0.
+template <class T, int W = 32> __device__ __forceinline__ T warp_butterfly_add(T a) {
 #pragma unroll
-  for (int off = 16; off >= 1; off >>= 1) a = Ar<T>::add(a, __shfl_xor_sync(kFull, a, off));
+  for (int off = W / 2; off >= 1; off >>= 1) a = Ar<T>::add(a, __shfl_xor_sync(kFull, a, off));
   return a;
 }
 

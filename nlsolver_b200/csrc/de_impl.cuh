@@ -47,19 +47,20 @@ __device__ __forceinline__ const T *de_row_of(const DEState &s, u64 r, u64 i) {
 #ifndef NLS_DE_UNROLL
 #define NLS_DE_UNROLL 1
 #endif
-template <class T, int OBJ, bool EVAL, bool WRITE>
+// W lanes cooperate on the agent (`lane` is the index inside that group); W < 32 requires d <= W * V.
+template <class T, int OBJ, bool EVAL, bool WRITE, int W = 32>
 __device__ __forceinline__ T de_sweep(const DEState &s, const T *p0, const T *p1, const T *p2, const T *p3, T *dst,
                                       u64 sbase, u32 dim, u64 i, int lane) {
   constexpr int V = Vec<T>::V;
   constexpr int U = NLS_DE_UNROLL;
-  constexpr u32 kStride = 32 * V;                      // coordinates per warp step
+  constexpr u32 kStride = W * V;                       // coordinates per group step
   typedef Ar<T> A;
   const u32 d = static_cast<u32>(s.d);
   const T F = static_cast<T>(s.F);
   const u64 cr_le = s.cr_le;
   const bool cr_any = !s.cr_none;
   const u32 n_steps = (d + kStride - 1) / kStride;
-  Objective<T, OBJ> obj;
+  Objective<T, OBJ, W> obj;
   if (EVAL) obj.begin(lane, d);
   u32 j0 = lane * V;                                   // first coordinate of this lane in the current step
   u64 st = sbase + kGolden * j0;                       // draw-stream state of coordinate j0
@@ -193,7 +194,9 @@ struct __align__(16) DETileEntry {
 //   epilogue  — one agent per lane again: coalesced stores of trial score / accept flag.
 // The tile size (2^tile_shift <= 32 agents) is chosen by the launcher so that every warp gets many tiles: with 32-agent
 // tiles a population of 2^18 would give 1.7 tiles per resident warp and a 15 % tail.
-template <class T, int OBJ>
+// W lanes per agent in the body: 32, or 16 / 8 / 4 when one step of W lanes covers the row (d <= W * V) — then the warp
+// streams 32 / W agents of the tile at a time instead of leaving lanes idle.
+template <class T, int OBJ, int W>
 __global__ void __launch_bounds__(kBlock, NLS_DE_MINBLOCKS) de_generation_kernel(DEState s, int tile_shift) {
   __shared__ DETileEntry tile_mem[kWarpsPerBlock][32];
   DECtrl *ctrl = s.ctrl;
@@ -242,8 +245,12 @@ __global__ void __launch_bounds__(kBlock, NLS_DE_MINBLOCKS) de_generation_kernel
     const int n_here = (P - first) < tile_size ? int(P - first) : int(tile_size);
     T my_score = T(0);
     bool my_ok = false;
-    for (int a = 0; a < n_here; a++) {
-      const DETileEntry e = tile_entries[a];              // broadcast read
+    constexpr int G = 32 / W;                              // agents streamed at a time
+    const int grp = lane / W, sub = lane % W;
+    for (int a0 = 0; a0 < n_here; a0 += G) {
+      const bool active = a0 + grp < n_here;               // idle groups redo the first agent, results discarded
+      const int a = active ? a0 + grp : a0;
+      const DETileEntry e = tile_entries[a];               // broadcast read inside the group
       const u64 i = first + a;
       const u64 r0 = random_mode ? i : best_id;
       const T *p0 = static_cast<const T *>(s.buf[e.wbits & 1u]) + r0 * s.stride;
@@ -252,11 +259,17 @@ __global__ void __launch_bounds__(kBlock, NLS_DE_MINBLOCKS) de_generation_kernel
       const T *p3 = static_cast<const T *>(s.buf[(e.wbits >> 3) & 1u]) + u64(e.r3) * s.stride;
       T *dst = static_cast<T *>(s.buf[((e.wbits >> 4) & 1u) ^ 1u]) + i * s.stride;
       const u64 sbase = tape_state(e.key, 4 + e.rej);
-      const T raw = de_sweep<T, OBJ, true, false>(s, p0, p1, p2, p3, dst, sbase, e.dim, i, lane);
+      const T raw = de_sweep<T, OBJ, true, false, W>(s, p0, p1, p2, p3, dst, sbase, e.dim, i, sub);
       const T sc = Ar<T>::mul(static_cast<T>(s.fm), raw);
-      const bool ok = sc < static_cast<T>(e.score);       // strict <, NaN never accepted (nlsolver.h:2466)
-      if (ok) de_sweep<T, OBJ, false, true>(s, p0, p1, p2, p3, dst, sbase, e.dim, i, lane);
-      if (lane == a) { my_score = sc; my_ok = ok; }
+      const bool ok = active && sc < static_cast<T>(e.score);   // strict <, NaN never accepted (nlsolver.h:2466)
+      if (ok) de_sweep<T, OBJ, false, true, W>(s, p0, p1, p2, p3, dst, sbase, e.dim, i, sub);
+      // hand the outcome of agent a0 + g to lane a0 + g (its owner in the epilogue)
+#pragma unroll
+      for (int g = 0; g < G; g++) {
+        const T sc_g = __shfl_sync(kFull, sc, g * W);
+        const bool ok_g = __shfl_sync(kFull, int(ok), g * W) != 0;
+        if (lane == a0 + g) { my_score = sc_g; my_ok = ok_g; }
+      }
     }
     // ---- epilogue
     if (own) {
@@ -535,6 +548,24 @@ cudaError_t de_launch_init(const DEState &s, const void *x0_dev, const LaunchGeo
   return de_launch_commit<T>(s, 1, g, st);
 }
 
+template <class T, int O, int W>
+void de_launch_k2_w(const DEState &s, const LaunchGeom &g, cudaStream_t st) {
+  const u64 want = (s.P + kWarpsPerBlock - 1) / kWarpsPerBlock;
+  const unsigned int grid = clamp_grid(want, u64(g.sm_count) * blocks_per_sm(de_generation_kernel<T, O, W>));
+  int shift = 5;                                       // largest tile that still gives >= 8 tiles per warp
+  while (shift > 0 && ((s.P + (1ull << shift) - 1) >> shift) < 8ull * grid * kWarpsPerBlock) shift--;
+  de_generation_kernel<T, O, W><<<grid, kBlock, 0, st>>>(s, shift);
+}
+// lanes per agent: the smallest of 4 / 8 / 16 whose single step covers the row, else the whole warp
+template <class T, int O>
+void de_launch_k2(const DEState &s, const LaunchGeom &g, cudaStream_t st) {
+  const u64 vecs = (s.d + Vec<T>::V - 1) / Vec<T>::V;   // 128-bit vectors per row
+  if (vecs <= 4) de_launch_k2_w<T, O, 4>(s, g, st);
+  else if (vecs <= 8) de_launch_k2_w<T, O, 8>(s, g, st);
+  else if (vecs <= 16) de_launch_k2_w<T, O, 16>(s, g, st);
+  else de_launch_k2_w<T, O, 32>(s, g, st);
+}
+
 // one generation: K2, K2r (cooperative), K3
 template <class T>
 cudaError_t de_launch_generation(const DEState &s, const LaunchGeom &g, cudaStream_t st, cudaEvent_t *ev) {
@@ -542,12 +573,7 @@ cudaError_t de_launch_generation(const DEState &s, const LaunchGeom &g, cudaStre
   cudaError_t e = cudaSuccess;
   if (ev) cudaEventRecord(ev[0], st);
 #define NLS_CALL(O)                                                                                                 \
-  {                                                                                                                 \
-    const unsigned int grid = clamp_grid(want, u64(g.sm_count) * blocks_per_sm(de_generation_kernel<T, O>));        \
-    int shift = 5;                                     /* largest tile that still gives >= 8 tiles per warp */   \
-    while (shift > 0 && ((s.P + (1ull << shift) - 1) >> shift) < 8ull * grid * kWarpsPerBlock) shift--;             \
-    de_generation_kernel<T, O><<<grid, kBlock, 0, st>>>(s, shift);                                                  \
-  }                                                                                                                 \
+  de_launch_k2<T, O>(s, g, st);                                                                                     \
   e = cudaGetLastError();                                                                                           \
   if (e != cudaSuccess) return e;                                                                                   \
   if (ev) cudaEventRecord(ev[1], st);                                                                               \

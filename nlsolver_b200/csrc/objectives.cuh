@@ -12,7 +12,9 @@ namespace nls {
 
 enum { OBJ_SPHERE = 0, OBJ_ROSENBROCK = 1, OBJ_RASTRIGIN = 2, OBJ_ACKLEY = 3, OBJ_ROSENBROCK_EX = 4, OBJ_COUNT = 5 };
 
-template <class T, int OBJ>
+// W = lanes that cooperate on one agent (32, or a smaller power of two when d <= W * V so that one step covers the
+// row); `lane` arguments are lane indices INSIDE the group.
+template <class T, int OBJ, int W = 32>
 struct Objective {
   static constexpr int V = Vec<T>::V;
   static constexpr bool kPairwise = (OBJ == OBJ_ROSENBROCK || OBJ == OBJ_ROSENBROCK_EX);
@@ -31,9 +33,9 @@ struct Objective {
   __device__ __forceinline__ void step(const T (&x)[V], u32 j0, u32 d, int lane) {
     T left = T(0);
     if (kPairwise) {
-      left = __shfl_up_sync(kFull, x[V - 1], 1);          // x[j0 - 1] lives in the previous lane ...
-      if (lane == 0) left = carry;                        // ... or in lane 31 of the previous step
-      carry = __shfl_sync(kFull, x[V - 1], 31);
+      left = __shfl_up_sync(kFull, x[V - 1], 1, W);       // x[j0 - 1] lives in the previous lane ...
+      if (lane == 0) left = carry;                        // ... or in the last lane of the previous step
+      carry = __shfl_sync(kFull, x[V - 1], W - 1, W);
     }
 #pragma unroll
     for (int q = 0; q < V; q++) {
@@ -65,9 +67,9 @@ struct Objective {
 
   // every lane returns the objective value
   __device__ __forceinline__ T finish(u32 d) {
-    a = warp_butterfly_add<T>(a);
+    a = warp_butterfly_add<T, W>(a);
     if (OBJ == OBJ_ACKLEY) {
-      b = warp_butterfly_add<T>(b);
+      b = warp_butterfly_add<T, W>(b);
       const T inv_d = T(1.0) / T(d);
       const T ra = A::mul(T(-20), t_exp<T>(A::mul(T(-0.2), t_sqrt<T>(A::mul(inv_d, a)))));
       const T rb = -t_exp<T>(A::mul(inv_d, b));
