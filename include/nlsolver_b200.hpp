@@ -91,6 +91,60 @@ struct xorshift {
  private:
   uint64_t x[2]{};
 };
+
+// nlsolver.h:1289-1341 — xoshiro-style generator.  Two quirks of the reference are kept so that streams match: s[2] is
+// seeded from splitmix::yield() (a value in [0,1] truncated to an integer, i.e. 0) and the rotation is by 45 of 64.
+template <typename scalar_t = float>
+struct xoshiro {
+  xoshiro() { reset(); }
+  scalar_t yield() {
+    const uint64_t result = s[0] + s[3];
+    const uint64_t t = s[1] << 17;
+    s[2] ^= s[0];
+    s[3] ^= s[1];
+    s[1] ^= s[2];
+    s[0] ^= s[3];
+    s[2] ^= t;
+    s[3] = (s[3] << 45) | (s[3] >> 19);
+    return detail::to_unit<scalar_t>(result);
+  }
+  scalar_t operator()() { return yield(); }
+  void reset() {
+    splitmix<scalar_t> gn;
+    s[0] = gn.yield_init();
+    s[1] = s[0] >> 32;
+    s[2] = static_cast<uint64_t>(gn.yield());
+    s[3] = s[2] >> 32;
+  }
+  void set_state(uint64_t x, uint64_t y, uint64_t z, uint64_t t) { s[0] = x; s[1] = y; s[2] = z; s[3] = t; }
+  std::vector<scalar_t> get_state() const {
+    return {static_cast<scalar_t>(s[0]), static_cast<scalar_t>(s[1]), static_cast<scalar_t>(s[2]),
+            static_cast<scalar_t>(s[3])};
+  }
+
+ private:
+  uint64_t s[4];
+};
+
+// nlsolver.h:1228-1261 — additive recurrence z <- frac(z + alpha), alpha = 0.618034
+template <typename scalar_t = float>
+struct recurrent {
+  recurrent() : recurrent(static_cast<scalar_t>(0.5)) {}
+  explicit recurrent(scalar_t seed) : alpha_(0.618034), seed_(seed), z_(alpha_ + seed_) { wrap(); }
+  scalar_t yield() {
+    z_ += alpha_;
+    wrap();
+    return z_;
+  }
+  scalar_t operator()() { return yield(); }
+  void reset() { alpha_ = 0.618034; seed_ = 0.5; z_ = 0; }
+  std::vector<scalar_t> get_state() const { return {alpha_, z_}; }
+  void set_state(scalar_t alpha = 0.618034, scalar_t z = 0) { alpha_ = alpha; z_ = z; }
+
+ private:
+  void wrap() { z_ -= static_cast<scalar_t>(static_cast<uint64_t>(z_)); }
+  scalar_t alpha_, seed_, z_;
+};
 }  // namespace rng
 
 // ------------------------------------------------------------------------------------------------ objectives
