@@ -179,6 +179,24 @@ NLS_API int nls_pso_step_local(nls_pso *pso, void *record_dev);
 NLS_API int nls_pso_export_candidate(nls_pso *pso, void *record_dev);
 NLS_API int nls_pso_apply_candidates(nls_pso *pso, const void *records_dev, uint64_t n_records);
 
+/* ---- fused exchange over peer memory (NVLink / NVSwitch), no host-side collective ----
+ * Each rank owns an exchange WINDOW in its HBM that every peer maps through CUDA IPC.  nls_pso_step_fused runs, per
+ * generation: move kernel -> candidate kernel whose last block stores the shard's record directly into every peer's
+ * window and releases a sequence flag -> apply kernel that waits on its own window's flags and then scans the records.
+ * Results are identical to nls_pso_step_local + all-gather + nls_pso_apply_candidates.
+ *   1. nls_xchg_create on every rank (world <= 16, same record size = nls_record_bytes(dtype, dim))
+ *   2. nls_xchg_get_handle -> exchange the NLS_XCHG_HANDLE_BYTES-byte handles between ranks (any transport)
+ *   3. nls_xchg_open_peers with the rank-ordered handles
+ *   4. nls_pso_attach_exchange (performs the pending initial exchange), then nls_pso_step_fused */
+#define NLS_XCHG_HANDLE_BYTES 64
+typedef struct nls_xchg nls_xchg;
+NLS_API int nls_xchg_create(nls_ctx *ctx, uint64_t record_bytes, int world, int rank, nls_xchg **out);
+NLS_API int nls_xchg_get_handle(nls_xchg *x, void *handle_out);
+NLS_API int nls_xchg_open_peers(nls_xchg *x, const void *handles);
+NLS_API int nls_xchg_destroy(nls_xchg *x);
+NLS_API int nls_pso_attach_exchange(nls_pso *pso, nls_xchg *x);
+NLS_API int nls_pso_step_fused(nls_pso *pso, uint64_t n_generations);
+
 #ifdef __cplusplus
 }
 #endif

@@ -5,6 +5,6 @@ Python host binding: `solvers` mirrors the reference's DE / PSO interface, `dist
 across GPUs with torch.distributed."""
 from ._lib import (ACKLEY, DE_BEST, DE_RANDOM, F32, F64, FLAG_RECORD_MASKS, FLAG_SOCIAL_INDEX_J, PSO_ACCELERATED,  # noqa: F401
                    PSO_VANILLA, RASTRIGIN, ROSENBROCK, ROSENBROCK_EX, SPHERE, NlsError, lib)
-from .solvers import (DE, PSO, Ackley, Context, DEPopulation, DESolver, PSOSolver, PSOSwarm, PSOType,  # noqa: F401
+from .solvers import (DE, PSO, Ackley, Context, DEPopulation, DESolver, ExchangeWindow, PSOSolver, PSOSwarm, PSOType,  # noqa: F401
                       Rastrigin, RecombinationStrategy, Rosenbrock, RosenbrockExample, SolverStatus, Sphere, de_cfg,
                       default_context, pso_cfg)

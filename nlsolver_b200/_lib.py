@@ -14,6 +14,7 @@ SPHERE, ROSENBROCK, RASTRIGIN, ACKLEY, ROSENBROCK_EX = range(5)
 DE_BEST, DE_RANDOM = 0, 1
 PSO_VANILLA, PSO_ACCELERATED = 0, 1
 FLAG_RECORD_MASKS, FLAG_SOCIAL_INDEX_J = 1, 2
+XCHG_HANDLE_BYTES = 64
 
 u64, i32, u32, f64 = C.c_uint64, C.c_int32, C.c_uint32, C.c_double
 
@@ -89,6 +90,12 @@ SYMBOLS = {
     "nls_pso_step_local": (C.c_int, [P, P]),
     "nls_pso_export_candidate": (C.c_int, [P, P]),
     "nls_pso_apply_candidates": (C.c_int, [P, P, u64]),
+    "nls_xchg_create": (C.c_int, [P, u64, C.c_int, C.c_int, C.POINTER(P)]),
+    "nls_xchg_get_handle": (C.c_int, [P, P]),
+    "nls_xchg_open_peers": (C.c_int, [P, P]),
+    "nls_xchg_destroy": (C.c_int, [P]),
+    "nls_pso_attach_exchange": (C.c_int, [P, P]),
+    "nls_pso_step_fused": (C.c_int, [P, u64]),
 }
 
 _lib = None

@@ -140,6 +140,15 @@ struct nls_de {
   u64 timed_generations;
 };
 
+struct nls_xchg {
+  nls_ctx *ctx;
+  XchgWindow w;
+  void *base;                       // this rank's window: records [2][world][record_bytes], then flags [2][world]
+  size_t bytes, flags_offset;
+  void *peer_base[kMaxPeers];       // IPC mappings of the peers' windows (NULL for self / not opened)
+  bool opened;
+};
+
 struct nls_pso {
   nls_ctx *ctx;
   nls_pso_cfg cfg;
@@ -151,6 +160,7 @@ struct nls_pso {
   u64 record_bytes;
   u64 enqueued;          // generations enqueued so far (the iter value the next move kernel will see)
   bool first_apply_pending;
+  nls_xchg *xchg;        // fused peer exchange, or NULL
   size_t elem;
 };
 
@@ -525,6 +535,7 @@ static int pso_build(nls_ctx *ctx, const nls_pso_cfg *cfg, const void *lower, co
   p->ops = cfg->dtype == NLS_F64 ? pso_ops_f64() : pso_ops_f32();
   p->g = make_geom(ctx, P);
   p->enqueued = 0;
+  p->xchg = nullptr;
   PSOState &s = p->s;
   std::memset(&s, 0, sizeof(s));
   s.P = P; s.d = d; s.stride = round_up(d, 32 / p->elem);
@@ -702,6 +713,97 @@ int nls_pso_solve(nls_ctx *ctx, const nls_pso_cfg *cfg, const void *lower_host, 
   if (rc == NLS_OK && status) *status = st;
   nls_pso_destroy(p);
   return rc;
+}
+
+/* ================================================================ peer exchange =============================== */
+
+int nls_xchg_create(nls_ctx *ctx, uint64_t record_bytes, int world, int rank, nls_xchg **out) {
+  if (!ctx || !out) return fail(NLS_ERR_INVALID, "nls_xchg_create: NULL argument");
+  *out = nullptr;
+  if (world < 1 || world > kMaxPeers || rank < 0 || rank >= world || record_bytes < sizeof(RecordHeader))
+    return fail(NLS_ERR_INVALID, "nls_xchg_create: world must be 1..%d, 0 <= rank < world", kMaxPeers);
+  NLS_CUDA(cudaSetDevice(ctx->device));
+  nls_xchg *x = new nls_xchg();
+  x->ctx = ctx;
+  x->opened = false;
+  x->flags_offset = round_up(2 * size_t(world) * record_bytes, 256);
+  x->bytes = x->flags_offset + 2 * size_t(world) * sizeof(unsigned long long);
+  for (int r = 0; r < kMaxPeers; r++) { x->peer_base[r] = nullptr; x->w.records[r] = nullptr; x->w.flags[r] = nullptr; }
+  x->w.world = world; x->w.rank = rank; x->w.record_bytes = record_bytes;
+  cudaError_t e = cudaMalloc(&x->base, x->bytes);     // plain cudaMalloc: the allocation must be IPC-exportable
+  if (e != cudaSuccess) { delete x; return fail(NLS_ERR_NOMEM, "nls_xchg_create: %s", cudaGetErrorString(e)); }
+  NLS_CUDA(cudaMemset(x->base, 0, x->bytes));
+  x->w.records[rank] = static_cast<char *>(x->base);
+  x->w.flags[rank] = reinterpret_cast<unsigned long long *>(static_cast<char *>(x->base) + x->flags_offset);
+  if (world == 1) x->opened = true;
+  *out = x;
+  return NLS_OK;
+}
+
+int nls_xchg_get_handle(nls_xchg *x, void *handle_out) {
+  if (!x || !handle_out) return fail(NLS_ERR_INVALID, "nls_xchg_get_handle: NULL argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) <= NLS_XCHG_HANDLE_BYTES, "IPC handle larger than the ABI slot");
+  NLS_CUDA(cudaSetDevice(x->ctx->device));
+  cudaIpcMemHandle_t h;
+  NLS_CUDA(cudaIpcGetMemHandle(&h, x->base));
+  std::memset(handle_out, 0, NLS_XCHG_HANDLE_BYTES);
+  std::memcpy(handle_out, &h, sizeof(h));
+  return NLS_OK;
+}
+
+int nls_xchg_open_peers(nls_xchg *x, const void *handles) {
+  if (!x || !handles) return fail(NLS_ERR_INVALID, "nls_xchg_open_peers: NULL argument");
+  NLS_CUDA(cudaSetDevice(x->ctx->device));
+  for (int r = 0; r < x->w.world; r++) {
+    if (r == x->w.rank || x->peer_base[r]) continue;
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, static_cast<const char *>(handles) + size_t(r) * NLS_XCHG_HANDLE_BYTES, sizeof(h));
+    NLS_CUDA(cudaIpcOpenMemHandle(&x->peer_base[r], h, cudaIpcMemLazyEnablePeerAccess));
+    x->w.records[r] = static_cast<char *>(x->peer_base[r]);
+    x->w.flags[r] = reinterpret_cast<unsigned long long *>(static_cast<char *>(x->peer_base[r]) + x->flags_offset);
+  }
+  x->opened = true;
+  return NLS_OK;
+}
+
+int nls_xchg_destroy(nls_xchg *x) {
+  if (!x) return NLS_OK;
+  cudaSetDevice(x->ctx->device);
+  cudaStreamSynchronize(x->ctx->stream);
+  for (int r = 0; r < kMaxPeers; r++)
+    if (x->peer_base[r]) cudaIpcCloseMemHandle(x->peer_base[r]);
+  cudaFree(x->base);
+  delete x;
+  return NLS_OK;
+}
+
+int nls_pso_attach_exchange(nls_pso *p, nls_xchg *x) {
+  if (!p || !x) return fail(NLS_ERR_INVALID, "nls_pso_attach_exchange: NULL argument");
+  if (!x->opened) return fail(NLS_ERR_STATE, "nls_pso_attach_exchange: open the peers' handles first");
+  if (x->w.record_bytes != p->record_bytes) return fail(NLS_ERR_INVALID, "exchange window record size mismatch");
+  NLS_CUDA(cudaSetDevice(p->ctx->device));
+  p->xchg = x;
+  if (p->first_apply_pending) {   // finish the first update_best_positions across the shards (nlsolver.h:2595)
+    NLS_CUDA(p->ops->candidate_publish(p->s, x->w, 1, p->g, p->ctx->stream));
+    NLS_CUDA(p->ops->gather_apply(p->s, x->w, 1, p->ctx->stream));
+    p->first_apply_pending = false;
+  }
+  return NLS_OK;
+}
+
+int nls_pso_step_fused(nls_pso *p, uint64_t n_generations) {
+  if (!p) return fail(NLS_ERR_INVALID, "nls_pso_step_fused: NULL handle");
+  if (!p->xchg) return fail(NLS_ERR_STATE, "nls_pso_step_fused: no exchange window attached");
+  if (p->first_apply_pending) return fail(NLS_ERR_STATE, "nls_pso_step_fused: initial exchange pending");
+  NLS_CUDA(cudaSetDevice(p->ctx->device));
+  cudaStream_t st = p->ctx->stream;
+  for (uint64_t g = 0; g < n_generations; g++) {
+    NLS_CUDA(p->ops->move(p->s, pso_inertia(p, p->enqueued), p->g, st));
+    NLS_CUDA(p->ops->candidate_publish(p->s, p->xchg->w, 0, p->g, st));
+    NLS_CUDA(p->ops->gather_apply(p->s, p->xchg->w, 0, st));
+    p->enqueued++;
+  }
+  return NLS_OK;
 }
 
 }  /* extern "C" */

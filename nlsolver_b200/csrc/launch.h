@@ -20,6 +20,10 @@ struct PSOOps {
   cudaError_t (*candidate)(const PSOState &s, void *record, const LaunchGeom &g, cudaStream_t st);
   cudaError_t (*apply)(const PSOState &s, const void *records, unsigned long long n, unsigned long long record_bytes,
                        int initial, cudaStream_t st);
+  // fused exchange over peer memory: candidate + publish to all peers, then wait for all peers + apply
+  cudaError_t (*candidate_publish)(const PSOState &s, const XchgWindow &w, int initial, const LaunchGeom &g,
+                                   cudaStream_t st);
+  cudaError_t (*gather_apply)(const PSOState &s, const XchgWindow &w, int initial, cudaStream_t st);
 };
 const DEOps *de_ops_f64();
 const DEOps *de_ops_f32();

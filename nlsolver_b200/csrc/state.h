@@ -72,6 +72,18 @@ struct PSOState {
   unsigned long long max_iter, vnc_limit;
 };
 
+// Peer exchange window of a sharded swarm (one per rank, mapped into every peer through CUDA IPC): for each of the two
+// generation parities, one record slot and one sequence flag per source rank.  A rank PUBLISHES its record by storing
+// it into slot [parity][rank] of every peer's window over NVLink, then releases the flag; it GATHERS by waiting on the
+// flags of its own window.  No host-side collective is involved.
+constexpr int kMaxPeers = 16;
+struct XchgWindow {
+  char *records[kMaxPeers];                 // base of rank r's record area  [2][world][record_bytes]
+  unsigned long long *flags[kMaxPeers];     // base of rank r's flag area    [2][world]
+  int world, rank;
+  unsigned long long record_bytes;
+};
+
 struct LaunchGeom {
   int sm_count;
   int reduce_blocks;   // grid of the reduction kernels (= number of partials)

@@ -204,6 +204,20 @@ class CudaPSOEngine:
     def apply_candidates(self, records, n):
         self.swarm.apply_candidates(records.data_ptr(), n)
 
+    def open_peer_exchange(self, comm, record_bytes):
+        """Map every rank's exchange window into this process (CUDA IPC) and attach it to the swarm: from here on a
+        generation needs no host-side collective (nls_pso_step_fused)."""
+        from .solvers import ExchangeWindow
+        self.window = ExchangeWindow(self.ctx, record_bytes, comm.world, comm.rank)
+        if comm.world > 1:
+            handles = [None] * comm.world
+            comm.dist.all_gather_object(handles, self.window.ipc_handle(), group=comm.group)
+            self.window.open_peers(handles)
+        self.swarm.attach_exchange(self.window)
+
+    def step_fused(self, n):
+        self.swarm.step_fused(n)
+
     def sync(self):
         return self.swarm.sync()
 
@@ -212,6 +226,8 @@ class CudaPSOEngine:
 
     def close(self):
         self.swarm.close()
+        if getattr(self, "window", None) is not None:
+            self.window.close()
         self.ctx.close()
 
 
@@ -230,7 +246,10 @@ class _NullStream:
 class ShardedPSO:
     """A global swarm of `cfg.n_particles` particles split across the ranks of `group`."""
 
-    def __init__(self, cfg, lower, upper, device=0, group=None, stream=None, engine_factory=None):
+    def __init__(self, cfg, lower, upper, device=0, group=None, stream=None, engine_factory=None, exchange="nccl"):
+        """exchange: "nccl" — all-gather of the candidate records through torch.distributed every generation;
+        "peer" — the fused kernels store the records straight into the peers' HBM over NVLink (CUDA IPC windows),
+        no host-side collective in the loop.  Both give identical results."""
         import torch
 
         from . import _lib as L
@@ -252,16 +271,22 @@ class ShardedPSO:
             self._scope = lambda: self.stream
             self.engine = engine_factory(local, lower, upper)
         self.rb = record_bytes(8 if cfg.dtype == L.F64 else 4, cfg.dim)
+        self.fused = exchange == "peer"
         with self._scope():
             self.mine = self.engine.tensor(self.rb, torch.uint8)
             self.all = self.engine.tensor(self.rb * self.comm.world, torch.uint8)
-            if self.comm.world > 1:   # finish the first update_best_positions across shards (nlsolver.h:2595)
+            if self.fused:
+                self.engine.open_peer_exchange(self.comm, self.rb)
+            elif self.comm.world > 1:   # finish the first update_best_positions across shards (nlsolver.h:2595)
                 self.engine.export_candidate(self.mine)
                 self.comm.all_gather(self.all, self.mine)
                 self.engine.apply_candidates(self.all, self.comm.world)
 
     def step(self, n=1):
         with self._scope():
+            if self.fused:
+                self.engine.step_fused(n)
+                return
             if self.comm.world == 1:
                 self.engine.step(n)
                 return

@@ -213,6 +213,12 @@ class PSOSwarm:
     def apply_candidates(self, records_ptr, n):
         L.check(L.lib().nls_pso_apply_candidates(self._h, C.c_void_p(records_ptr), n))
 
+    def attach_exchange(self, window):
+        L.check(L.lib().nls_pso_attach_exchange(self._h, window.handle))
+
+    def step_fused(self, n=1):
+        L.check(L.lib().nls_pso_step_fused(self._h, n))
+
     def sync(self):
         st = L.Status()
         L.check(L.lib().nls_pso_sync(self._h, C.byref(st)))
@@ -248,6 +254,33 @@ class PSOSwarm:
             self.close()
         except Exception:
             pass
+
+
+class ExchangeWindow:
+    """Peer-memory exchange window (nls_xchg_*): records and flags in this rank's HBM, mapped by every peer via IPC."""
+
+    def __init__(self, ctx, record_bytes, world, rank):
+        self._h = C.c_void_p()
+        L.check(L.lib().nls_xchg_create(ctx.handle, record_bytes, world, rank, C.byref(self._h)))
+
+    @property
+    def handle(self):
+        return self._h
+
+    def ipc_handle(self):
+        buf = (C.c_ubyte * L.XCHG_HANDLE_BYTES)()
+        L.check(L.lib().nls_xchg_get_handle(self._h, buf))
+        return bytes(buf)
+
+    def open_peers(self, handles):
+        """handles: rank-ordered list of the bytes objects returned by every rank's ipc_handle()."""
+        blob = b"".join(handles)
+        L.check(L.lib().nls_xchg_open_peers(self._h, blob))
+
+    def close(self):
+        if self._h:
+            L.lib().nls_xchg_destroy(self._h)
+            self._h = C.c_void_p()
 
 
 def de_cfg(dtype=L.F64, objective=L.SPHERE, strategy=L.DE_RANDOM, minimize=True, pop_size=50, dim=2,

@@ -156,3 +156,26 @@ def test_sharded_swarm_equals_single_swarm(ctx):
         assert abs(ss["std_err"] - sw["std_err"]) <= 1e-12 * abs(sw["std_err"])
         assert np.array_equal(bits(s.best()), bits(whole.best()))
     assert np.array_equal(bits(np.concatenate([s.positions() for s in shards])), bits(whole.positions()))
+
+
+def test_fused_peer_exchange_single_rank_equals_plain_step(ctx):
+    """nls_pso_step_fused with a one-rank exchange window (records published into the rank's own window) must equal
+    nls_pso_step; the multi-rank case needs several GPUs and is checked by tools/multi_gpu_check.py."""
+    P, d, G = 500, 40, 7
+    up = np.full(d, 5.12)
+    kw = dict(objective=nb.RASTRIGIN, pso_type=nb.PSO_ACCELERATED, n_particles=P, dim=d, eps=0.0, max_iter=1 << 40,
+              best_val_no_change=1 << 40, seed=99)
+    plain = nb.PSOSwarm(ctx, nb.pso_cfg(**kw), -up, up)
+    fused = nb.PSOSwarm(ctx, nb.pso_cfg(**kw), -up, up)
+    win = nb.ExchangeWindow(ctx, nb.lib().nls_record_bytes(nb.F64, d), 1, 0)
+    fused.attach_exchange(win)
+    plain.step(G)
+    fused.step_fused(G)
+    a, b = plain.sync(), fused.sync()
+    for k in ("f_value", "iterations", "function_calls", "best_index", "val_no_change", "std_err"):
+        assert a[k] == b[k], k
+    assert np.array_equal(bits(plain.positions()), bits(fused.positions()))
+    assert np.array_equal(bits(plain.best()), bits(fused.best()))
+    fused.close()
+    win.close()
+    plain.close()

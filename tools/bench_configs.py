@@ -28,6 +28,7 @@ def main():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--per-gpu", type=int, default=1 << 21)
+    ap.add_argument("--exchange", default="nccl", choices=["nccl", "peer"], help="config 3: record exchange path")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -48,8 +49,8 @@ def main():
         cfg = nb.pso_cfg(objective=nb.ACKLEY, pso_type=nb.PSO_ACCELERATED, n_particles=P, dim=d, inertia=0.8,
                          cognitive_coef=1.8, social_coef=1.8, eps=0.0, max_iter=NEVER, best_val_no_change=NEVER,
                          seed=0x7c26ca28fb68bc1b)
-        job = D.ShardedPSO(cfg, -up, up, device=local)
-        units, name = P, f"PSO-accelerated Ackley d={d}, {P} particles over {world} GPU(s), fp64, exchange every generation"
+        job = D.ShardedPSO(cfg, -up, up, device=local, exchange=args.exchange)
+        units, name = P, f"PSO-accelerated Ackley d={d}, {P} particles over {world} GPU(s), fp64, {args.exchange} exchange every generation"
         alg_bytes = 2 * d * 8 + 2 * 8
     else:
         d, P = 4096, args.per_gpu

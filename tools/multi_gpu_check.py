@@ -51,6 +51,20 @@ def main():
         whole.close()
         ctx.close()
 
+    # ---- the same swarm with the fused peer-memory exchange (no NCCL in the loop) ----
+    sw = D.ShardedPSO(nb.pso_cfg(**kw), -up, up, device=local, exchange="peer")
+    sw.step(gens)
+    fst = sw.sync()
+    fbest = sw.best()
+    same = all(fst[k] == st[k] for k in ("f_value", "iterations", "function_calls", "best_index", "val_no_change"))
+    same &= np.array_equal(fbest, best)
+    flag = torch.tensor([1 if same else 0], device=f"cuda:{local}")
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    sw.close()
+    if rank == 0:
+        print(f"sharded PSO x{world}, fused peer exchange: identical to the NCCL path = {bool(flag.item())}", flush=True)
+    ok &= bool(flag.item())
+
     # ---- island DE with ring migration ----
     Pi, di, every, k, gens = 512, 24, 3, 8, 10
     dkw = dict(objective=nb.ROSENBROCK, strategy=nb.DE_BEST, pop_size=Pi, dim=di, eps=0.0, max_iter=1 << 40,
