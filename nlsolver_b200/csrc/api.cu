@@ -123,6 +123,36 @@ LaunchGeom make_geom(const nls_ctx *ctx, u64 n) {
 
 }  // namespace
 
+// Small populations are launch-bound (a generation is three kernels of a few microseconds each): their generations are
+// replayed from a CUDA graph of kGraphGens generations instead of being launched one kernel at a time.
+constexpr int kGraphGens = 8;
+constexpr unsigned long long kGraphMaxElems = 1ull << 24;   // P * d above which launch overhead no longer matters
+struct GraphCache {
+  cudaGraphExec_t exec = nullptr;
+  bool failed = false;
+  void reset() { if (exec) cudaGraphExecDestroy(exec); exec = nullptr; }
+};
+// capture `body` (which enqueues kGraphGens generations on `st`) once, then replay it
+template <class Body>
+static bool graph_replay(GraphCache &gc, cudaStream_t st, Body body) {
+  if (gc.failed) return false;
+  if (!gc.exec) {
+    cudaGraph_t graph = nullptr;
+    if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); gc.failed = true; return false; }
+    const bool ok = body();
+    cudaError_t e = cudaStreamEndCapture(st, &graph);
+    if (!ok || e != cudaSuccess || !graph || cudaGraphInstantiate(&gc.exec, graph, 0) != cudaSuccess) {
+      cudaGetLastError();
+      if (graph) cudaGraphDestroy(graph);
+      gc.exec = nullptr;
+      gc.failed = true;
+      return false;
+    }
+    cudaGraphDestroy(graph);
+  }
+  return cudaGraphLaunch(gc.exec, st) == cudaSuccess;
+}
+
 struct nls_de {
   nls_ctx *ctx;
   nls_de_cfg cfg;
@@ -138,6 +168,7 @@ struct nls_de {
   std::vector<cudaEvent_t> events;      // 4 per timed generation
   double timed_ms[3];
   u64 timed_generations;
+  GraphCache graph;
 };
 
 struct nls_xchg {
@@ -161,6 +192,7 @@ struct nls_pso {
   u64 enqueued;          // generations enqueued so far (the iter value the next move kernel will see)
   bool first_apply_pending;
   nls_xchg *xchg;        // fused peer exchange, or NULL
+  GraphCache graph;
   size_t elem;
 };
 
@@ -236,6 +268,7 @@ int nls_de_destroy(nls_de *de) {
   cudaSetDevice(de->ctx->device);
   cudaStreamSynchronize(de->ctx->stream);
   for (cudaEvent_t e : de->events) cudaEventDestroy(e);
+  de->graph.reset();
   de->mem.release();
   delete de;
   return NLS_OK;
@@ -319,7 +352,19 @@ int nls_de_create(nls_ctx *ctx, const nls_de_cfg *cfg, const void *x0_host, nls_
 int nls_de_step(nls_de *de, uint64_t n_generations) {
   if (!de) return fail(NLS_ERR_INVALID, "nls_de_step: NULL handle");
   NLS_CUDA(cudaSetDevice(de->ctx->device));
-  for (uint64_t g = 0; g < n_generations; g++) {
+  uint64_t left = n_generations;
+  if (!de->timing && de->s.P * de->s.d <= kGraphMaxElems) {
+    while (left >= kGraphGens) {
+      const bool ok = graph_replay(de->graph, de->ctx->stream, [&] {
+        for (int g = 0; g < kGraphGens; g++)
+          if (de->ops->generation(de->s, de->g, de->ctx->stream, nullptr) != cudaSuccess) return false;
+        return true;
+      });
+      if (!ok) break;
+      left -= kGraphGens;
+    }
+  }
+  for (uint64_t g = 0; g < left; g++) {
     cudaEvent_t *ev = nullptr;
     if (de->timing) {
       const size_t base = de->events.size();
@@ -521,9 +566,18 @@ int nls_pso_destroy(nls_pso *pso) {
   if (!pso) return NLS_OK;
   cudaSetDevice(pso->ctx->device);
   cudaStreamSynchronize(pso->ctx->stream);
+  pso->graph.reset();
   pso->mem.release();
   delete pso;
   return NLS_OK;
+}
+
+// inertia the reference would hold while moving in iteration `iter` (nlsolver.h:2613; vanilla keeps the ctor value)
+static double pso_inertia(const nls_pso *p, u64 iter) {
+  if (p->cfg.pso_type == NLS_PSO_VANILLA) return p->cfg.inertia;
+  if (p->cfg.dtype == NLS_F64) return std::pow(p->cfg.inertia, static_cast<double>(iter));
+  return static_cast<double>(static_cast<float>(std::pow(static_cast<double>(static_cast<float>(p->cfg.inertia)),
+                                                         static_cast<double>(iter))));
 }
 
 static int pso_build(nls_ctx *ctx, const nls_pso_cfg *cfg, const void *lower, const void *upper, nls_pso *p) {
@@ -562,6 +616,16 @@ static int pso_build(nls_ctx *ctx, const nls_pso_cfg *cfg, const void *lower, co
   NLS_ALLOC(s.part_idx, p->g.reduce_blocks * sizeof(unsigned long long));
   NLS_ALLOC(s.part_mom, p->g.reduce_blocks * sizeof(Moments));
   NLS_ALLOC(p->record, p->record_bytes);
+  std::vector<double> inertia_table;
+  if (cfg->pso_type == NLS_PSO_ACCELERATED) {
+    const u64 n = std::min<u64>(cfg->max_iter == ~0ull ? 16384 : cfg->max_iter + 1, 16384);
+    inertia_table.resize(n);
+    for (u64 k = 0; k < n; k++) inertia_table[k] = pso_inertia(p, k);
+    double *tab = nullptr;
+    NLS_ALLOC(tab, n * sizeof(double));
+    s.inertia_table = tab;
+    s.inertia_n = n;
+  }
 #undef NLS_ALLOC
   cudaStream_t st = ctx->stream;
   PSOCtrl c0;
@@ -572,6 +636,9 @@ static int pso_build(nls_ctx *ctx, const nls_pso_cfg *cfg, const void *lower, co
   NLS_CUDA(cudaMemsetAsync(p->record, 0, p->record_bytes, st));
   NLS_CUDA(cudaMemsetAsync(s.lower, 0, s.stride * p->elem, st));
   NLS_CUDA(cudaMemsetAsync(s.upper, 0, s.stride * p->elem, st));
+  if (!inertia_table.empty())
+    NLS_CUDA(cudaMemcpyAsync(const_cast<double *>(s.inertia_table), inertia_table.data(),
+                             inertia_table.size() * sizeof(double), cudaMemcpyHostToDevice, st));
   NLS_CUDA(cudaMemcpyAsync(s.lower, lower, d * p->elem, cudaMemcpyHostToDevice, st));
   NLS_CUDA(cudaMemcpyAsync(s.upper, upper, d * p->elem, cudaMemcpyHostToDevice, st));
   NLS_CUDA(cudaStreamSynchronize(st));               // c0 lives on this stack frame
@@ -600,20 +667,12 @@ int nls_pso_create(nls_ctx *ctx, const nls_pso_cfg *cfg, const void *lower_host,
   return NLS_OK;
 }
 
-// inertia the reference would hold while moving in iteration `iter` (nlsolver.h:2613; vanilla keeps the ctor value)
-static double pso_inertia(const nls_pso *p, u64 iter) {
-  if (p->cfg.pso_type == NLS_PSO_VANILLA) return p->cfg.inertia;
-  if (p->cfg.dtype == NLS_F64) return std::pow(p->cfg.inertia, static_cast<double>(iter));
-  return static_cast<double>(static_cast<float>(std::pow(static_cast<double>(static_cast<float>(p->cfg.inertia)),
-                                                         static_cast<double>(iter))));
-}
-
 int nls_pso_step_local(nls_pso *p, void *record_dev) {
   if (!p) return fail(NLS_ERR_INVALID, "nls_pso_step_local: NULL handle");
   if (p->first_apply_pending) return fail(NLS_ERR_STATE, "sharded swarm: apply the initial candidates before stepping");
   NLS_CUDA(cudaSetDevice(p->ctx->device));
   cudaStream_t st = p->ctx->stream;
-  NLS_CUDA(p->ops->move(p->s, pso_inertia(p, p->enqueued), p->g, st));
+  NLS_CUDA(p->ops->move(p->s, p->g, st));
   NLS_CUDA(p->ops->candidate(p->s, p->record, p->g, st));
   p->enqueued++;
   if (record_dev) NLS_CUDA(cudaMemcpyAsync(record_dev, p->record, p->record_bytes, cudaMemcpyDeviceToDevice, st));
@@ -638,7 +697,25 @@ int nls_pso_apply_candidates(nls_pso *p, const void *records_dev, uint64_t n_rec
 int nls_pso_step(nls_pso *p, uint64_t n_generations) {
   if (!p) return fail(NLS_ERR_INVALID, "nls_pso_step: NULL handle");
   if (p->s.P_global != p->s.P) return fail(NLS_ERR_STATE, "nls_pso_step is for a single-GPU swarm; a shard uses step_local / apply_candidates");
-  for (uint64_t g = 0; g < n_generations; g++) {
+  uint64_t left = n_generations;
+  if (p->s.P * p->s.d <= kGraphMaxElems && !p->first_apply_pending) {
+    NLS_CUDA(cudaSetDevice(p->ctx->device));
+    cudaStream_t st = p->ctx->stream;
+    while (left >= kGraphGens) {
+      const bool ok = graph_replay(p->graph, st, [&] {
+        for (int g = 0; g < kGraphGens; g++) {
+          if (p->ops->move(p->s, p->g, st) != cudaSuccess) return false;
+          if (p->ops->candidate(p->s, p->record, p->g, st) != cudaSuccess) return false;
+          if (p->ops->apply(p->s, p->record, 1, p->record_bytes, 0, st) != cudaSuccess) return false;
+        }
+        return true;
+      });
+      if (!ok) break;
+      left -= kGraphGens;
+      p->enqueued += kGraphGens;
+    }
+  }
+  for (uint64_t g = 0; g < left; g++) {
     int rc = nls_pso_step_local(p, nullptr);
     if (rc != NLS_OK) return rc;
     rc = nls_pso_apply_candidates(p, p->record, 1);
@@ -653,9 +730,6 @@ int nls_pso_sync(nls_pso *p, nls_status *status) {
   PSOCtrl c;
   NLS_CUDA(cudaMemcpyAsync(&c, p->s.ctrl, sizeof(c), cudaMemcpyDeviceToHost, p->ctx->stream));
   NLS_CUDA(cudaStreamSynchronize(p->ctx->stream));
-  // a stop rule that fired on the device turned the generations enqueued after it into no-ops; until then every
-  // enqueued generation ran, so the host count (which picks the accelerated inertia, nlsolver.h:2613) is exact
-  if (c.stop) p->enqueued = c.iter;
   if (status) {
     std::memset(status, 0, sizeof(*status));
     status->f_value = c.best_value;
@@ -798,7 +872,7 @@ int nls_pso_step_fused(nls_pso *p, uint64_t n_generations) {
   NLS_CUDA(cudaSetDevice(p->ctx->device));
   cudaStream_t st = p->ctx->stream;
   for (uint64_t g = 0; g < n_generations; g++) {
-    NLS_CUDA(p->ops->move(p->s, pso_inertia(p, p->enqueued), p->g, st));
+    NLS_CUDA(p->ops->move(p->s, p->g, st));
     NLS_CUDA(p->ops->candidate_publish(p->s, p->xchg->w, 0, p->g, st));
     NLS_CUDA(p->ops->gather_apply(p->s, p->xchg->w, 0, st));
     p->enqueued++;

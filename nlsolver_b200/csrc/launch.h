@@ -16,7 +16,7 @@ struct DEOps {
 };
 struct PSOOps {
   cudaError_t (*init)(const PSOState &s, const LaunchGeom &g, cudaStream_t st);
-  cudaError_t (*move)(const PSOState &s, double inertia, const LaunchGeom &g, cudaStream_t st);
+  cudaError_t (*move)(const PSOState &s, const LaunchGeom &g, cudaStream_t st);
   cudaError_t (*candidate)(const PSOState &s, void *record, const LaunchGeom &g, cudaStream_t st);
   cudaError_t (*apply)(const PSOState &s, const void *records, unsigned long long n, unsigned long long record_bytes,
                        int initial, cudaStream_t st);

@@ -70,6 +70,10 @@ struct PSOState {
   int pso_type, objective, constrained, social_j;
   double init_inertia, cog, soc, fm, eps;
   unsigned long long max_iter, vnc_limit;
+  // accelerated type: inertia of loop iteration k = pow(init_inertia, k) (nlsolver.h:2613), tabulated on the host with
+  // the reference's own libm call so that the device never depends on how many generations the host has enqueued
+  const double *inertia_table;
+  unsigned long long inertia_n;
 };
 
 // Peer exchange window of a sharded swarm (one per rank, mapped into every peer through CUDA IPC): for each of the two
