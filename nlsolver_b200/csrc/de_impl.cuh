@@ -308,37 +308,91 @@ __global__ void __launch_bounds__(kBlock) de_repair_kernel(DEState s) {
     // phase A: classify the pending agents.  A donor is "final for this round" iff it was finalised in an EARLIER
     // round (0 < fin < round), which makes the outcome independent of the order in which threads run.
     const u32 n_in = *reinterpret_cast<volatile unsigned int *>(&ctrl->pending[prev]);
-    for (u64 base = warp * 32; base < n_in; base += n_threads) {
-      const u64 idx = base + lane;
-      bool rerun = false, wait = false;
-      u32 i = 0;
-      if (idx < n_in) {
-        i = pin[idx];
-        const uint4 dc = s.dec[i];
-        bool dirty = false;
-        auto look = [&](u64 r) {
-          if (r < i) {
-            const u32 f = s.fin[r];
-            if (f == 0 || f >= round) wait = true;
-            else if (s.acc[r]) dirty = true;
-          }
-        };
-        look(dc.x); look(dc.y); look(dc.z);
-        if (best_mode) look(best_id);
-        if (!wait) { s.fin[i] = uint16_t(round); rerun = dirty; }
+    // Phase A is a chain of dependent L2 reads per entry (list -> donors -> their state -> their donors -> state), so
+    // each thread walks UA entries at once with the loads of one level issued together (predicated, no branches).
+    constexpr int UA = 2;
+    for (u64 base = warp * (32 * UA); base < n_in; base += n_warps * (32 * UA)) {
+      u32 ii[UA];
+      bool valid[UA], wait[UA], dirty[UA];
+      uint4 dc[UA];
+#pragma unroll
+      for (int u = 0; u < UA; u++) {
+        const u64 idx = base + u * 32 + lane;
+        valid[u] = idx < n_in;
+        ii[u] = valid[u] ? pin[idx] : 0u;
       }
-      const u32 vote_w = __ballot_sync(kFull, wait), vote_r = __ballot_sync(kFull, rerun);
-      if (vote_w | vote_r) {
-        u32 slot_w = 0, slot_r = 0;
-        if (lane == 0) {
-          if (vote_w) slot_w = atomicAdd(&ctrl->pending[cur], __popc(vote_w));
-          if (vote_r) slot_r = atomicAdd(&ctrl->list_count[cur], __popc(vote_r));
+#pragma unroll
+      for (int u = 0; u < UA; u++) dc[u] = s.dec[ii[u]];
+      // level 1: the (up to four) lower donors of the entry
+      u32 don[UA][4], f1[UA][4];
+      bool low[UA][4];
+#pragma unroll
+      for (int u = 0; u < UA; u++) {
+        don[u][0] = dc[u].x; don[u][1] = dc[u].y; don[u][2] = dc[u].z; don[u][3] = u32(best_id);
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          low[u][k] = valid[u] && don[u][k] < ii[u] && (k < 3 || best_mode);
+          f1[u][k] = low[u][k] ? u32(s.fin[don[u][k]]) : 1u;
         }
-        slot_w = __shfl_sync(kFull, slot_w, 0);
-        slot_r = __shfl_sync(kFull, slot_r, 0);
-        const u32 below = (1u << lane) - 1u;
-        if (wait) pout[slot_w + __popc(vote_w & below)] = i;
-        if (rerun) s.list[slot_r + __popc(vote_r & below)] = i;
+      }
+      // A donor is "settled" iff it was finalised in an EARLIER round (0 < fin < round): everything read here was
+      // written before this round's barrier, so the outcome does not depend on the order in which threads run.
+      u32 a1[UA][4];
+      uint4 dd[UA][4];
+      bool deep[UA][4];
+#pragma unroll
+      for (int u = 0; u < UA; u++)
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          const bool settled = f1[u][k] != 0 && f1[u][k] < round;
+          deep[u][k] = low[u][k] && !settled;
+          a1[u][k] = low[u][k] ? u32(s.acc[don[u][k]]) : 0u;        // speculative / settled accept flag of the donor
+          dd[u][k] = deep[u][k] ? s.dec[don[u][k]] : make_uint4(0, 0, 0, 0);
+        }
+      // level 2: a donor r that is still pending is looked through — if all of ITS lower donors are settled and none of
+      // them was accepted, r becomes final this round WITHOUT re-evaluation, i.e. with the accept flag it already has,
+      // and the entry can rely on that now instead of waiting a round (two DAG levels per barrier).
+#pragma unroll
+      for (int u = 0; u < UA; u++) {
+        wait[u] = false; dirty[u] = false;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          bool clean = true;
+          if (deep[u][k]) {
+            const u32 r = don[u][k];
+            const u32 q[4] = {dd[u][k].x, dd[u][k].y, dd[u][k].z, u32(best_id)};
+#pragma unroll
+            for (int m = 0; m < 4; m++) {
+              const bool lowq = q[m] < r && (m < 3 || best_mode);
+              const u32 fq = lowq ? u32(s.fin[q[m]]) : 1u;
+              const u32 aq = lowq ? u32(s.acc[q[m]]) : 0u;
+              clean &= (fq != 0 && fq < round) && aq == 0;
+            }
+          }
+          if (low[u][k]) {
+            if (deep[u][k] && !clean) wait[u] = true;
+            else dirty[u] |= a1[u][k] != 0;
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < UA; u++) {
+        const bool w_ = valid[u] && wait[u];
+        const bool rerun = valid[u] && !wait[u] && dirty[u];
+        if (valid[u] && !wait[u]) s.fin[ii[u]] = uint16_t(round);
+        const u32 vote_w = __ballot_sync(kFull, w_), vote_r = __ballot_sync(kFull, rerun);
+        if (vote_w | vote_r) {
+          u32 slot_w = 0, slot_r = 0;
+          if (lane == 0) {
+            if (vote_w) slot_w = atomicAdd(&ctrl->pending[cur], __popc(vote_w));
+            if (vote_r) slot_r = atomicAdd(&ctrl->list_count[cur], __popc(vote_r));
+          }
+          slot_w = __shfl_sync(kFull, slot_w, 0);
+          slot_r = __shfl_sync(kFull, slot_r, 0);
+          const u32 below = (1u << lane) - 1u;
+          if (w_) pout[slot_w + __popc(vote_w & below)] = ii[u];
+          if (rerun) s.list[slot_r + __popc(vote_r & below)] = ii[u];
+        }
       }
     }
     grid.sync();
