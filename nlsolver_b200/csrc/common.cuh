@@ -73,6 +73,15 @@ __device__ __forceinline__ void ld_row(const float *p, float (&x)[4]) {
   const float4 v = __ldcg(reinterpret_cast<const float4 *>(p));
   x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w;
 }
+// read-only rows shared by every agent / particle of a launch (swarm best, bounds, DE best row): keep them in L1
+__device__ __forceinline__ void ld_row_shared(const double *p, double (&x)[2]) {
+  const double2 v = __ldg(reinterpret_cast<const double2 *>(p));
+  x[0] = v.x; x[1] = v.y;
+}
+__device__ __forceinline__ void ld_row_shared(const float *p, float (&x)[4]) {
+  const float4 v = __ldg(reinterpret_cast<const float4 *>(p));
+  x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w;
+}
 __device__ __forceinline__ void st_row(double *p, const double (&x)[2]) {
   __stcg(reinterpret_cast<double2 *>(p), make_double2(x[0], x[1]));
 }

@@ -48,7 +48,9 @@ __device__ __forceinline__ const T *de_row_of(const DEState &s, u64 r, u64 i) {
 #define NLS_DE_UNROLL 1
 #endif
 // W lanes cooperate on the agent (`lane` is the index inside that group); W < 32 requires d <= W * V.
-template <class T, int OBJ, bool EVAL, bool WRITE, int W = 32>
+// SHARED_BASE: the base row is the single best row (best recombination, speculative pass): read-only for the launch and
+// shared by every agent, so it goes through L1 instead of being re-fetched from L2 per agent.
+template <class T, int OBJ, bool EVAL, bool WRITE, int W = 32, bool SHARED_BASE = false>
 __device__ __forceinline__ T de_sweep(const DEState &s, const T *p0, const T *p1, const T *p2, const T *p3, T *dst,
                                       u64 sbase, u32 dim, u64 i, int lane) {
   constexpr int V = Vec<T>::V;
@@ -78,7 +80,10 @@ __device__ __forceinline__ T de_sweep(const DEState &s, const T *p0, const T *p1
       }
       const u32 jl = jj < d ? jj : 0u;
       ld_row(p1 + jl, x1[u]); ld_row(p2 + jl, x2[u]); ld_row(p3 + jl, x3[u]);
-      if (!all_mut) ld_row(p0 + jl, x0[u]);            // the base row is only touched where a coordinate keeps it
+      if (!all_mut) {                                  // the base row is only touched where a coordinate keeps it
+        if (SHARED_BASE) ld_row_shared(p0 + jl, x0[u]);
+        else ld_row(p0 + jl, x0[u]);
+      }
     }
 #pragma unroll
     for (int u = 0; u < U; u++) {
@@ -259,7 +264,9 @@ __global__ void __launch_bounds__(kBlock, NLS_DE_MINBLOCKS) de_generation_kernel
       const T *p3 = static_cast<const T *>(s.buf[(e.wbits >> 3) & 1u]) + u64(e.r3) * s.stride;
       T *dst = static_cast<T *>(s.buf[((e.wbits >> 4) & 1u) ^ 1u]) + i * s.stride;
       const u64 sbase = tape_state(e.key, 4 + e.rej);
-      const T raw = de_sweep<T, OBJ, true, false, W>(s, p0, p1, p2, p3, dst, sbase, e.dim, i, sub);
+      // (warp-uniform branch: in best mode every agent's base row is the pre-generation best row)
+      const T raw = random_mode ? de_sweep<T, OBJ, true, false, W, false>(s, p0, p1, p2, p3, dst, sbase, e.dim, i, sub)
+                                : de_sweep<T, OBJ, true, false, W, true>(s, p0, p1, p2, p3, dst, sbase, e.dim, i, sub);
       const T sc = Ar<T>::mul(static_cast<T>(s.fm), raw);
       const bool ok = active && sc < static_cast<T>(e.score);   // strict <, NaN never accepted (nlsolver.h:2466)
       if (ok) de_sweep<T, OBJ, false, true, W>(s, p0, p1, p2, p3, dst, sbase, e.dim, i, sub);
