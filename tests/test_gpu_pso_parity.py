@@ -160,7 +160,7 @@ def test_sharded_swarm_equals_single_swarm(ctx):
 
 def test_fused_peer_exchange_single_rank_equals_plain_step(ctx):
     """nls_pso_step_fused with a one-rank exchange window (records published into the rank's own window) must equal
-    nls_pso_step; the multi-rank case needs several GPUs and is checked by tools/multi_gpu_check.py."""
+    nls_pso_step; the multi-rank case needs several GPUs and is checked by tests/tools/multi_gpu_check.py."""
     P, d, G = 500, 40, 7
     up = np.full(d, 5.12)
     kw = dict(objective=nb.RASTRIGIN, pso_type=nb.PSO_ACCELERATED, n_particles=P, dim=d, eps=0.0, max_iter=1 << 40,

@@ -9,7 +9,7 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import nlsolver_b200 as nb  # noqa: E402
 from nlsolver_b200 import distributed as D  # noqa: E402
 from oracle import binding as B  # noqa: E402

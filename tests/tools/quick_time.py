@@ -1,12 +1,12 @@
 """Kernel-level timing of one DE configuration (tuning aid; bench.py is the measurement of record).
-usage: python tools/quick_time.py [P] [d] [G] [objective] ; env NLS_B200_LIB selects a library variant."""
+usage: python tests/tools/quick_time.py [P] [d] [G] [objective] ; env NLS_B200_LIB selects a library variant."""
 import os
 import sys
 
 import numpy as np
 import torch
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import nlsolver_b200 as nb  # noqa: E402
 
 P = int(sys.argv[1]) if len(sys.argv) > 1 else 1 << 20

@@ -5,7 +5,7 @@ import sys
 import numpy as np
 import torch
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import nlsolver_b200 as nb  # noqa: E402
 from oracle import binding as B  # noqa: E402
 

@@ -78,7 +78,7 @@ if t:
         "source": f"profiles/{TAG}_de_generation_ncu_full.txt (dram__bytes_read.sum + dram__bytes_write.sum, mean of the captured launches)"}},
         open(os.path.join(PROF, "roofline_traffic.json"), "w"), indent=1)
 ncu_raw("prof_pso_move.ncu-rep", "pso_move_kernel", WANT,
-        "ncu --set full --clock-control none -k regex:pso_move_kernel -s 4 -c 1 python tools/quick_time_pso.py 2097152 256 3 3 1 1"
+        "ncu --set full --clock-control none -k regex:pso_move_kernel -s 4 -c 1 python tests/tools/quick_time_pso.py 2097152 256 3 3 1 1"
         "   (B200; accelerated PSO, Ackley d=256, 2^21 particles, fp64 = one GPU's share of BASELINE configs[2])",
         f"{TAG}_pso_move_ncu_full.txt")
 
