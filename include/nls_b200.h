@@ -179,6 +179,12 @@ NLS_API int nls_pso_step_local(nls_pso *pso, void *record_dev);
 NLS_API int nls_pso_export_candidate(nls_pso *pso, void *record_dev);
 NLS_API int nls_pso_apply_candidates(nls_pso *pso, const void *records_dev, uint64_t n_records);
 
+/* ---- objective plugins: the reference accepts ANY functor as Callable (README.md:127-136); on
+ * the GPU a functor must be device code, so a user objective is a small .cu file built on
+ * nlsolver_b200/csrc/objective_plugin.cuh and compiled with nvcc into a shared library.  nls_load_objective loads it and
+ * returns an objective id (>= 100) valid wherever NLS_SPHERE ... are (nls_de_cfg.objective, nls_pso_cfg.objective). */
+NLS_API int nls_load_objective(const char *plugin_path, int32_t *objective_id);
+
 /* ---- fused exchange over peer memory (NVLink / NVSwitch), no host-side collective ----
  * Each rank owns an exchange WINDOW in its HBM that every peer maps through CUDA IPC.  nls_pso_step_fused runs, per
  * generation: move kernel -> candidate kernel whose last block stores the shard's record directly into every peer's

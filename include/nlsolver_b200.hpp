@@ -235,6 +235,22 @@ template <typename T> constexpr int dtype_of() {
 inline void check(int rc) {
   if (rc != NLS_OK) throw std::runtime_error(std::string("nls_b200: ") + nls_last_error());
 }
+// A user objective built as an objective plugin (nlsolver_b200/csrc/objective_plugin.cuh) fills the Callable slot
+// through this type:   auto prob = nlsolver::b200::load_objective("libmy_objective.so");
+//                      nlsolver::DE<nlsolver::b200::PluginObjective, xorshift<double>> solver(prob, gen);
+struct PluginObjective { int id; };
+inline PluginObjective load_objective(const std::string &plugin_path) {
+  int32_t id = -1;
+  check(nls_load_objective(plugin_path.c_str(), &id));
+  return PluginObjective{id};
+}
+template <typename C> constexpr bool is_objective() {
+  return objective_of<C>::value >= 0 || std::is_same<C, PluginObjective>::value;
+}
+template <typename C> int objective_id(const C &f) {
+  if constexpr (std::is_same<C, PluginObjective>::value) return f.id;
+  else return objective_of<C>::value;
+}
 // one context per process, created on first use on device $NLS_B200_DEVICE (default 0)
 inline nls_ctx *default_context() {
   struct Holder {
@@ -300,9 +316,10 @@ enum RecombinationStrategy { best, random };   // nlsolver.h:2377
 template <typename Callable, typename RNG, typename scalar_t = double,
           RecombinationStrategy RecombinationType = random>
 class DE {
-  static_assert(b200::objective_of<Callable>::value >= 0,
+  static_assert(b200::is_objective<Callable>(),
                 "nlsolver_b200: Callable must be a device objective tag (nlsolver::test_functions::Sphere, "
-                "Rosenbrock, Rastrigin, Ackley, RosenbrockExample); host functors cannot run on the GPU");
+                "Rosenbrock, Rastrigin, Ackley, RosenbrockExample) or a loaded nlsolver::b200::PluginObjective; "
+                "host functors cannot run on the GPU");
 
  public:
   DE(Callable &f, RNG &generator, const scalar_t crossover_prob = 0.9, const scalar_t differential_weight = 0.8,
@@ -317,7 +334,7 @@ class DE {
   solver_status<scalar_t> solve(std::vector<scalar_t> &x, bool minimize) {
     nls_de_cfg cfg{};
     cfg.dtype = b200::dtype_of<scalar_t>();
-    cfg.objective = b200::objective_of<Callable>::value;
+    cfg.objective = b200::objective_id(f);
     cfg.strategy = RecombinationType == random ? NLS_DE_RANDOM : NLS_DE_BEST;
     cfg.minimize = minimize ? 1 : 0;
     cfg.pop_size = pop_size;
@@ -346,8 +363,9 @@ enum PSOType { Vanilla, Accelerated };   // nlsolver.h:2496
 // nlsolver.h:2498-2742
 template <typename Callable, typename RNG, typename scalar_t = double, PSOType Type = Vanilla>
 class PSO {
-  static_assert(b200::objective_of<Callable>::value >= 0,
-                "nlsolver_b200: Callable must be a device objective tag (see nlsolver::test_functions)");
+  static_assert(b200::is_objective<Callable>(),
+                "nlsolver_b200: Callable must be a device objective tag (see nlsolver::test_functions) or a loaded "
+                "nlsolver::b200::PluginObjective");
 
  public:
   PSO(Callable &f, RNG &generator, const scalar_t inertia = 0.8, const scalar_t cognitive_coef = 1.8,
@@ -375,7 +393,7 @@ class PSO {
     if (lower.size() != upper.size()) throw std::invalid_argument("nlsolver_b200: lower / upper sizes differ");
     nls_pso_cfg cfg{};
     cfg.dtype = b200::dtype_of<scalar_t>();
-    cfg.objective = b200::objective_of<Callable>::value;
+    cfg.objective = b200::objective_id(f);
     cfg.pso_type = Type == Vanilla ? NLS_PSO_VANILLA : NLS_PSO_ACCELERATED;
     cfg.minimize = minimize ? 1 : 0;
     cfg.n_particles = n_particles;

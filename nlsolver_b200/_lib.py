@@ -90,6 +90,7 @@ SYMBOLS = {
     "nls_pso_step_local": (C.c_int, [P, P]),
     "nls_pso_export_candidate": (C.c_int, [P, P]),
     "nls_pso_apply_candidates": (C.c_int, [P, P, u64]),
+    "nls_load_objective": (C.c_int, [C.c_char_p, C.POINTER(i32)]),
     "nls_xchg_create": (C.c_int, [P, u64, C.c_int, C.c_int, C.POINTER(P)]),
     "nls_xchg_get_handle": (C.c_int, [P, P]),
     "nls_xchg_open_peers": (C.c_int, [P, P]),

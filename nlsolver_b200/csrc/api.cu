@@ -3,6 +3,8 @@
 // Owns every device allocation behind opaque handles, validates arguments (the reference validates nothing:
 // pop_size < 4 loops forever in generate_indices, nlsolver.h:2344-2354), turns CUDA errors into return codes and
 // enqueues the kernels of de_impl.cuh / pso_impl.cuh on the context stream.  No CPU compute path exists here.
+#include <dlfcn.h>
+
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -42,6 +44,25 @@ int fail(int code, const char *fmt, ...) {
   } while (0)
 
 size_t elem_size(int dtype) { return dtype == NLS_F64 ? 8 : 4; }
+
+// objective plugins (objective_plugin.cuh): same ops tables as the built-in dtypes, instantiated for a user functor
+struct ObjectivePlugin {
+  int abi;
+  const DEOps *de_f64, *de_f32;
+  const PSOOps *pso_f64, *pso_f32;
+};
+constexpr int kFirstPluginId = 100;
+std::vector<const ObjectivePlugin *> &plugin_registry() {
+  static std::vector<const ObjectivePlugin *> r;
+  return r;
+}
+const ObjectivePlugin *plugin_for(int objective) {
+  const int k = objective - kFirstPluginId;
+  return (k >= 0 && k < int(plugin_registry().size())) ? plugin_registry()[k] : nullptr;
+}
+bool objective_known(int objective) {
+  return (objective >= 0 && objective <= NLS_ROSENBROCK_EX) || plugin_for(objective) != nullptr;
+}
 u64 round_up(u64 v, u64 m) { return (v + m - 1) / m * m; }
 
 // host mirror of unit<T>() for the crossover threshold search
@@ -255,7 +276,7 @@ uint64_t nls_record_bytes(int32_t dtype, uint64_t dim) {
 
 static int de_validate(const nls_de_cfg *c) {
   if (c->dtype != NLS_F32 && c->dtype != NLS_F64) return fail(NLS_ERR_INVALID, "DE: unknown dtype %d", c->dtype);
-  if (c->objective < 0 || c->objective > NLS_ROSENBROCK_EX) return fail(NLS_ERR_INVALID, "DE: unknown objective %d", c->objective);
+  if (!objective_known(c->objective)) return fail(NLS_ERR_INVALID, "DE: unknown objective %d", c->objective);
   if (c->strategy != NLS_DE_BEST && c->strategy != NLS_DE_RANDOM) return fail(NLS_ERR_INVALID, "DE: unknown strategy %d", c->strategy);
   if (c->pop_size < 4) return fail(NLS_ERR_INVALID, "DE: pop_size must be >= 4 (three distinct donors besides the fixed agent)");
   if (c->dim < 1) return fail(NLS_ERR_INVALID, "DE: dim must be >= 1");
@@ -284,13 +305,15 @@ static int de_build(nls_ctx *ctx, const nls_de_cfg *cfg, const void *x0_host, nl
   de->timed_generations = 0;
   de->elem = elem_size(cfg->dtype);
   de->ops = cfg->dtype == NLS_F64 ? de_ops_f64() : de_ops_f32();
+  if (const ObjectivePlugin *pl = plugin_for(cfg->objective)) de->ops = cfg->dtype == NLS_F64 ? pl->de_f64 : pl->de_f32;
   de->g = make_geom(ctx, P);
   DEState &s = de->s;
   std::memset(&s, 0, sizeof(s));
   s.P = P; s.d = d;
   s.stride = round_up(d, 32 / de->elem);            // rows start on 32-byte sector boundaries
   s.seed = cfg->seed; s.offset = cfg->agent_offset;
-  s.strategy = cfg->strategy; s.objective = cfg->objective;
+  s.strategy = cfg->strategy;
+  s.objective = plugin_for(cfg->objective) ? 100 /* OBJ_CUSTOM */ : cfg->objective;
   s.F = cfg->differential_weight; s.fm = cfg->minimize ? 1.0 : -1.0; s.eps = cfg->eps;
   s.max_iter = cfg->max_iter; s.vnc_limit = cfg->best_val_no_change;
   u64 cr_le; int cr_none;
@@ -550,7 +573,7 @@ int nls_de_solve(nls_ctx *ctx, const nls_de_cfg *cfg, const void *x0_host, void 
 
 static int pso_validate(const nls_pso_cfg *c) {
   if (c->dtype != NLS_F32 && c->dtype != NLS_F64) return fail(NLS_ERR_INVALID, "PSO: unknown dtype %d", c->dtype);
-  if (c->objective < 0 || c->objective > NLS_ROSENBROCK_EX) return fail(NLS_ERR_INVALID, "PSO: unknown objective %d", c->objective);
+  if (!objective_known(c->objective)) return fail(NLS_ERR_INVALID, "PSO: unknown objective %d", c->objective);
   if (c->pso_type != NLS_PSO_VANILLA && c->pso_type != NLS_PSO_ACCELERATED) return fail(NLS_ERR_INVALID, "PSO: unknown type %d", c->pso_type);
   if (c->n_particles < 1 || c->dim < 1) return fail(NLS_ERR_INVALID, "PSO: n_particles and dim must be >= 1");
   const u64 pg = c->n_particles_global ? c->n_particles_global : c->n_particles;
@@ -587,6 +610,7 @@ static int pso_build(nls_ctx *ctx, const nls_pso_cfg *cfg, const void *lower, co
   p->cfg = *cfg;
   p->elem = elem_size(cfg->dtype);
   p->ops = cfg->dtype == NLS_F64 ? pso_ops_f64() : pso_ops_f32();
+  if (const ObjectivePlugin *pl = plugin_for(cfg->objective)) p->ops = cfg->dtype == NLS_F64 ? pl->pso_f64 : pl->pso_f32;
   p->g = make_geom(ctx, P);
   p->enqueued = 0;
   p->xchg = nullptr;
@@ -595,7 +619,8 @@ static int pso_build(nls_ctx *ctx, const nls_pso_cfg *cfg, const void *lower, co
   s.P = P; s.d = d; s.stride = round_up(d, 32 / p->elem);
   s.P_global = cfg->n_particles_global ? cfg->n_particles_global : P;
   s.seed = cfg->seed; s.offset = cfg->particle_offset;
-  s.pso_type = cfg->pso_type; s.objective = cfg->objective; s.constrained = cfg->constrained;
+  s.pso_type = cfg->pso_type; s.constrained = cfg->constrained;
+  s.objective = plugin_for(cfg->objective) ? 100 /* OBJ_CUSTOM */ : cfg->objective;
   s.social_j = (cfg->flags & NLS_FLAG_SOCIAL_INDEX_J) ? 1 : 0;
   s.init_inertia = cfg->inertia; s.cog = cfg->cognitive_coef; s.soc = cfg->social_coef;
   s.fm = cfg->minimize ? 1.0 : -1.0; s.eps = cfg->eps;
@@ -787,6 +812,25 @@ int nls_pso_solve(nls_ctx *ctx, const nls_pso_cfg *cfg, const void *lower_host, 
   if (rc == NLS_OK && status) *status = st;
   nls_pso_destroy(p);
   return rc;
+}
+
+/* ================================================================ objective plugins =========================== */
+
+int nls_load_objective(const char *plugin_path, int32_t *objective_id) {
+  if (!plugin_path || !objective_id) return fail(NLS_ERR_INVALID, "nls_load_objective: NULL argument");
+  void *h = dlopen(plugin_path, RTLD_NOW | RTLD_LOCAL);
+  if (!h) return fail(NLS_ERR_INVALID, "nls_load_objective: %s", dlerror());
+  typedef const ObjectivePlugin *(*entry_t)();
+  entry_t entry = reinterpret_cast<entry_t>(dlsym(h, "nls_objective_plugin_v1"));
+  if (!entry) { dlclose(h); return fail(NLS_ERR_INVALID, "nls_load_objective: %s exports no nls_objective_plugin_v1", plugin_path); }
+  const ObjectivePlugin *pl = entry();
+  if (!pl || pl->abi != 1 || !pl->de_f64 || !pl->de_f32 || !pl->pso_f64 || !pl->pso_f32) {
+    dlclose(h);
+    return fail(NLS_ERR_INVALID, "nls_load_objective: plugin ABI mismatch (rebuild it against this library's headers)");
+  }
+  plugin_registry().push_back(pl);    // the handle stays open for the life of the process
+  *objective_id = kFirstPluginId + int(plugin_registry().size()) - 1;
+  return NLS_OK;
 }
 
 /* ================================================================ peer exchange =============================== */

@@ -562,6 +562,13 @@ inline unsigned int clamp_grid(u64 want, u64 cap) {
   return static_cast<unsigned int>(g < 1 ? 1 : g);
 }
 
+#ifdef NLS_PLUGIN_BUILD   // an objective plugin instantiates the kernels for its own functor only
+#define NLS_OBJ_SWITCH(obj, CALL)                             \
+  switch (obj) {                                       \
+    case OBJ_CUSTOM: { CALL(OBJ_CUSTOM); } break;      \
+    default: return cudaErrorInvalidValue;             \
+  }
+#else
 #define NLS_OBJ_SWITCH(obj, CALL)                      \
   switch (obj) {                                       \
     case OBJ_SPHERE: { CALL(OBJ_SPHERE); } break;      \
@@ -571,6 +578,7 @@ inline unsigned int clamp_grid(u64 want, u64 cap) {
     case OBJ_ROSENBROCK_EX: { CALL(OBJ_ROSENBROCK_EX); } break; \
     default: return cudaErrorInvalidValue;             \
   }
+#endif
 
 template <class T>
 cudaError_t de_launch_commit(const DEState &s, int mode, const LaunchGeom &g, cudaStream_t st) {
@@ -630,7 +638,6 @@ void de_launch_k2(const DEState &s, const LaunchGeom &g, cudaStream_t st) {
 // one generation: K2, K2r (cooperative), K3
 template <class T>
 cudaError_t de_launch_generation(const DEState &s, const LaunchGeom &g, cudaStream_t st, cudaEvent_t *ev) {
-  const u64 want = (s.P + kWarpsPerBlock - 1) / kWarpsPerBlock;
   cudaError_t e = cudaSuccess;
   if (ev) cudaEventRecord(ev[0], st);
 #define NLS_CALL(O)                                                                                                 \

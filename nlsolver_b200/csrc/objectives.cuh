@@ -10,20 +10,34 @@
 
 namespace nls {
 
-enum { OBJ_SPHERE = 0, OBJ_ROSENBROCK = 1, OBJ_RASTRIGIN = 2, OBJ_ACKLEY = 3, OBJ_ROSENBROCK_EX = 4, OBJ_COUNT = 5 };
+enum { OBJ_SPHERE = 0, OBJ_ROSENBROCK = 1, OBJ_RASTRIGIN = 2, OBJ_ACKLEY = 3, OBJ_ROSENBROCK_EX = 4, OBJ_COUNT = 5,
+       OBJ_CUSTOM = 100 };
+
+// User-supplied objective of an objective plugin (objective_plugin.cuh): defined only in the plugin's translation unit.
+//   static constexpr bool pairwise;                      term also receives x[j-1] (terms start at j = 1)
+//   static __device__ T lane0_seed(unsigned d);          constant the sum starts from (0 for a plain sum)
+//   static __device__ T term(T x, T x_prev, unsigned j, unsigned d);
+//   static __device__ T finish(T sum, unsigned d);
+// f(x) = finish(lane0_seed + sum_j term(x[j], x[j-1], j, d), d), summed in the canonical lane order.
+template <class T> struct CustomObjective;
 
 // W = lanes that cooperate on one agent (32, or a smaller power of two when d <= W * V so that one step covers the
 // row); `lane` arguments are lane indices INSIDE the group.
 template <class T, int OBJ, int W = 32>
 struct Objective {
   static constexpr int V = Vec<T>::V;
-  static constexpr bool kPairwise = (OBJ == OBJ_ROSENBROCK || OBJ == OBJ_ROSENBROCK_EX);
+  static constexpr bool custom_pairwise() {
+    if constexpr (OBJ == OBJ_CUSTOM) return CustomObjective<T>::pairwise;
+    else return false;
+  }
+  static constexpr bool kPairwise = (OBJ == OBJ_ROSENBROCK || OBJ == OBJ_ROSENBROCK_EX) || custom_pairwise();
   typedef Ar<T> A;
   T a, b, carry;
 
   __device__ __forceinline__ void begin(int lane, u32 d) {
     // Rastrigin's leading `2*10` (10*d in N-D) seeds lane 0's accumulator so that d = 2 gives (20 + t0) + t1
     a = (OBJ == OBJ_RASTRIGIN && lane == 0) ? A::mul(T(10), T(d)) : T(0);
+    if constexpr (OBJ == OBJ_CUSTOM) a = lane == 0 ? CustomObjective<T>::lane0_seed(d) : T(0);
     b = T(0);
     carry = T(0);
   }
@@ -41,7 +55,10 @@ struct Objective {
     for (int q = 0; q < V; q++) {
       const u32 j = j0 + q;
       const T xj = x[q];
-      if (kPairwise) {
+      if constexpr (OBJ == OBJ_CUSTOM) {
+        const T xl = (q == 0) ? left : x[q == 0 ? 0 : q - 1];
+        if ((!kPairwise || j >= 1) && j < d) a = A::add(a, CustomObjective<T>::term(xj, xl, j, d));
+      } else if (kPairwise) {
         const T xl = (q == 0) ? left : x[q == 0 ? 0 : q - 1];
         if (j >= 1 && j < d) {
           if (OBJ == OBJ_ROSENBROCK) {                     // 100*pow(x0*x0 - x1, 2) + pow(x0 - 1, 2)
@@ -68,6 +85,7 @@ struct Objective {
   // every lane returns the objective value
   __device__ __forceinline__ T finish(u32 d) {
     a = warp_butterfly_add<T, W>(a);
+    if constexpr (OBJ == OBJ_CUSTOM) return CustomObjective<T>::finish(a, d);
     if (OBJ == OBJ_ACKLEY) {
       b = warp_butterfly_add<T, W>(b);
       const T inv_d = T(1.0) / T(d);

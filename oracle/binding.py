@@ -18,6 +18,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 
 F32, F64 = 0, 1
 SPHERE, ROSENBROCK, RASTRIGIN, ACKLEY, ROSENBROCK_EX = range(5)
+CUSTOM = 100
 DE_BEST, DE_RANDOM = 0, 1
 PSO_VANILLA, PSO_ACCELERATED = 0, 1
 RNG_TAPE, RNG_XORSHIFT = 0, 1
@@ -173,6 +174,20 @@ def pso_run(lib, cfg, lower, upper, prefix=None):
     if rc != 0:
         raise RuntimeError(f"{prefix}pso_run failed: {rc}")
     return st.as_dict(), a
+
+
+TERM_FN = C.CFUNCTYPE(f64, f64, f64, u64, u64)
+FINISH_FN = C.CFUNCTYPE(f64, f64, u64)
+_custom_keepalive = []
+
+
+def set_custom_objective(term, finish, pairwise=False, lane0_seed=0.0):
+    """Install Python callables as objective CUSTOM of the restatement (small cases only: one call per coordinate)."""
+    lib = oracle()
+    t, f = TERM_FN(term), FINISH_FN(finish)
+    _custom_keepalive[:] = [t, f]
+    lib.oracle_set_custom_objective.argtypes = [C.c_int, f64, TERM_FN, FINISH_FN]
+    lib.oracle_set_custom_objective(int(pairwise), lane0_seed, t, f)
 
 
 def objective(dtype, obj_id, x):

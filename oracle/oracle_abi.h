@@ -20,7 +20,8 @@ extern "C" {
 
 enum { ORC_F32 = 0, ORC_F64 = 1 };
 /* objective ids: N-D forms that reduce to test_functions.h:51-92 at d = 2; id 4 is example.cpp:41-48 */
-enum { ORC_SPHERE = 0, ORC_ROSENBROCK = 1, ORC_RASTRIGIN = 2, ORC_ACKLEY = 3, ORC_ROSENBROCK_EX = 4 };
+enum { ORC_SPHERE = 0, ORC_ROSENBROCK = 1, ORC_RASTRIGIN = 2, ORC_ACKLEY = 3, ORC_ROSENBROCK_EX = 4,
+       ORC_CUSTOM = 100 /* callbacks installed with oracle_set_custom_objective (objective-plugin tests) */ };
 /* same order as the reference enums (nlsolver.h:2377, 2496) */
 enum { ORC_DE_BEST = 0, ORC_DE_RANDOM = 1 };
 enum { ORC_PSO_VANILLA = 0, ORC_PSO_ACCELERATED = 1 };

@@ -105,10 +105,23 @@ struct Lanes {
   }
 };
 
+/* custom objective of the objective-plugin tests: f = finish(seed + sum_j term(x[j], x[j-1], j, d), d) in the canonical
+ * lane order, the contract of nlsolver_b200/csrc/objective_plugin.cuh */
+typedef double (*orc_term_fn)(double x, double x_prev, uint64_t j, uint64_t d);
+typedef double (*orc_finish_fn)(double sum, uint64_t d);
+struct CustomObjective { int pairwise = 0; double seed = 0; orc_term_fn term = nullptr; orc_finish_fn finish = nullptr; } g_custom;
+
 template <class T>
 T objective(int id, const T *x, size_t d) {
   const T two_pi = static_cast<T>(2 * M_PI);
   switch (id) {
+    case ORC_CUSTOM: {
+      if (!g_custom.term || !g_custom.finish) return std::nan("");
+      Lanes<T> s(static_cast<T>(g_custom.seed));
+      for (size_t j = g_custom.pairwise ? 1 : 0; j < d; j++)
+        s.add(j, static_cast<T>(g_custom.term(x[j], j ? x[j - 1] : 0, j, d)));
+      return static_cast<T>(g_custom.finish(s.total(), d));
+    }
     case ORC_SPHERE: {  /* test_functions.h:55  x0*x0 + x1*x1 */
       Lanes<T> s;
       for (size_t j = 0; j < d; j++) s.add(j, x[j] * x[j]);
@@ -507,6 +520,10 @@ int oracle_pso_adopt(void *p, int have, double value, uint64_t global_index, con
 void oracle_pso_move(void *p) { static_cast<PSOHandle *>(p)->move(); }
 void oracle_pso_report(void *p, const orc_pso_out *out, orc_status *st) { static_cast<PSOHandle *>(p)->report(out, st); }
 void oracle_pso_close(void *p) { delete static_cast<PSOHandle *>(p); }
+
+void oracle_set_custom_objective(int pairwise, double lane0_seed, orc_term_fn term, orc_finish_fn finish) {
+  g_custom.pairwise = pairwise; g_custom.seed = lane0_seed; g_custom.term = term; g_custom.finish = finish;
+}
 
 double oracle_objective(int dtype, int id, const void *x, uint64_t d) {
   return dtype == ORC_F64 ? objective<double>(id, static_cast<const double *>(x), d)

@@ -1,0 +1,116 @@
+"""Objective plugins: a user objective compiled from functor source runs through the same DE / PSO
+kernels; checked against the oracle with the same objective installed as Python callbacks (canonical lane order)."""
+import numpy as np
+import pytest
+
+import nlsolver_b200 as nb
+from nlsolver_b200 import plugins
+from oracle import binding as B
+from tests.gpu_util import bits, rel_close
+
+pytestmark = pytest.mark.gpu
+
+STYBLINSKI = """
+template <class T> struct StyblinskiTang {          // f(x) = 0.5 * sum(x^4 - 16 x^2 + 5 x)  (test_functions.h StyblinskiTang, N-D)
+  static constexpr bool pairwise = false;
+  static __device__ T lane0_seed(unsigned) { return T(0); }
+  static __device__ T term(T x, T, unsigned, unsigned) { const T x2 = x * x; return x2 * x2 - T(16) * x2 + T(5) * x; }
+  static __device__ T finish(T sum, unsigned) { return T(0.5) * sum; }
+};
+"""
+CHAIN = """
+template <class T> struct Chain {                   // pairwise form: sum_{j>=1} (x_j - x_{j-1})^2 + 3, then sqrt
+  static constexpr bool pairwise = true;
+  static __device__ T lane0_seed(unsigned) { return T(3); }
+  static __device__ T term(T x, T xp, unsigned, unsigned) { const T t = x - xp; return t * t; }
+  static __device__ T finish(T sum, unsigned d) { return sqrt(sum) + T(d); }
+};
+"""
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = nb.Context(0)
+    yield c
+    c.close()
+
+
+@pytest.fixture(scope="module")
+def plugin_ids(tmp_path_factory):
+    out = str(tmp_path_factory.mktemp("objectives"))
+    ids = {}
+    for name, src in (("StyblinskiTang", STYBLINSKI), ("Chain", CHAIN)):
+        so = plugins.compile_objective(src, name, out_dir=out, extra_flags=("-fmad=false",))
+        ids[name] = plugins.load_objective(so)
+    assert all(v >= 100 for v in ids.values()) and len(set(ids.values())) == 2
+    return ids
+
+
+def install(name):
+    if name == "StyblinskiTang":
+        def term(x, xp, j, d):
+            x2 = x * x
+            return x2 * x2 - 16.0 * x2 + 5.0 * x
+        B.set_custom_objective(term, lambda s, d: 0.5 * s)
+    else:
+        def term(x, xp, j, d):
+            t = x - xp
+            return t * t
+        B.set_custom_objective(term, lambda s, d: float(np.sqrt(s)) + float(d), pairwise=True, lane0_seed=3.0)
+
+
+@pytest.mark.parametrize("name,strategy,P,d,G", [("StyblinskiTang", nb.DE_RANDOM, 96, 11, 6),
+                                                 ("Chain", nb.DE_BEST, 64, 70, 5), ("StyblinskiTang", nb.DE_BEST, 40, 2, 8)])
+def test_de_with_plugin_objective_matches_oracle(ctx, plugin_ids, name, strategy, P, d, G):
+    install(name)
+    x0 = np.full(d, 8.0)
+    pop = nb.DEPopulation(ctx, nb.de_cfg(objective=plugin_ids[name], strategy=strategy, pop_size=P, dim=d, eps=0.0,
+                                         max_iter=1 << 40, best_val_no_change=1 << 40, seed=31,
+                                         flags=nb.FLAG_RECORD_MASKS), x0)
+    pop.step(G)
+    st = pop.sync()
+    so, ao = B.de_run(B.oracle(), B.de_cfg(objective=B.CUSTOM, strategy=strategy, pop_size=P, dim=d, eps=0.0, max_iter=G,
+                                           best_val_no_change=1 << 40, seed=31), x0, masks=True)
+    dec = pop.decisions(masks=True)
+    for k in ("donors", "dim_idx", "rejects", "masks", "accepted"):
+        assert np.array_equal(dec[k], ao[k]), k
+    if name == "StyblinskiTang":      # + - * only, compiled without FMA contraction: bit-exact
+        assert np.array_equal(bits(pop.population()), bits(ao["rows"])) and st["f_value"] == so["f_value"]
+    else:                             # sqrt in finish()
+        assert rel_close(pop.population(), ao["rows"], 1e-12) and rel_close(st["f_value"], so["f_value"], 1e-12)
+    assert st["best_index"] == so["best_index"]
+    pop.close()
+
+
+def test_pso_with_plugin_objective_matches_oracle(ctx, plugin_ids):
+    install("StyblinskiTang")
+    P, d, G = 50, 9, 8
+    up = np.full(d, 5.0)
+    kw = dict(pso_type=nb.PSO_ACCELERATED, n_particles=P, dim=d, eps=0.0, max_iter=1 << 40, best_val_no_change=1 << 40, seed=8)
+    sw = nb.PSOSwarm(ctx, nb.pso_cfg(objective=plugin_ids["StyblinskiTang"], **kw), -up, up)
+    sw.step(G)
+    st = sw.sync()
+    so, ao = B.pso_run(B.oracle(), B.pso_cfg(objective=B.CUSTOM, **dict(kw, max_iter=G)), -up, up)
+    assert st["best_index"] == so["best_index"] and rel_close(st["f_value"], so["f_value"], 1e-12)
+    assert rel_close(sw.positions(), ao["positions"], 1e-12)
+    sw.close()
+
+
+def test_plugin_objective_through_the_solver_mirror(plugin_ids):
+    """DE(...).minimize with a plugin id as the Callable: converges to the known minimum x_j = -2.903534."""
+    class Gen:
+        def __init__(self):
+            self.v = iter([0.3, 0.7])
+
+        def __call__(self):
+            return next(self.v)
+    x = [4.0] * 6
+    st = nb.DE(plugin_ids["StyblinskiTang"], Gen(), pop_size=400, max_iter=400, best_val_no_change=400, eps=0.0,
+               differential_weight=0.5).minimize(x)
+    assert st.iteration == 400 and np.allclose(x, -2.903534, atol=1e-3), x
+    assert abs(st.f_value - 6 * -39.16616570377142) < 1e-3
+
+
+def test_unknown_objective_ids_are_rejected(ctx):
+    with pytest.raises(nb.NlsError):
+        nb.DEPopulation(ctx, nb.de_cfg(objective=9999, pop_size=10, dim=2), np.ones(2))
