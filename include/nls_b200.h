@@ -134,6 +134,8 @@ NLS_API int nls_de_sync(nls_de *de, nls_status *status);
 NLS_API int nls_de_read_best(nls_de *de, void *x_host);             /* agents[best_id], dim elements */
 NLS_API int nls_de_read_population(nls_de *de, void *rows_host);    /* agents, pop_size * dim elements, agent-major */
 NLS_API int nls_de_read_scores(nls_de *de, void *scores_host);      /* scores, pop_size elements */
+/* agents[first .. first+count), count * dim elements (spot checks on populations too large to copy whole) */
+NLS_API int nls_de_read_rows(nls_de *de, uint64_t first, uint64_t count, void *rows_host);
 /* decisions of the last executed generation; any pointer may be NULL.
  * donors: pop_size*3 (ids[1..3] of generate_indices, nlsolver.h:2331-2355); dim_idx / rejects / accepted: pop_size;
  * trial_scores: pop_size elements of dtype; masks: pop_size*dim bytes (needs NLS_FLAG_RECORD_MASKS) */

@@ -70,6 +70,7 @@ SYMBOLS = {
     "nls_de_read_best": (C.c_int, [P, P]),
     "nls_de_read_population": (C.c_int, [P, P]),
     "nls_de_read_scores": (C.c_int, [P, P]),
+    "nls_de_read_rows": (C.c_int, [P, u64, u64, P]),
     "nls_de_read_decisions": (C.c_int, [P, P, P, P, P, P, P]),
     "nls_de_destroy": (C.c_int, [P]),
     "nls_de_enable_kernel_timing": (C.c_int, [P, C.c_int]),

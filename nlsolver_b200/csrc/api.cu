@@ -492,6 +492,14 @@ int nls_de_read_population(nls_de *de, void *rows_host) {
   return de_read_rows(de, 0, de->s.P, rows_host);
 }
 
+int nls_de_read_rows(nls_de *de, uint64_t first, uint64_t count, void *rows_host) {
+  if (!de || !rows_host) return fail(NLS_ERR_INVALID, "nls_de_read_rows: NULL argument");
+  if (first + count > de->s.P) return fail(NLS_ERR_INVALID, "nls_de_read_rows: range exceeds the population");
+  NLS_CUDA(cudaSetDevice(de->ctx->device));
+  NLS_CUDA(cudaStreamSynchronize(de->ctx->stream));
+  return de_read_rows(de, first, count, rows_host);
+}
+
 int nls_de_read_scores(nls_de *de, void *scores_host) {
   if (!de || !scores_host) return fail(NLS_ERR_INVALID, "nls_de_read_scores: NULL argument");
   NLS_CUDA(cudaSetDevice(de->ctx->device));

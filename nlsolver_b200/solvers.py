@@ -7,6 +7,7 @@ Names, argument order, defaults and behaviour follow nlsolver::DE (nlsolver.h:23
 [0, 1] — two draws are taken from it per solve to seed the device draw tape, so it advances deterministically.
 """
 import ctypes as C
+import weakref
 
 import numpy as np
 
@@ -76,7 +77,11 @@ class Context:
 
     def __init__(self, device=0, stream=None):
         self._h = C.c_void_p()
+        self._children = weakref.WeakSet()   # live solver handles: they must be destroyed before the context
         L.check(L.lib().nls_ctx_create(device, C.c_void_p(stream) if stream else None, C.byref(self._h)))
+
+    def _adopt(self, child):
+        self._children.add(child)
 
     @property
     def handle(self):
@@ -92,6 +97,8 @@ class Context:
 
     def close(self):
         if self._h:
+            for child in list(self._children):
+                child.close()
             L.lib().nls_ctx_destroy(self._h)
             self._h = C.c_void_p()
 
@@ -121,6 +128,7 @@ class DEPopulation:
         assert x0.size == cfg.dim
         self._h = C.c_void_p()
         L.check(L.lib().nls_de_create(ctx.handle, C.byref(cfg), x0.ctypes.data, C.byref(self._h)))
+        ctx._adopt(self)
 
     def step(self, n=1):
         L.check(L.lib().nls_de_step(self._h, n))
@@ -139,6 +147,11 @@ class DEPopulation:
         rows = np.zeros((self.cfg.pop_size, self.cfg.dim), self.dt)
         L.check(L.lib().nls_de_read_population(self._h, rows.ctypes.data))
         return rows
+
+    def rows(self, first, count):
+        out = np.zeros((count, self.cfg.dim), self.dt)
+        L.check(L.lib().nls_de_read_rows(self._h, first, count, out.ctypes.data))
+        return out
 
     def scores(self):
         s = np.zeros(self.cfg.pop_size, self.dt)
@@ -200,6 +213,7 @@ class PSOSwarm:
         self._h = C.c_void_p()
         L.check(L.lib().nls_pso_create(ctx.handle, C.byref(cfg), lower.ctypes.data, upper.ctypes.data,
                                        C.byref(self._h)))
+        ctx._adopt(self)
 
     def step(self, n=1):
         L.check(L.lib().nls_pso_step(self._h, n))
@@ -262,6 +276,13 @@ class ExchangeWindow:
     def __init__(self, ctx, record_bytes, world, rank):
         self._h = C.c_void_p()
         L.check(L.lib().nls_xchg_create(ctx.handle, record_bytes, world, rank, C.byref(self._h)))
+        ctx._adopt(self)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
     @property
     def handle(self):
