@@ -185,6 +185,7 @@ struct nls_de {
   void *staging;      // read-back staging
   size_t staging_bytes;
   size_t elem;
+  size_t topk_capacity;                 // bytes behind s.topk_scratch (migration top-k candidates)
   bool timing;                          // measurement hook (nls_de_enable_kernel_timing)
   std::vector<cudaEvent_t> events;      // 4 per timed generation
   double timed_ms[3];
@@ -301,6 +302,7 @@ static int de_build(nls_ctx *ctx, const nls_de_cfg *cfg, const void *x0_host, nl
   de->mem.ctx = ctx;
   de->cfg = *cfg;
   de->timing = false;
+  de->topk_capacity = 0;
   de->timed_ms[0] = de->timed_ms[1] = de->timed_ms[2] = 0.0;
   de->timed_generations = 0;
   de->elem = elem_size(cfg->dtype);
@@ -540,10 +542,22 @@ int nls_de_export_best(nls_de *de, void *record_dev) {
   NLS_CUDA(de->ops->export_best(de->s, record_dev, de->ctx->stream));
   return NLS_OK;
 }
+static int de_ensure_topk_scratch(nls_de *de, uint64_t k) {
+  const size_t need = ((de->s.P + 4095) / 4096) * k * 16;
+  if (need <= de->topk_capacity) return NLS_OK;
+  void *p = nullptr;
+  int rc = de->mem.alloc(&p, need);
+  if (rc != NLS_OK) return rc;
+  de->s.topk_scratch = p;
+  de->topk_capacity = need;
+  return NLS_OK;
+}
+
 int nls_de_export_top(nls_de *de, uint64_t k, void *rows_dev, void *scores_dev) {
   if (!de || !rows_dev || !scores_dev) return fail(NLS_ERR_INVALID, "nls_de_export_top: NULL argument");
   if (k < 1 || k > de->s.P) return fail(NLS_ERR_INVALID, "nls_de_export_top: k out of range");
   NLS_CUDA(cudaSetDevice(de->ctx->device));
+  if (int rc = de_ensure_topk_scratch(de, k)) return rc;
   NLS_CUDA(de->ops->migrate(de->s, +1, k, rows_dev, scores_dev, de->g, de->ctx->stream));
   return NLS_OK;
 }
@@ -551,6 +565,7 @@ int nls_de_import_migrants(nls_de *de, uint64_t k, const void *rows_dev, const v
   if (!de || !rows_dev || !scores_dev) return fail(NLS_ERR_INVALID, "nls_de_import_migrants: NULL argument");
   if (k < 1 || k > de->s.P) return fail(NLS_ERR_INVALID, "nls_de_import_migrants: k out of range");
   NLS_CUDA(cudaSetDevice(de->ctx->device));
+  if (int rc = de_ensure_topk_scratch(de, k)) return rc;
   NLS_CUDA(de->ops->migrate(de->s, -1, k, const_cast<void *>(rows_dev), const_cast<void *>(scores_dev), de->g,
                             de->ctx->stream));
   return NLS_OK;

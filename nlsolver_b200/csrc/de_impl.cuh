@@ -489,31 +489,84 @@ __global__ void __launch_bounds__(kBlock) de_export_best_kernel(DEState s, void 
   for (u64 j = threadIdx.x; j < s.d; j += kBlock) row[j] = __ldcg(src + j);
 }
 
-// One selection round: the next agent after the cursor (sel_value, sel_index) in the order
+// Top-k selection for migration, deterministic and in two kernels.  Order:
 //   best-first  (sign = +1): ascending score, ascending index on ties
 //   worst-first (sign = -1): descending score, descending index on ties
-// The last block stores the pick in list[slot] and advances the cursor.  `first` starts a new selection.
+// Both are "ascending (key, visit)" with key = sign * score and visit = i or P - 1 - i.  Phase 1: every block extracts
+// the k smallest (key, visit) pairs of its contiguous slice by k rounds of a block-wide arg-min that only admits pairs
+// beyond the previous pick (no marking needed).  Phase 2: one block does the same over the blocks' candidates.
+struct TopKey { double key; unsigned long long visit; };
+__device__ __forceinline__ bool topkey_less(const TopKey &a, const TopKey &b) {
+  return a.key < b.key || (a.key == b.key && a.visit < b.visit);
+}
+__device__ __forceinline__ TopKey topkey_block_min(TopKey mine, TopKey *sm) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    TopKey o; o.key = __shfl_down_sync(kFull, mine.key, off); o.visit = __shfl_down_sync(kFull, mine.visit, off);
+    if (topkey_less(o, mine)) mine = o;
+  }
+  if (lane == 0) sm[w] = mine;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int k = 1; k < kWarpsPerBlock; k++) if (topkey_less(sm[k], mine)) mine = sm[k];
+    sm[0] = mine;
+  }
+  __syncthreads();
+  mine = sm[0];
+  __syncthreads();
+  return mine;
+}
+constexpr unsigned long long kNoVisit = ~0ull;
+
 template <class T>
-__global__ void __launch_bounds__(kBlock) de_select_kernel(DEState s, int sign, u32 slot, int first) {
-  DECtrl *ctrl = s.ctrl;
+__global__ void __launch_bounds__(kBlock) de_topk_partial_kernel(DEState s, int sign, u32 k, u64 slice, TopKey *cand) {
+  __shared__ TopKey sm[kWarpsPerBlock];
   const T *score = static_cast<const T *>(s.score);
-  const double cv = ctrl->sel_value;
-  const u64 ci = ctrl->sel_index;
-  const u64 P = s.P;
-  auto item = [&](u64 i, double &for_min, double &for_moments) {
-    // keys: (sign * score, sign > 0 ? i : P - 1 - i); population_reduce walks i upward, so for the worst-first
-    // order the element visited is P - 1 - i, which keeps "lower visit index wins ties" == "higher agent index wins"
-    const u64 a = sign > 0 ? i : P - 1 - i;
-    const double v = sign * static_cast<double>(score[a]);
-    const bool beyond = first || v > cv || (v == cv && i > ci);
-    for_min = beyond ? v : CUDART_INF;
-    for_moments = 0.0;
-  };
-  MinLoc ml;
-  Moments mo;
-  if (population_reduce(P, s.part_min, s.part_idx, s.part_mom, &ctrl->ticket, item, [] {}, ml, mo) && threadIdx.x == 0) {
-    ctrl->sel_value = ml.v; ctrl->sel_index = ml.i;
-    s.list[slot] = ml.i == ~0ull ? 0xffffffffu : u32(sign > 0 ? ml.i : P - 1 - ml.i);
+  const u64 P = s.P, lo = u64(blockIdx.x) * slice, hi = (lo + slice < P) ? lo + slice : P;
+  TopKey cursor; cursor.key = -CUDART_INF; cursor.visit = kNoVisit;   // kNoVisit + 1 wraps to 0: "before everything"
+  bool started = false;
+  for (u32 e = 0; e < k; e++) {
+    TopKey best; best.key = CUDART_INF; best.visit = kNoVisit;
+    for (u64 v = lo + threadIdx.x; v < hi; v += kBlock) {
+      const u64 a = sign > 0 ? v : P - 1 - v;
+      TopKey c; c.key = sign * static_cast<double>(score[a]); c.visit = v;
+      const bool beyond = !started || topkey_less(cursor, c);
+      if (beyond && topkey_less(c, best)) best = c;
+    }
+    best = topkey_block_min(best, sm);
+    if (threadIdx.x == 0) cand[u64(blockIdx.x) * k + e] = best;
+    if (best.visit == kNoVisit) {                       // slice exhausted: pad the remaining slots
+      for (u32 r = e + 1 + threadIdx.x; r < k; r += kBlock) cand[u64(blockIdx.x) * k + r] = best;
+      break;
+    }
+    cursor = best;
+    started = true;
+  }
+}
+
+template <class T>
+__global__ void __launch_bounds__(kBlock) de_topk_final_kernel(DEState s, int sign, u32 k, u64 n_cand, const TopKey *cand) {
+  __shared__ TopKey sm[kWarpsPerBlock];
+  TopKey cursor; cursor.key = -CUDART_INF; cursor.visit = kNoVisit;
+  bool started = false;
+  for (u32 e = 0; e < k; e++) {
+    TopKey best; best.key = CUDART_INF; best.visit = kNoVisit;
+    for (u64 q = threadIdx.x; q < n_cand; q += kBlock) {
+      TopKey c; c.key = cand[q].key; c.visit = cand[q].visit;
+      if (c.visit == kNoVisit) continue;
+      const bool beyond = !started || topkey_less(cursor, c);
+      if (beyond && topkey_less(c, best)) best = c;
+    }
+    best = topkey_block_min(best, sm);
+    if (threadIdx.x == 0)
+      s.list[e] = best.visit == kNoVisit ? 0xffffffffu : u32(sign > 0 ? best.visit : s.P - 1 - best.visit);
+    if (best.visit == kNoVisit) {
+      for (u32 r = e + 1 + threadIdx.x; r < k; r += kBlock) s.list[r] = 0xffffffffu;
+      break;
+    }
+    cursor = best;
+    started = true;
   }
 }
 
@@ -594,7 +647,12 @@ cudaError_t de_launch_export_best(const DEState &s, void *record, cudaStream_t s
 template <class T>
 cudaError_t de_launch_migrate(const DEState &s, int sign, unsigned long long k, void *rows, void *scores,
                               const LaunchGeom &g, cudaStream_t st) {
-  for (u32 e = 0; e < k; e++) de_select_kernel<T><<<g.reduce_blocks, kBlock, 0, st>>>(s, sign, e, e == 0);
+  const u64 slice = 4096;
+  const u64 blocks = (s.P + slice - 1) / slice;
+  if (!s.topk_scratch) return cudaErrorInvalidValue;   // sized by the host side: ceil(P / 4096) * k pairs
+  TopKey *cand = reinterpret_cast<TopKey *>(s.topk_scratch);
+  de_topk_partial_kernel<T><<<static_cast<unsigned int>(blocks), kBlock, 0, st>>>(s, sign, u32(k), slice, cand);
+  de_topk_final_kernel<T><<<1, kBlock, 0, st>>>(s, sign, u32(k), blocks * k, cand);
   const unsigned int grid = clamp_grid(k, 4096);
   if (sign > 0) de_gather_kernel<T><<<grid, kBlock, 0, st>>>(s, u32(k), static_cast<T *>(rows), static_cast<T *>(scores));
   else {

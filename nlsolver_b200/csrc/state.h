@@ -24,7 +24,6 @@ struct DECtrl {
   unsigned int pending[3];      // repair: pending-list length produced in round r, slot r % 3 (K2 fills slot 1)
   unsigned int list_count[3];   // repair: agents to re-evaluate in round r, slot r % 3
   Moments score_moments;        // moments of the scores at the last scan (island exchange record)
-  double sel_value; unsigned long long sel_index;   // cursor of the top-k / worst-k selection (island migration)
 };
 
 struct DEState {
@@ -39,6 +38,7 @@ struct DEState {
   uint8_t *masks;        // [P*d] crossover mask of the last generation, or NULL
   uint32_t *list;        // [P] repair: agents to re-evaluate in the current round
   uint32_t *pend[2];     // [P] each: ping-pong lists of agents whose outcome is not final yet
+  void *topk_scratch;    // migration top-k candidates: ceil(P / 4096) * k (key, visit) pairs
   DECtrl *ctrl;
   // reduction partials [n_partials]
   double *part_min; unsigned long long *part_idx; Moments *part_mom;

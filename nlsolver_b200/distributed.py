@@ -165,11 +165,11 @@ class CudaDEEngine:
 
     def export_top(self, k, rows, scores):
         self.pop.export_top(k, rows.data_ptr(), scores.data_ptr())
-        self.kernel_launches += k + 1
+        self.kernel_launches += 3
 
     def import_migrants(self, k, rows, scores):
         self.pop.import_migrants(k, rows.data_ptr(), scores.data_ptr())
-        self.kernel_launches += k + 2
+        self.kernel_launches += 4
 
     def sync(self):
         return self.pop.sync()
