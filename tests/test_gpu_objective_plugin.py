@@ -8,7 +8,9 @@ from nlsolver_b200 import plugins
 from oracle import binding as B
 from tests.gpu_util import bits, rel_close
 
-pytestmark = pytest.mark.gpu
+import shutil
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(shutil.which("nvcc") is None, reason="objective plugins are built with nvcc")]
 
 STYBLINSKI = """
 template <class T> struct StyblinskiTang {          // f(x) = 0.5 * sum(x^4 - 16 x^2 + 5 x)  (test_functions.h StyblinskiTang, N-D)
