@@ -1,0 +1,72 @@
+"""The drop-in C++ header on the GPU: examples/example_de_pso.cpp (the reference's example.cpp DE / PSO call sites) is
+built with g++, run, and its solver_status::print() output compared with the same solves through the Python mirror
+(same generator, hence the same two seed draws) — both go through nls_de_solve / nls_pso_solve."""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+import nlsolver_b200 as nb
+from tests.test_gpu_convergence import XorShift
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def parse(out):
+    """-> list of (title, calls, iterations, f_value string, x strings) per printed solver block."""
+    blocks = []
+    for m in re.finditer(r"([^\n]*): ?\nFunction calls used: (\d+)\nAlgorithm iterations used: (\d+)\n"
+                         r"With final function value of ([^\n]+)\n([^\n]*)\n", out):
+        blocks.append((m.group(1).strip(), int(m.group(2)), int(m.group(3)), m.group(4), m.group(5)))
+    return blocks
+
+
+def test_example_program_matches_python_mirror(tmp_path):
+    exe = tmp_path / "example_de_pso"
+    subprocess.run(["g++", "-std=c++17", "-O2", "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "examples", "example_de_pso.cpp"), "-L", os.path.join(ROOT, "nlsolver_b200"),
+                    "-lnls_b200", "-Wl,-rpath," + os.path.join(ROOT, "nlsolver_b200"), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout
+    blocks = parse(out)
+    assert len(blocks) >= 5, out
+    gen = XorShift()                      # example: DE-best with a fresh xorshift, x0 = {2, 7}
+    x = [2.0, 7.0]
+    st = nb.DE(nb.RosenbrockExample, gen, recombination=nb.RecombinationStrategy.best).minimize(x)
+    title, calls, iters, fval, xs = blocks[0]
+    assert (calls, iters) == (st.function_calls_used, st.iteration)
+    assert fval == "%g" % st.f_value and xs == "".join("%g," % v for v in x)
+    gen = XorShift()                      # README snippet: DE-random after gen.reset(), x0 = {5, 7}
+    x = [5.0, 7.0]
+    st = nb.DE(nb.RosenbrockExample, gen).minimize(x)
+    title, calls, iters, fval, xs = blocks[1]
+    assert (calls, iters) == (st.function_calls_used, st.iteration) and fval == "%g" % st.f_value
+    gen = XorShift()                      # PSO vanilla (10 particles > 2 dims -> corrected social index), x0 = {3, 3}
+    x = [3.0, 3.0]
+    st = nb.PSO(nb.RosenbrockExample, gen).minimize(x)
+    title, calls, iters, fval, xs = blocks[2]
+    assert (calls, iters) == (st.function_calls_used, st.iteration) and fval == "%g" % st.f_value
+    # the big Rastrigin run at the end re-evaluates its result on the host with the header's own functor
+    m = re.search(r"With final function value of ([^\n]+)\nhost re-evaluation of the returned point: ([^\n]+)", out)
+    assert m and abs(float(m.group(1)) - float(m.group(2))) <= 1e-5 * abs(float(m.group(2)))
+
+
+def test_plugin_example_program(tmp_path):
+    import shutil
+    if shutil.which("nvcc") is None:
+        pytest.skip("objective plugins are built with nvcc")
+    so = tmp_path / "libstyblinski_tang.so"
+    subprocess.run(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-shared", "-Xcompiler",
+                    "-fPIC", "-I", os.path.join(ROOT, "nlsolver_b200", "csrc"), "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "examples", "objectives", "styblinski_tang.cu"), "-o", str(so)], check=True,
+                   capture_output=True)
+    exe = tmp_path / "example_plugin_objective"
+    subprocess.run(["g++", "-std=c++17", "-O2", "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "examples", "example_plugin_objective.cpp"), "-L",
+                    os.path.join(ROOT, "nlsolver_b200"), "-lnls_b200", "-Wl,-rpath," + os.path.join(ROOT, "nlsolver_b200"),
+                    "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe), str(so)], check=True, capture_output=True, text=True).stdout
+    xs = [float(v) for v in out.strip().splitlines()[-1].rstrip(",").split(",")]
+    assert len(xs) == 8 and np.allclose(xs, -2.903534, atol=2e-2), out
