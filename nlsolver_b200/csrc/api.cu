@@ -48,6 +48,7 @@ size_t elem_size(int dtype) { return dtype == NLS_F64 ? 8 : 4; }
 // objective plugins (objective_plugin.cuh): same ops tables as the built-in dtypes, instantiated for a user functor
 struct ObjectivePlugin {
   int abi;
+  unsigned full_dim;
   const DEOps *de_f64, *de_f32;
   const PSOOps *pso_f64, *pso_f32;
 };
@@ -278,6 +279,10 @@ uint64_t nls_record_bytes(int32_t dtype, uint64_t dim) {
 static int de_validate(const nls_de_cfg *c) {
   if (c->dtype != NLS_F32 && c->dtype != NLS_F64) return fail(NLS_ERR_INVALID, "DE: unknown dtype %d", c->dtype);
   if (!objective_known(c->objective)) return fail(NLS_ERR_INVALID, "DE: unknown objective %d", c->objective);
+  if (const ObjectivePlugin *pl = plugin_for(c->objective))
+    if (pl->full_dim && pl->full_dim != c->dim)
+      return fail(NLS_ERR_INVALID, "DE: objective %d is a closed form of dimension %u, dim is %llu", c->objective,
+                  pl->full_dim, static_cast<unsigned long long>(c->dim));
   if (c->strategy != NLS_DE_BEST && c->strategy != NLS_DE_RANDOM) return fail(NLS_ERR_INVALID, "DE: unknown strategy %d", c->strategy);
   if (c->pop_size < 4) return fail(NLS_ERR_INVALID, "DE: pop_size must be >= 4 (three distinct donors besides the fixed agent)");
   if (c->dim < 1) return fail(NLS_ERR_INVALID, "DE: dim must be >= 1");
@@ -597,6 +602,10 @@ int nls_de_solve(nls_ctx *ctx, const nls_de_cfg *cfg, const void *x0_host, void 
 static int pso_validate(const nls_pso_cfg *c) {
   if (c->dtype != NLS_F32 && c->dtype != NLS_F64) return fail(NLS_ERR_INVALID, "PSO: unknown dtype %d", c->dtype);
   if (!objective_known(c->objective)) return fail(NLS_ERR_INVALID, "PSO: unknown objective %d", c->objective);
+  if (const ObjectivePlugin *pl = plugin_for(c->objective))
+    if (pl->full_dim && pl->full_dim != c->dim)
+      return fail(NLS_ERR_INVALID, "PSO: objective %d is a closed form of dimension %u, dim is %llu", c->objective,
+                  pl->full_dim, static_cast<unsigned long long>(c->dim));
   if (c->pso_type != NLS_PSO_VANILLA && c->pso_type != NLS_PSO_ACCELERATED) return fail(NLS_ERR_INVALID, "PSO: unknown type %d", c->pso_type);
   if (c->n_particles < 1 || c->dim < 1) return fail(NLS_ERR_INVALID, "PSO: n_particles and dim must be >= 1");
   const u64 pg = c->n_particles_global ? c->n_particles_global : c->n_particles;
@@ -847,7 +856,7 @@ int nls_load_objective(const char *plugin_path, int32_t *objective_id) {
   entry_t entry = reinterpret_cast<entry_t>(dlsym(h, "nls_objective_plugin_v1"));
   if (!entry) { dlclose(h); return fail(NLS_ERR_INVALID, "nls_load_objective: %s exports no nls_objective_plugin_v1", plugin_path); }
   const ObjectivePlugin *pl = entry();
-  if (!pl || pl->abi != 1 || !pl->de_f64 || !pl->de_f32 || !pl->pso_f64 || !pl->pso_f32) {
+  if (!pl || pl->abi != 2 || !pl->de_f64 || !pl->de_f32 || !pl->pso_f64 || !pl->pso_f32) {
     dlclose(h);
     return fail(NLS_ERR_INVALID, "nls_load_objective: plugin ABI mismatch (rebuild it against this library's headers)");
   }

@@ -15,6 +15,13 @@
 //
 //     nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -shared -Xcompiler -fPIC -I... my_objective.cu -o libmy_objective.so
 //
+// Closed forms over a short vector (e.g. the reference's 2-D test problems, test_functions.h:94-318) use the other form:
+//
+//     template <class T> struct Beale {                     // test_functions.h:94-105
+//       static constexpr unsigned full_dim = 2;             // 1..8; the solver must then be run with dim == full_dim
+//       static __device__ T full(const T (&x)[2]) { ... return f; }
+//     };
+//
 // The kernels (donor selection, crossover, repair, reductions, PSO moves) are the engine's own templates instantiated
 // for the functor; the sum runs in the canonical lane order (objectives.cuh), so results are reproducible.
 #pragma once
@@ -22,9 +29,10 @@
 #include "de_impl.cuh"
 #include "pso_impl.cuh"
 
-#define NLS_PLUGIN_ABI 1
+#define NLS_PLUGIN_ABI 2
 struct nls_objective_plugin {
   int abi;
+  unsigned full_dim;   // 0: separable / pairwise sum of any dimension; D > 0: closed form, the solver's dim must be D
   const nls::DEOps *de_f64, *de_f32;
   const nls::PSOOps *pso_f64, *pso_f32;
 };
@@ -38,7 +46,8 @@ struct nls_objective_plugin {
   NLS_DEFINE_PSO_OPS(float, plugin_pso_f32)                                                              \
   }                                                                                                      \
   extern "C" __attribute__((visibility("default"))) const nls_objective_plugin *nls_objective_plugin_v1() { \
-    static const nls_objective_plugin p = {NLS_PLUGIN_ABI, nls::plugin_de_f64(), nls::plugin_de_f32(),   \
+    static const nls_objective_plugin p = {NLS_PLUGIN_ABI, nls::plugin_full_dim<NAME<double>>::value,    \
+                                           nls::plugin_de_f64(), nls::plugin_de_f32(),                   \
                                            nls::plugin_pso_f64(), nls::plugin_pso_f32()};                \
     return &p;                                                                                           \
   }

@@ -6,6 +6,8 @@
 // CPU oracle mirrors (oracle/popsolve_oracle.cpp `Lanes`), and each form is arranged so that at d = 2 it performs the
 // reference's own operations in the reference's order.
 #pragma once
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace nls {
@@ -19,15 +21,26 @@ enum { OBJ_SPHERE = 0, OBJ_ROSENBROCK = 1, OBJ_RASTRIGIN = 2, OBJ_ACKLEY = 3, OB
 //   static __device__ T term(T x, T x_prev, unsigned j, unsigned d);
 //   static __device__ T finish(T sum, unsigned d);
 // f(x) = finish(lane0_seed + sum_j term(x[j], x[j-1], j, d), d), summed in the canonical lane order.
+// Alternatively, for small fixed dimension (closed forms like the reference's 2-D test problems):
+//   static constexpr unsigned full_dim = D;              1 <= D <= 8, the solver must be run with dim == D
+//   static __device__ T full(const T (&x)[D]);           f(x) from the whole vector
 template <class T> struct CustomObjective;
+constexpr unsigned kMaxFullDim = 8;
+template <class C, class = void> struct plugin_full_dim : std::integral_constant<unsigned, 0> {};
+template <class C> struct plugin_full_dim<C, std::void_t<decltype(C::full_dim)>> : std::integral_constant<unsigned, C::full_dim> {};
 
 // W = lanes that cooperate on one agent (32, or a smaller power of two when d <= W * V so that one step covers the
 // row); `lane` arguments are lane indices INSIDE the group.
 template <class T, int OBJ, int W = 32>
 struct Objective {
   static constexpr int V = Vec<T>::V;
+  static constexpr unsigned custom_full_dim() {
+    if constexpr (OBJ == OBJ_CUSTOM) return plugin_full_dim<CustomObjective<T>>::value;
+    else return 0;
+  }
+  static constexpr unsigned kFullDim = custom_full_dim();  // > 0: closed form over the whole (short) vector
   static constexpr bool custom_pairwise() {
-    if constexpr (OBJ == OBJ_CUSTOM) return CustomObjective<T>::pairwise;
+    if constexpr (OBJ == OBJ_CUSTOM && kFullDim == 0) return CustomObjective<T>::pairwise;
     else return false;
   }
   static constexpr bool kPairwise = (OBJ == OBJ_ROSENBROCK || OBJ == OBJ_ROSENBROCK_EX) || custom_pairwise();
@@ -37,7 +50,7 @@ struct Objective {
   __device__ __forceinline__ void begin(int lane, u32 d) {
     // Rastrigin's leading `2*10` (10*d in N-D) seeds lane 0's accumulator so that d = 2 gives (20 + t0) + t1
     a = (OBJ == OBJ_RASTRIGIN && lane == 0) ? A::mul(T(10), T(d)) : T(0);
-    if constexpr (OBJ == OBJ_CUSTOM) a = lane == 0 ? CustomObjective<T>::lane0_seed(d) : T(0);
+    if constexpr (OBJ == OBJ_CUSTOM && kFullDim == 0) a = lane == 0 ? CustomObjective<T>::lane0_seed(d) : T(0);
     b = T(0);
     carry = T(0);
   }
@@ -45,6 +58,15 @@ struct Objective {
   // x[q] is coordinate j0 + q of the agent; coordinates >= d are padding and contribute nothing.
   // Must be called by all 32 lanes (the pairwise forms shuffle).
   __device__ __forceinline__ void step(const T (&x)[V], u32 j0, u32 d, int lane) {
+    if constexpr (kFullDim > 0) {
+      // gather the whole vector into every lane of the group (coordinate k sits in lane k / V, slot k % V); the
+      // group's first lane evaluates the closed form, the others contribute 0 to the butterfly
+      static_assert(kFullDim <= kMaxFullDim && kFullDim <= W * V, "full_dim must fit one step of the smallest lane group");
+      T xs[kFullDim];
+#pragma unroll
+      for (unsigned k = 0; k < kFullDim; k++) xs[k] = __shfl_sync(kFull, x[k % V], k / V, W);
+      if (lane == 0 && j0 == 0 && d == kFullDim) a = CustomObjective<T>::full(xs);
+    } else {
     T left = T(0);
     if (kPairwise) {
       left = __shfl_up_sync(kFull, x[V - 1], 1, W);       // x[j0 - 1] lives in the previous lane ...
@@ -80,12 +102,14 @@ struct Objective {
         }
       }
     }
+    }   // separable / pairwise forms
   }
 
   // every lane returns the objective value
   __device__ __forceinline__ T finish(u32 d) {
     a = warp_butterfly_add<T, W>(a);
-    if constexpr (OBJ == OBJ_CUSTOM) return CustomObjective<T>::finish(a, d);
+    if constexpr (OBJ == OBJ_CUSTOM && kFullDim > 0) return a;
+    else if constexpr (OBJ == OBJ_CUSTOM) return CustomObjective<T>::finish(a, d);
     if (OBJ == OBJ_ACKLEY) {
       b = warp_butterfly_add<T, W>(b);
       const T inv_d = T(1.0) / T(d);

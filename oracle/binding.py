@@ -190,6 +190,18 @@ def set_custom_objective(term, finish, pairwise=False, lane0_seed=0.0):
     lib.oracle_set_custom_objective(int(pairwise), lane0_seed, t, f)
 
 
+FULL_FN = C.CFUNCTYPE(f64, C.POINTER(f64), u64)
+
+
+def set_custom_full(fn):
+    """Install a Python callable f(list of coordinates) -> value as objective CUSTOM (closed forms, small d)."""
+    lib = oracle()
+    cb = FULL_FN(lambda p, d: float(fn([p[k] for k in range(d)])))
+    _custom_keepalive[:] = [cb]
+    lib.oracle_set_custom_full.argtypes = [FULL_FN]
+    lib.oracle_set_custom_full(cb)
+
+
 def objective(dtype, obj_id, x):
     x = np.ascontiguousarray(x, dtype=np_dtype(dtype))
     return oracle().oracle_objective(dtype, obj_id, x.ctypes.data, x.size)

@@ -109,13 +109,21 @@ struct Lanes {
  * lane order, the contract of nlsolver_b200/csrc/objective_plugin.cuh */
 typedef double (*orc_term_fn)(double x, double x_prev, uint64_t j, uint64_t d);
 typedef double (*orc_finish_fn)(double sum, uint64_t d);
-struct CustomObjective { int pairwise = 0; double seed = 0; orc_term_fn term = nullptr; orc_finish_fn finish = nullptr; } g_custom;
+typedef double (*orc_full_fn)(const double *x, uint64_t d);
+struct CustomObjective {
+  int pairwise = 0; double seed = 0; orc_term_fn term = nullptr; orc_finish_fn finish = nullptr;
+  orc_full_fn full = nullptr;   /* closed form over the whole vector (plugin full_dim mode); takes precedence */
+} g_custom;
 
 template <class T>
 T objective(int id, const T *x, size_t d) {
   const T two_pi = static_cast<T>(2 * M_PI);
   switch (id) {
     case ORC_CUSTOM: {
+      if (g_custom.full) {
+        std::vector<double> xd(x, x + d);
+        return static_cast<T>(g_custom.full(xd.data(), d));
+      }
       if (!g_custom.term || !g_custom.finish) return std::nan("");
       Lanes<T> s(static_cast<T>(g_custom.seed));
       for (size_t j = g_custom.pairwise ? 1 : 0; j < d; j++)
@@ -523,7 +531,9 @@ void oracle_pso_close(void *p) { delete static_cast<PSOHandle *>(p); }
 
 void oracle_set_custom_objective(int pairwise, double lane0_seed, orc_term_fn term, orc_finish_fn finish) {
   g_custom.pairwise = pairwise; g_custom.seed = lane0_seed; g_custom.term = term; g_custom.finish = finish;
+  g_custom.full = nullptr;
 }
+void oracle_set_custom_full(orc_full_fn full) { g_custom.full = full; }
 
 double oracle_objective(int dtype, int id, const void *x, uint64_t d) {
   return dtype == ORC_F64 ? objective<double>(id, static_cast<const double *>(x), d)
