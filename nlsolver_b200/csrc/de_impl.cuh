@@ -448,7 +448,7 @@ __global__ void __launch_bounds__(kBlock) de_commit_kernel(DEState s, int mode) 
     if (ctrl->iter >= s.max_iter) reason = 1;
     else if (ctrl->vnc >= s.vnc_limit) reason = 2;
     else {
-      const T se = static_cast<T>(sqrt(mo.m2 / (mo.n - 1.0)));
+      const T se = stop_std_err<T>(mo, score, s.P, s.eps);
       ctrl->std_err = static_cast<double>(se);
       if (se < static_cast<T>(s.eps)) reason = 3;
     }

@@ -90,6 +90,30 @@ __device__ __forceinline__ bool population_reduce(u64 n, double *part_min, unsig
   return true;
 }
 
+// std_err exactly as the reference computes it (nlsolver.h:2037-2052): sequential sums in index order, the square
+// evaluated in double.  One thread, O(n) dependent additions — only used when the pairwise value lands within 1e-9
+// (relative) of eps, where the last bits decide whether the stop rule fires; everywhere else the two agree on the
+// comparison and the pairwise value is used.
+template <class T>
+__device__ T sequential_std_err(const T *x, u64 n) {
+  T mean_val = T(0), result = T(0);
+  for (u64 i = 0; i < n; i++) mean_val = Ar<T>::add(mean_val, __ldcg(x + i));
+  mean_val = mean_val / static_cast<T>(n);
+  for (u64 i = 0; i < n; i++) {
+    const double dlt = static_cast<double>(Ar<T>::sub(__ldcg(x + i), mean_val));
+    result = static_cast<T>(__dadd_rn(static_cast<double>(result), __dmul_rn(dlt, dlt)));
+  }
+  result = result / static_cast<T>(n - 1);
+  return static_cast<T>(sqrt(static_cast<double>(result)));
+}
+template <class T>
+__device__ __forceinline__ T stop_std_err(const Moments &mo, const T *values, u64 n, double eps) {
+  T se = static_cast<T>(sqrt(mo.m2 / (mo.n - 1.0)));
+  const double e = static_cast<double>(static_cast<T>(eps));
+  if (values != nullptr && e > 0.0 && fabs(static_cast<double>(se) - e) <= 1e-9 * e) se = sequential_std_err<T>(values, n);
+  return se;
+}
+
 // Exchange record (island best / sharded-swarm candidate): 48-byte header followed by one row of dim elements.
 struct RecordHeader {
   double value;                 // candidate objective value (already multiplied by -1 when maximising)

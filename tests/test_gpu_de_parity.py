@@ -179,3 +179,26 @@ def test_de_large_population_properties(ctx):
         assert np.allclose((rows * rows).sum(1), cur, rtol=1e-12)
         prev = cur
     pop.close()
+
+
+def test_std_err_stop_rule_is_exact_at_the_threshold(ctx, oracle_lib):
+    """The stop statistic is a pairwise reduction on the device and sequential sums in the reference; when it lands
+    within 1e-9 of eps the device recomputes it sequentially, so the stop fires in the same generation even when eps
+    sits one ulp above / exactly at the reference's value."""
+    P, d, seed = 200, 6, 77
+    x0 = np.full(d, 2.0)
+    # std_err of the scores the reference sees at the top of iteration 7
+    so, ao = oracle_de(oracle_lib, B.F64, B.SPHERE, B.DE_RANDOM, True, P, d, 7, seed, x0, masks=False)
+    se = oracle_lib.oracle_std_err_f64(ao["scores"].ctypes.data, P)
+    for eps, stops_at in ((np.nextafter(se, np.inf), 7), (se, None)):
+        cfg = B.de_cfg(objective=B.SPHERE, pop_size=P, dim=d, eps=float(eps), max_iter=40, best_val_no_change=1 << 40, seed=seed)
+        want, _ = B.de_run(oracle_lib, cfg, x0)
+        if stops_at is not None:
+            assert want["iterations"] == stops_at and want["stop_reason"] == 3
+        pop = nb.DEPopulation(ctx, nb.de_cfg(objective=nb.SPHERE, pop_size=P, dim=d, eps=float(eps), max_iter=40,
+                                             best_val_no_change=1 << 40, seed=seed), x0)
+        pop.step(40)
+        st = pop.sync()
+        assert (st["iterations"], st["stop_reason"]) == (want["iterations"], want["stop_reason"]), (eps, st, want)
+        assert st["f_value"] == want["f_value"]
+        pop.close()

@@ -24,7 +24,9 @@ NEVER = 1 << 62
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--config", type=int, required=True, choices=[3, 4])
+    ap.add_argument("--config", type=int, required=True, choices=[3, 4, 5])
+    ap.add_argument("--solver", default="de", choices=["de", "pso-accelerated", "pso-vanilla"], help="config 5")
+    ap.add_argument("--dtype", default="f64", choices=["f32", "f64"], help="config 5")
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--per-gpu", type=int, default=1 << 21)
@@ -52,6 +54,26 @@ def main():
         job = D.ShardedPSO(cfg, -up, up, device=local, exchange=args.exchange)
         units, name = P, f"PSO-accelerated Ackley d={d}, {P} particles over {world} GPU(s), fp64, {args.exchange} exchange every generation"
         alg_bytes = 2 * d * 8 + 2 * 8
+    elif args.config == 5:
+        # population sweep point: d = 64, Sphere; PSO is one global swarm sharded over the ranks, DE one island per rank
+        d = 64
+        dtype = nb.F64 if args.dtype == "f64" else nb.F32
+        es = 8 if args.dtype == "f64" else 4
+        if args.solver == "de":
+            cfg = nb.de_cfg(dtype=dtype, objective=nb.SPHERE, pop_size=args.per_gpu, dim=d, eps=0.0, max_iter=NEVER,
+                            best_val_no_change=NEVER, seed=0x7c26ca28fb68bc1b)
+            job = D.IslandDE(cfg, np.full(d, 10.24), device=local, migrate_every=10, migrants=64)
+            alg_bytes = 4 * d * es
+        else:
+            ptype = nb.PSO_ACCELERATED if args.solver == "pso-accelerated" else nb.PSO_VANILLA
+            up = np.full(d, 10.24)
+            cfg = nb.pso_cfg(dtype=dtype, objective=nb.SPHERE, pso_type=ptype, n_particles=args.per_gpu * world, dim=d,
+                             eps=0.0, max_iter=NEVER, best_val_no_change=NEVER, seed=0x7c26ca28fb68bc1b,
+                             flags=nb.FLAG_SOCIAL_INDEX_J)
+            job = D.ShardedPSO(cfg, -up, up, device=local, exchange=args.exchange)
+            alg_bytes = (2 if ptype == nb.PSO_ACCELERATED else 4) * d * es
+        units = args.per_gpu * world
+        name = f"sweep point: {args.solver} Sphere d={d} {args.dtype}, {args.per_gpu} per GPU x {world} GPU(s)"
     else:
         d, P = 4096, args.per_gpu
         cfg = nb.de_cfg(objective=nb.ROSENBROCK, strategy=nb.DE_BEST, pop_size=P, dim=d, eps=0.0, max_iter=NEVER,
