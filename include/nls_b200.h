@@ -195,7 +195,8 @@ NLS_API int nls_load_objective(const char *plugin_path, int32_t *objective_id);
  *   1. nls_xchg_create on every rank (world <= 16, same record size = nls_record_bytes(dtype, dim))
  *   2. nls_xchg_get_handle -> exchange the NLS_XCHG_HANDLE_BYTES-byte handles between ranks (any transport)
  *   3. nls_xchg_open_peers with the rank-ordered handles
- *   4. nls_pso_attach_exchange (performs the pending initial exchange), then nls_pso_step_fused */
+ *   4. nls_pso_attach_exchange (performs the pending initial exchange), then nls_pso_step_fused
+ * A window serves exactly one swarm (its sequence flags only grow); all ranks must step the same number of times. */
 #define NLS_XCHG_HANDLE_BYTES 64
 typedef struct nls_xchg nls_xchg;
 NLS_API int nls_xchg_create(nls_ctx *ctx, uint64_t record_bytes, int world, int rank, nls_xchg **out);

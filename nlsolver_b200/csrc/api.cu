@@ -201,6 +201,7 @@ struct nls_xchg {
   size_t bytes, flags_offset;
   void *peer_base[kMaxPeers];       // IPC mappings of the peers' windows (NULL for self / not opened)
   bool opened;
+  bool attached;                    // sequence flags only ever grow: a window serves exactly one swarm
 };
 
 struct nls_pso {
@@ -876,6 +877,7 @@ int nls_xchg_create(nls_ctx *ctx, uint64_t record_bytes, int world, int rank, nl
   nls_xchg *x = new nls_xchg();
   x->ctx = ctx;
   x->opened = false;
+  x->attached = false;
   x->flags_offset = round_up(2 * size_t(world) * record_bytes, 256);
   x->bytes = x->flags_offset + 2 * size_t(world) * sizeof(unsigned long long);
   for (int r = 0; r < kMaxPeers; r++) { x->peer_base[r] = nullptr; x->w.records[r] = nullptr; x->w.flags[r] = nullptr; }
@@ -931,6 +933,8 @@ int nls_pso_attach_exchange(nls_pso *p, nls_xchg *x) {
   if (!p || !x) return fail(NLS_ERR_INVALID, "nls_pso_attach_exchange: NULL argument");
   if (!x->opened) return fail(NLS_ERR_STATE, "nls_pso_attach_exchange: open the peers' handles first");
   if (x->w.record_bytes != p->record_bytes) return fail(NLS_ERR_INVALID, "exchange window record size mismatch");
+  if (x->attached) return fail(NLS_ERR_STATE, "nls_pso_attach_exchange: an exchange window serves one swarm; create a new one");
+  x->attached = true;
   NLS_CUDA(cudaSetDevice(p->ctx->device));
   p->xchg = x;
   if (p->first_apply_pending) {   // finish the first update_best_positions across the shards (nlsolver.h:2595)

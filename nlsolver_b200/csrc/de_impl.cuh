@@ -1,5 +1,6 @@
-// de_impl.cuh — the DE generation on B200.  One warp owns one agent; rows live agent-major in HBM and are streamed
-// with 128-bit loads; the objective is a lane-strided sum closed by a warp butterfly.
+// de_impl.cuh — the DE generation on B200.  A warp owns a tile of agents: per-agent scalar work runs one agent per lane,
+// row streaming runs one agent per warp (or per 4 / 8 / 16-lane group for short rows); rows live agent-major in HBM and
+// are streamed with 128-bit loads; the objective is a lane-strided sum closed by a butterfly.
 //
 // Reference semantics being reproduced (DE::solve, nlsolver.h:2413-2476): agents are processed sequentially and IN
 // PLACE — agent i reads donor r's row *after* r's own greedy selection when r < i and *before* it when r > i
@@ -13,6 +14,7 @@
 //                              Round by round, an agent whose lower donors are all final becomes final; if any of
 //                              them was accepted, its trial is re-evaluated against the now-known rows.  Each agent
 //                              is therefore evaluated at most twice and the result equals the sequential loop.
+//                              Returns at once when the speculative pass accepted nothing.
 //   K3  de_commit_kernel     : commits accepted trials (score, row-location bit), then the population reduction:
 //                              min-loc with the reference's tie rule (nlsolver.h:2432-2437), the std_err statistic
 //                              (nlsolver.h:2037-2052) and the stop test (nlsolver.h:2439-2447), last block finalises.
