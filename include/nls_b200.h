@@ -44,7 +44,12 @@ enum { NLS_F32 = 0, NLS_F64 = 1 };
 
 /* Device objective functors: N-D forms that reduce to test_functions.h:51-92 at d = 2 (summation order is the
  * canonical one described in DESIGN.md); NLS_ROSENBROCK_EX is example.cpp:41-48 / README.md:83-90. */
-enum { NLS_SPHERE = 0, NLS_ROSENBROCK = 1, NLS_RASTRIGIN = 2, NLS_ACKLEY = 3, NLS_ROSENBROCK_EX = 4 };
+enum { NLS_SPHERE = 0, NLS_ROSENBROCK = 1, NLS_RASTRIGIN = 2, NLS_ACKLEY = 3, NLS_ROSENBROCK_EX = 4,
+       /* the other problems of the reference's test driver (test_functions.h:94-318, 485-524).  Closed forms of fixed
+        * dimension: dim must be 2 (NLS_SHEKEL: 4); NLS_STYBLINSKI_TANG is a sum of any dimension. */
+       NLS_BEALE = 5, NLS_GOLDSTEIN_PRICE = 6, NLS_THREE_HUMP_CAMEL = 7, NLS_MCCORMICK = 8, NLS_SCHAFFER_N2 = 9,
+       NLS_STYBLINSKI_TANG = 10, NLS_SHEKEL = 11, NLS_BOOTH = 12, NLS_BUKIN_N6 = 13, NLS_MATYAS = 14, NLS_LEVI_N13 = 15,
+       NLS_OBJECTIVE_COUNT = 16 };
 
 /* Same enumerator order as nlsolver::RecombinationStrategy {best, random} (nlsolver.h:2377) */
 enum { NLS_DE_BEST = 0, NLS_DE_RANDOM = 1 };

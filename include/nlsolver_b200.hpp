@@ -210,6 +210,71 @@ template <typename T> struct Ackley {                      // test_functions.h:8
   }
   std::vector<T> minimum() const { return {0.0, 0.0}; }
 };
+// ---- the other problems of the reference's test driver (test_functions.h:94-318, 485-524).  Closed forms of fixed
+// dimension (2, Shekel 4) except StyblinskiTang; operator() is the host evaluation in T (pow(v,2) written as v*v).
+#define NLS_B200_TAG(NAME, ID, DIM, MIN, ...)                                    \
+  template <typename T> struct NAME {                                            \
+    static constexpr int nls_objective = ID;                                     \
+    static constexpr size_t input_size() { return DIM; }                         \
+    T operator()(const std::vector<T> &x) const __VA_ARGS__                      \
+    std::vector<T> minimum() const { return MIN; }                               \
+  };
+#define NLS_B200_MIN(...) std::vector<T>{__VA_ARGS__}
+NLS_B200_TAG(Beale, NLS_BEALE, 2, NLS_B200_MIN(3.0, 0.5), {
+  const T xy = x[0] * x[1], a = T(1.5) - x[0] + xy, b = T(2.25) - x[0] + xy * x[1], c = T(2.625) - x[0] + xy * x[1] * x[1];
+  return a * a + b * b + c * c;
+})
+NLS_B200_TAG(Goldstein_Price, NLS_GOLDSTEIN_PRICE, 2, NLS_B200_MIN(0.0, -1.0), {
+  const T x0 = x[0], x1 = x[1], s1 = x0 + x1 + 1, s2 = 2 * x0 - 3 * x1;
+  const T a = 1 + (s1 * s1) * (19 - 14 * x0 + 3 * x0 * x0 - 14 * x1 + 6 * x0 * x1 + 3 * x1 * x1);
+  const T b = 30 + (s2 * s2) * (18 - 32 * x0 + 12 * x0 * x0 + 48 * x1 - 36 * x0 * x1 + 27 * x1 * x1);
+  return a * b;
+})
+NLS_B200_TAG(ThreeHumpCamel, NLS_THREE_HUMP_CAMEL, 2, NLS_B200_MIN(0.0, 0.0), {
+  const T x2 = x[0] * x[0], x4 = x2 * x2;
+  return 2 * x[0] * x[0] - T(1.05) * x4 + x4 * x2 / 6 + x[0] * x[1] + x[1] * x[1];
+})
+NLS_B200_TAG(McCormick, NLS_MCCORMICK, 2, NLS_B200_MIN(-0.54719, -1.54719), {
+  const T dlt = x[0] - x[1];
+  return std::sin(x[0] + x[1]) + dlt * dlt - T(1.5) * x[0] + T(2.5) * x[1] + 1;
+})
+NLS_B200_TAG(SchafferN2, NLS_SCHAFFER_N2, 2, NLS_B200_MIN(0.0, 0.0), {
+  const T sn = std::sin(x[0] * x[0] - x[1] * x[1]), dn = 1 + T(0.001) * (x[0] * x[0] + x[1] * x[1]);
+  return T(0.5) + (sn * sn - T(0.5)) / (dn * dn);
+})
+NLS_B200_TAG(StyblinskiTang, NLS_STYBLINSKI_TANG, 2, NLS_B200_MIN(-2.903534, -2.903534), {
+  return detail::lane_sum<T>(0, x.size(), T(0), [&](size_t j) { const T x2 = x[j] * x[j]; return x2 * x2 - 16 * x2 + 5 * x[j]; }) / T(2.0);
+})
+NLS_B200_TAG(Shekel, NLS_SHEKEL, 4, NLS_B200_MIN(4.0, 4.0, 4.0, 4.0), {
+  const T a[40] = {4, 4, 4, 4, 1, 1, 1, 1, 8, 8, 8, 8, 6, 6, 6, 6, 3, 7, 3, 7,
+                   2, 9, 2, 9, 5, 5, 3, 3, 8, 1, 8, 1, 6, 2, 6, 2, 7, T(3.6), 7, T(3.2)};
+  const T c[10] = {T(0.1), T(0.2), T(0.2), T(0.4), T(0.4), T(0.6), T(0.3), T(0.7), T(0.5), T(0.5)};
+  T sum = 0;
+  for (int i = 0; i < 10; i++) {
+    T inner = 0;
+    for (int j = 0; j < 4; j++) { const T dlt = x[j] - a[i * 4 + j]; inner += dlt * dlt; }
+    sum += T(1.0) / (inner + c[i]);
+  }
+  return -sum;
+})
+NLS_B200_TAG(Booth, NLS_BOOTH, 2, NLS_B200_MIN(1.0, 3.0), {
+  const T a = x[0] + 2 * x[1] - 7, b = 2 * x[0] + x[1] - 5;
+  return a * a + b * b;
+})
+NLS_B200_TAG(BukinN6, NLS_BUKIN_N6, 2, NLS_B200_MIN(-10.0, 1.0), {
+  return 100 * std::sqrt(std::abs(x[1] - T(0.01) * x[0] * x[0])) + T(0.01) * std::abs(x[0] + 10);
+})
+NLS_B200_TAG(Matyas, NLS_MATYAS, 2, NLS_B200_MIN(0.0, 0.0), {
+  return T(0.26) * (x[0] * x[0] + x[1] * x[1]) - T(0.48) * x[0] * x[1];
+})
+NLS_B200_TAG(LeviN13, NLS_LEVI_N13, 2, NLS_B200_MIN(1.0, 1.0), {
+  const T pi3 = T(3 * 3.14159265358979323846), pi2 = T(2 * 3.14159265358979323846);
+  const T s0 = std::sin(pi3 * x[0]), s1 = std::sin(pi3 * x[1]), s2 = std::sin(pi2 * x[1]), a = x[0] - 1, b = x[1] - 1;
+  return s0 * s0 + (a * a) * (1 + s1 * s1) + (b * b) * (1 + s2 * s2);
+})
+#undef NLS_B200_TAG
+#undef NLS_B200_MIN
+
 // the Rosenbrock variant of example.cpp:41-48 and README.md:83-90
 template <typename T> struct RosenbrockExample {
   static constexpr int nls_objective = NLS_ROSENBROCK_EX;

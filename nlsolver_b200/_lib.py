@@ -11,6 +11,8 @@ LIB_PATH = os.environ.get("NLS_B200_LIB") or os.path.join(HERE, "libnls_b200.so"
 
 F32, F64 = 0, 1
 SPHERE, ROSENBROCK, RASTRIGIN, ACKLEY, ROSENBROCK_EX = range(5)
+(BEALE, GOLDSTEIN_PRICE, THREE_HUMP_CAMEL, MCCORMICK, SCHAFFER_N2, STYBLINSKI_TANG, SHEKEL, BOOTH, BUKIN_N6, MATYAS,
+ LEVI_N13) = range(5, 16)
 DE_BEST, DE_RANDOM = 0, 1
 PSO_VANILLA, PSO_ACCELERATED = 0, 1
 FLAG_RECORD_MASKS, FLAG_SOCIAL_INDEX_J = 1, 2

@@ -62,7 +62,14 @@ const ObjectivePlugin *plugin_for(int objective) {
   return (k >= 0 && k < int(plugin_registry().size())) ? plugin_registry()[k] : nullptr;
 }
 bool objective_known(int objective) {
-  return (objective >= 0 && objective <= NLS_ROSENBROCK_EX) || plugin_for(objective) != nullptr;
+  return (objective >= 0 && objective < NLS_OBJECTIVE_COUNT) || plugin_for(objective) != nullptr;
+}
+// dimension a closed-form objective is defined for (0: any)
+unsigned objective_fixed_dim(int objective) {
+  if (const ObjectivePlugin *pl = plugin_for(objective)) return pl->full_dim;
+  if (objective == NLS_SHEKEL) return 4;
+  if (objective >= NLS_BEALE && objective <= NLS_LEVI_N13 && objective != NLS_STYBLINSKI_TANG) return 2;
+  return 0;
 }
 u64 round_up(u64 v, u64 m) { return (v + m - 1) / m * m; }
 
@@ -280,10 +287,10 @@ uint64_t nls_record_bytes(int32_t dtype, uint64_t dim) {
 static int de_validate(const nls_de_cfg *c) {
   if (c->dtype != NLS_F32 && c->dtype != NLS_F64) return fail(NLS_ERR_INVALID, "DE: unknown dtype %d", c->dtype);
   if (!objective_known(c->objective)) return fail(NLS_ERR_INVALID, "DE: unknown objective %d", c->objective);
-  if (const ObjectivePlugin *pl = plugin_for(c->objective))
-    if (pl->full_dim && pl->full_dim != c->dim)
-      return fail(NLS_ERR_INVALID, "DE: objective %d is a closed form of dimension %u, dim is %llu", c->objective,
-                  pl->full_dim, static_cast<unsigned long long>(c->dim));
+  if (const unsigned fd = objective_fixed_dim(c->objective))
+    if (fd != c->dim)
+      return fail(NLS_ERR_INVALID, "DE: objective %d is a closed form of dimension %u, dim is %llu", c->objective, fd,
+                  static_cast<unsigned long long>(c->dim));
   if (c->strategy != NLS_DE_BEST && c->strategy != NLS_DE_RANDOM) return fail(NLS_ERR_INVALID, "DE: unknown strategy %d", c->strategy);
   if (c->pop_size < 4) return fail(NLS_ERR_INVALID, "DE: pop_size must be >= 4 (three distinct donors besides the fixed agent)");
   if (c->dim < 1) return fail(NLS_ERR_INVALID, "DE: dim must be >= 1");
@@ -603,10 +610,10 @@ int nls_de_solve(nls_ctx *ctx, const nls_de_cfg *cfg, const void *x0_host, void 
 static int pso_validate(const nls_pso_cfg *c) {
   if (c->dtype != NLS_F32 && c->dtype != NLS_F64) return fail(NLS_ERR_INVALID, "PSO: unknown dtype %d", c->dtype);
   if (!objective_known(c->objective)) return fail(NLS_ERR_INVALID, "PSO: unknown objective %d", c->objective);
-  if (const ObjectivePlugin *pl = plugin_for(c->objective))
-    if (pl->full_dim && pl->full_dim != c->dim)
-      return fail(NLS_ERR_INVALID, "PSO: objective %d is a closed form of dimension %u, dim is %llu", c->objective,
-                  pl->full_dim, static_cast<unsigned long long>(c->dim));
+  if (const unsigned fd = objective_fixed_dim(c->objective))
+    if (fd != c->dim)
+      return fail(NLS_ERR_INVALID, "PSO: objective %d is a closed form of dimension %u, dim is %llu", c->objective, fd,
+                  static_cast<unsigned long long>(c->dim));
   if (c->pso_type != NLS_PSO_VANILLA && c->pso_type != NLS_PSO_ACCELERATED) return fail(NLS_ERR_INVALID, "PSO: unknown type %d", c->pso_type);
   if (c->n_particles < 1 || c->dim < 1) return fail(NLS_ERR_INVALID, "PSO: n_particles and dim must be >= 1");
   const u64 pg = c->n_particles_global ? c->n_particles_global : c->n_particles;

@@ -12,8 +12,95 @@
 
 namespace nls {
 
-enum { OBJ_SPHERE = 0, OBJ_ROSENBROCK = 1, OBJ_RASTRIGIN = 2, OBJ_ACKLEY = 3, OBJ_ROSENBROCK_EX = 4, OBJ_COUNT = 5,
-       OBJ_CUSTOM = 100 };
+enum { OBJ_SPHERE = 0, OBJ_ROSENBROCK = 1, OBJ_RASTRIGIN = 2, OBJ_ACKLEY = 3, OBJ_ROSENBROCK_EX = 4,
+       // the other problems the reference's test driver runs DE / PSO on (test_functions.h:94-318, 485-524)
+       OBJ_BEALE = 5, OBJ_GOLDSTEIN_PRICE = 6, OBJ_THREE_HUMP_CAMEL = 7, OBJ_MCCORMICK = 8, OBJ_SCHAFFER_N2 = 9,
+       OBJ_STYBLINSKI_TANG = 10, OBJ_SHEKEL = 11, OBJ_BOOTH = 12, OBJ_BUKIN_N6 = 13, OBJ_MATYAS = 14, OBJ_LEVI_N13 = 15,
+       OBJ_COUNT = 16, OBJ_CUSTOM = 100 };
+
+// Closed forms over a short vector: the reference's fixed-dimension test problems.  Dimension of objective `obj`
+// (0: not a closed form — a sum of any dimension).
+__host__ __device__ constexpr unsigned closed_form_dim(int obj) {
+  return obj == OBJ_SHEKEL ? 4u
+         : (obj == OBJ_BEALE || obj == OBJ_GOLDSTEIN_PRICE || obj == OBJ_THREE_HUMP_CAMEL || obj == OBJ_MCCORMICK ||
+            obj == OBJ_SCHAFFER_N2 || obj == OBJ_BOOTH || obj == OBJ_BUKIN_N6 || obj == OBJ_MATYAS || obj == OBJ_LEVI_N13)
+               ? 2u : 0u;
+}
+
+template <class T> __device__ __forceinline__ T t_sin(T x);
+template <> __device__ __forceinline__ double t_sin<double>(double x) { return sin(x); }
+template <> __device__ __forceinline__ float t_sin<float>(float x) { return sinf(x); }
+
+// f(x) for the closed forms, contraction-free; pow(v, 2) of the reference is v*v, pow(v, 4) = (v*v)*(v*v),
+// pow(v, 6) = ((v*v)*(v*v))*(v*v) (the oracle restates them the same way).
+template <class T, int OBJ, unsigned D>
+__device__ __forceinline__ T closed_form(const T (&x)[D]) {
+  typedef Ar<T> A;
+  auto sq = [](T v) { return Ar<T>::mul(v, v); };
+  if constexpr (OBJ == OBJ_BEALE) {                     // test_functions.h:98-102
+    const T xy = A::mul(x[0], x[1]), xyy = A::mul(xy, x[1]), xyyy = A::mul(xyy, x[1]);
+    return A::add(A::add(sq(A::add(A::sub(T(1.5), x[0]), xy)), sq(A::add(A::sub(T(2.25), x[0]), xyy))),
+                  sq(A::add(A::sub(T(2.625), x[0]), xyyy)));
+  } else if constexpr (OBJ == OBJ_GOLDSTEIN_PRICE) {    // :109-117
+    const T x0 = x[0], x1 = x[1];
+    T p = A::sub(T(19), A::mul(T(14), x0));
+    p = A::add(p, A::mul(A::mul(T(3), x0), x0));
+    p = A::sub(p, A::mul(T(14), x1));
+    p = A::add(p, A::mul(A::mul(T(6), x0), x1));
+    p = A::add(p, A::mul(A::mul(T(3), x1), x1));
+    const T a = A::add(T(1), A::mul(sq(A::add(A::add(x0, x1), T(1))), p));
+    T q = A::sub(T(18), A::mul(T(32), x0));
+    q = A::add(q, A::mul(A::mul(T(12), x0), x0));
+    q = A::add(q, A::mul(T(48), x1));
+    q = A::sub(q, A::mul(A::mul(T(36), x0), x1));
+    q = A::add(q, A::mul(A::mul(T(27), x1), x1));
+    const T b = A::add(T(30), A::mul(sq(A::sub(A::mul(T(2), x0), A::mul(T(3), x1))), q));
+    return A::mul(a, b);
+  } else if constexpr (OBJ == OBJ_THREE_HUMP_CAMEL) {   // :146-148
+    const T x2 = sq(x[0]), x4 = A::mul(x2, x2), x6 = A::mul(x4, x2);
+    T r = A::sub(A::mul(A::mul(T(2), x[0]), x[0]), A::mul(T(1.05), x4));
+    r = A::add(r, x6 / T(6));
+    r = A::add(r, A::mul(x[0], x[1]));
+    return A::add(r, sq(x[1]));
+  } else if constexpr (OBJ == OBJ_MCCORMICK) {          // :209-211
+    T r = A::add(t_sin<T>(A::add(x[0], x[1])), sq(A::sub(x[0], x[1])));
+    r = A::sub(r, A::mul(T(1.5), x[0]));
+    r = A::add(r, A::mul(T(2.5), x[1]));
+    return A::add(r, T(1));
+  } else if constexpr (OBJ == OBJ_SCHAFFER_N2) {        // :219-221
+    const T s2 = sq(t_sin<T>(A::sub(sq(x[0]), sq(x[1]))));
+    const T den = sq(A::add(T(1), A::mul(T(0.001), A::add(sq(x[0]), sq(x[1])))));
+    return A::add(T(0.5), A::sub(s2, T(0.5)) / den);
+  } else if constexpr (OBJ == OBJ_SHEKEL) {             // :258-276, 4-D, ten wells
+    const T a[40] = {4, 4, 4, 4, 1, 1, 1, 1, 8, 8, 8, 8, 6, 6, 6, 6, 3, 7, 3, 7,
+                     2, 9, 2, 9, 5, 5, 3, 3, 8, 1, 8, 1, 6, 2, 6, 2, 7, T(3.6), 7, T(3.2)};
+    const T c[10] = {T(0.1), T(0.2), T(0.2), T(0.4), T(0.4), T(0.6), T(0.3), T(0.7), T(0.5), T(0.5)};
+    T sum = T(0);
+#pragma unroll
+    for (int i = 0; i < 10; i++) {
+      T inner = T(0);
+#pragma unroll
+      for (int j = 0; j < 4; j++) inner = A::add(inner, sq(A::sub(x[j], a[i * 4 + j])));
+      sum = A::add(sum, T(1.0) / A::add(inner, c[i]));
+    }
+    return -sum;
+  } else if constexpr (OBJ == OBJ_BOOTH) {              // :283-285
+    return A::add(sq(A::sub(A::add(x[0], A::mul(T(2), x[1])), T(7))), sq(A::sub(A::add(A::mul(T(2), x[0]), x[1]), T(5))));
+  } else if constexpr (OBJ == OBJ_BUKIN_N6) {           // :292-295
+    const T r = t_sqrt<T>(fabs(A::sub(x[1], A::mul(A::mul(T(0.01), x[0]), x[0]))));
+    return A::add(A::mul(T(100), r), A::mul(T(0.01), fabs(A::add(x[0], T(10)))));
+  } else if constexpr (OBJ == OBJ_MATYAS) {             // :302-304
+    return A::sub(A::mul(T(0.26), A::add(sq(x[0]), sq(x[1]))), A::mul(A::mul(T(0.48), x[0]), x[1]));
+  } else if constexpr (OBJ == OBJ_LEVI_N13) {           // :311-317
+    const T pi3 = T(3 * 3.14159265358979323846), pi2 = T(2 * 3.14159265358979323846);
+    const T s0 = sq(t_sin<T>(A::mul(pi3, x[0])));
+    const T t1 = A::mul(sq(A::sub(x[0], T(1))), A::add(T(1), sq(t_sin<T>(A::mul(pi3, x[1])))));
+    const T t2 = A::mul(sq(A::sub(x[1], T(1))), A::add(T(1), sq(t_sin<T>(A::mul(pi2, x[1])))));
+    return A::add(A::add(s0, t1), t2);
+  } else {
+    return T(0);
+  }
+}
 
 // User-supplied objective of an objective plugin (objective_plugin.cuh): defined only in the plugin's translation unit.
 //   static constexpr bool pairwise;                      term also receives x[j-1] (terms start at j = 1)
@@ -36,7 +123,7 @@ struct Objective {
   static constexpr int V = Vec<T>::V;
   static constexpr unsigned custom_full_dim() {
     if constexpr (OBJ == OBJ_CUSTOM) return plugin_full_dim<CustomObjective<T>>::value;
-    else return 0;
+    else return closed_form_dim(OBJ);
   }
   static constexpr unsigned kFullDim = custom_full_dim();  // > 0: closed form over the whole (short) vector
   static constexpr bool custom_pairwise() {
@@ -65,7 +152,10 @@ struct Objective {
       T xs[kFullDim];
 #pragma unroll
       for (unsigned k = 0; k < kFullDim; k++) xs[k] = __shfl_sync(kFull, x[k % V], k / V, W);
-      if (lane == 0 && j0 == 0 && d == kFullDim) a = CustomObjective<T>::full(xs);
+      if (lane == 0 && j0 == 0 && d == kFullDim) {
+        if constexpr (OBJ == OBJ_CUSTOM) a = CustomObjective<T>::full(xs);
+        else a = closed_form<T, OBJ, kFullDim>(xs);
+      }
     } else {
     T left = T(0);
     if (kPairwise) {
@@ -99,6 +189,9 @@ struct Objective {
         } else if (OBJ == OBJ_ACKLEY) {
           a = A::add(a, A::mul(xj, xj));
           b = A::add(b, cos2pi<T>(xj));
+        } else if (OBJ == OBJ_STYBLINSKI_TANG) {         // pow(x,4) - 16*pow(x,2) + 5*x, test_functions.h:246-252
+          const T x2 = A::mul(xj, xj);
+          a = A::add(a, A::add(A::sub(A::mul(x2, x2), A::mul(T(16), x2)), A::mul(T(5), xj)));
         }
       }
     }
@@ -108,7 +201,8 @@ struct Objective {
   // every lane returns the objective value
   __device__ __forceinline__ T finish(u32 d) {
     a = warp_butterfly_add<T, W>(a);
-    if constexpr (OBJ == OBJ_CUSTOM && kFullDim > 0) return a;
+    if constexpr (kFullDim > 0) return a;
+    if (OBJ == OBJ_STYBLINSKI_TANG) return a / T(2.0);
     else if constexpr (OBJ == OBJ_CUSTOM) return CustomObjective<T>::finish(a, d);
     if (OBJ == OBJ_ACKLEY) {
       b = warp_butterfly_add<T, W>(b);

@@ -15,6 +15,9 @@ from . import _lib as L
 
 Sphere, Rosenbrock, Rastrigin, Ackley, RosenbrockExample = (L.SPHERE, L.ROSENBROCK, L.RASTRIGIN, L.ACKLEY,
                                                              L.ROSENBROCK_EX)
+# the other problems of the reference's test driver (test_functions.h:94-318)
+(Beale, Goldstein_Price, ThreeHumpCamel, McCormick, SchafferN2, StyblinskiTang, Shekel, Booth, BukinN6, Matyas,
+ LeviN13) = range(5, 16)
 
 
 class RecombinationStrategy:  # nlsolver.h:2377

@@ -18,6 +18,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 
 F32, F64 = 0, 1
 SPHERE, ROSENBROCK, RASTRIGIN, ACKLEY, ROSENBROCK_EX = range(5)
+(BEALE, GOLDSTEIN_PRICE, THREE_HUMP_CAMEL, MCCORMICK, SCHAFFER_N2, STYBLINSKI_TANG, SHEKEL, BOOTH, BUKIN_N6, MATYAS,
+ LEVI_N13) = range(5, 16)
 CUSTOM = 100
 DE_BEST, DE_RANDOM = 0, 1
 PSO_VANILLA, PSO_ACCELERATED = 0, 1
@@ -98,6 +100,8 @@ def _load(path, prefix, with_extras):
     if with_extras:
         lib.ref_de_time.argtypes = [C.POINTER(DECfg), C.c_void_p, C.POINTER(f64), C.POINTER(Status)]
         lib.ref_pso_time.argtypes = [C.POINTER(PSOCfg), C.c_void_p, C.POINTER(f64), C.POINTER(Status)]
+        lib.ref_objective_nd.argtypes = [C.c_int, C.c_void_p, u64]
+        lib.ref_objective_nd.restype = f64
         lib.ref_objective_2d.argtypes = [C.c_int, f64, f64]
         lib.ref_objective_2d.restype = f64
         lib.ref_xorshift_draws.argtypes = [C.c_int, u64, C.c_void_p]

@@ -21,6 +21,9 @@ extern "C" {
 enum { ORC_F32 = 0, ORC_F64 = 1 };
 /* objective ids: N-D forms that reduce to test_functions.h:51-92 at d = 2; id 4 is example.cpp:41-48 */
 enum { ORC_SPHERE = 0, ORC_ROSENBROCK = 1, ORC_RASTRIGIN = 2, ORC_ACKLEY = 3, ORC_ROSENBROCK_EX = 4,
+       /* the other problems of the reference's test driver, test_functions.h:94-318 */
+       ORC_BEALE = 5, ORC_GOLDSTEIN_PRICE = 6, ORC_THREE_HUMP_CAMEL = 7, ORC_MCCORMICK = 8, ORC_SCHAFFER_N2 = 9,
+       ORC_STYBLINSKI_TANG = 10, ORC_SHEKEL = 11, ORC_BOOTH = 12, ORC_BUKIN_N6 = 13, ORC_MATYAS = 14, ORC_LEVI_N13 = 15,
        ORC_CUSTOM = 100 /* callbacks installed with oracle_set_custom_objective (objective-plugin tests) */ };
 /* same order as the reference enums (nlsolver.h:2377, 2496) */
 enum { ORC_DE_BEST = 0, ORC_DE_RANDOM = 1 };

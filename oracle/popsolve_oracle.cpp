@@ -164,6 +164,65 @@ T objective(int id, const T *x, size_t d) {
       const T b = -std::exp(inv_d * cs.total());
       return a + b + static_cast<T>(std::exp(1.0)) + static_cast<T>(20);
     }
+    /* ---- the other problems of the reference's test driver (test_functions.h:94-318).  pow(v, 2) is restated as v*v,
+     *      pow(v, 4) as (v*v)*(v*v), pow(v, 6) as ((v*v)*(v*v))*(v*v); everything in T. ---- */
+    case ORC_BEALE: {  /* :98-102 */
+      const T xy = x[0] * x[1], xyy = xy * x[1], xyyy = xyy * x[1];
+      const T a = static_cast<T>(1.5) - x[0] + xy, b = static_cast<T>(2.25) - x[0] + xyy, c = static_cast<T>(2.625) - x[0] + xyyy;
+      return a * a + b * b + c * c;
+    }
+    case ORC_GOLDSTEIN_PRICE: {  /* :109-117 */
+      const T x0 = x[0], x1 = x[1];
+      const T s1 = x0 + x1 + 1, s2 = 2 * x0 - 3 * x1;
+      const T a = 1 + (s1 * s1) * (19 - 14 * x0 + 3 * x0 * x0 - 14 * x1 + 6 * x0 * x1 + 3 * x1 * x1);
+      const T b = 30 + (s2 * s2) * (18 - 32 * x0 + 12 * x0 * x0 + 48 * x1 - 36 * x0 * x1 + 27 * x1 * x1);
+      return a * b;
+    }
+    case ORC_THREE_HUMP_CAMEL: {  /* :146-148 */
+      const T x2 = x[0] * x[0], x4 = x2 * x2, x6 = x4 * x2;
+      return 2 * x[0] * x[0] - static_cast<T>(1.05) * x4 + x6 / 6 + x[0] * x[1] + x[1] * x[1];
+    }
+    case ORC_MCCORMICK: {  /* :209-211 */
+      const T dlt = x[0] - x[1];
+      return std::sin(x[0] + x[1]) + dlt * dlt - static_cast<T>(1.5) * x[0] + static_cast<T>(2.5) * x[1] + 1;
+    }
+    case ORC_SCHAFFER_N2: {  /* :219-221 */
+      const T sn = std::sin(x[0] * x[0] - x[1] * x[1]);
+      const T dn = 1 + static_cast<T>(0.001) * (x[0] * x[0] + x[1] * x[1]);
+      return static_cast<T>(0.5) + (sn * sn - static_cast<T>(0.5)) / (dn * dn);
+    }
+    case ORC_STYBLINSKI_TANG: {  /* :246-252, any dimension */
+      Lanes<T> s;
+      for (size_t j = 0; j < d; j++) { const T x2 = x[j] * x[j]; s.add(j, x2 * x2 - 16 * x2 + 5 * x[j]); }
+      return s.total() / static_cast<T>(2.0);
+    }
+    case ORC_SHEKEL: {  /* :258-276 */
+      const T a[40] = {4, 4, 4, 4, 1, 1, 1, 1, 8, 8, 8, 8, 6, 6, 6, 6, 3, 7, 3, 7,
+                       2, 9, 2, 9, 5, 5, 3, 3, 8, 1, 8, 1, 6, 2, 6, 2, 7, static_cast<T>(3.6), 7, static_cast<T>(3.2)};
+      const T c[10] = {static_cast<T>(0.1), static_cast<T>(0.2), static_cast<T>(0.2), static_cast<T>(0.4), static_cast<T>(0.4),
+                       static_cast<T>(0.6), static_cast<T>(0.3), static_cast<T>(0.7), static_cast<T>(0.5), static_cast<T>(0.5)};
+      T sum = 0;
+      for (int i = 0; i < 10; i++) {
+        T inner = 0;
+        for (int j = 0; j < 4; j++) { const T dlt = x[j] - a[i * 4 + j]; inner += dlt * dlt; }
+        sum += static_cast<T>(1.0) / (inner + c[i]);
+      }
+      return -sum;
+    }
+    case ORC_BOOTH: {  /* :283-285 */
+      const T a = x[0] + 2 * x[1] - 7, b = 2 * x[0] + x[1] - 5;
+      return a * a + b * b;
+    }
+    case ORC_BUKIN_N6:  /* :292-295 */
+      return 100 * std::sqrt(std::abs(x[1] - static_cast<T>(0.01) * x[0] * x[0])) + static_cast<T>(0.01) * std::abs(x[0] + 10);
+    case ORC_MATYAS:  /* :302-304 */
+      return static_cast<T>(0.26) * (x[0] * x[0] + x[1] * x[1]) - static_cast<T>(0.48) * x[0] * x[1];
+    case ORC_LEVI_N13: {  /* :311-317 */
+      const T pi3 = static_cast<T>(3 * M_PI), pi2 = static_cast<T>(2 * M_PI);
+      const T s0 = std::sin(pi3 * x[0]), s1 = std::sin(pi3 * x[1]), s2 = std::sin(pi2 * x[1]);
+      const T a = x[0] - 1, b = x[1] - 1;
+      return s0 * s0 + (a * a) * (1 + s1 * s1) + (b * b) * (1 + s2 * s2);
+    }
   }
   return std::nan("");
 }

@@ -333,6 +333,29 @@ int ref_pso_time(const orc_pso_cfg *c, const void *upper, double *seconds, orc_s
   return c->dtype == ORC_F64 ? pso_time<double>(c, upper, seconds, st) : pso_time<float>(c, upper, seconds, st);
 }
 /* the reference's own 2-D objectives (test_functions.h:51-92), double */
+/* every objective the reference's test driver uses, evaluated by the reference's own functor (double) */
+double ref_objective_nd(int id, const double *xs, uint64_t d) {
+  std::vector<double> x(xs, xs + d);
+  namespace tf = nlsolver::test_functions;
+  switch (id) {
+    case ORC_SPHERE: return tf::Sphere<double>()(x);
+    case ORC_ROSENBROCK: return tf::Rosenbrock<double>()(x);
+    case ORC_RASTRIGIN: return tf::Rastrigin<double>()(x);
+    case ORC_ACKLEY: return tf::Ackley<double>()(x);
+    case ORC_BEALE: return tf::Beale<double>()(x);
+    case ORC_GOLDSTEIN_PRICE: return tf::Goldstein_Price<double>()(x);
+    case ORC_THREE_HUMP_CAMEL: return tf::ThreeHumpCamel<double>()(x);
+    case ORC_MCCORMICK: return tf::McCormick<double>()(x);
+    case ORC_SCHAFFER_N2: return tf::SchafferN2<double>()(x);
+    case ORC_STYBLINSKI_TANG: return tf::StyblinskiTang<double>()(x);
+    case ORC_SHEKEL: return tf::Shekel<double>()(x);
+    case ORC_BOOTH: return tf::Booth<double>()(x);
+    case ORC_BUKIN_N6: return tf::BukinN6<double>()(x);
+    case ORC_MATYAS: return tf::Matyas<double>()(x);
+    case ORC_LEVI_N13: return tf::LeviN13<double>()(x);
+  }
+  return 0.0 / 0.0;
+}
 double ref_objective_2d(int id, double x0, double x1) {
   std::vector<double> x = {x0, x1};
   switch (id) {
