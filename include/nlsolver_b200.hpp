@@ -126,6 +126,33 @@ struct xoshiro {
   uint64_t s[4];
 };
 
+// nlsolver.h:1179-1225 — van der Corput / Halton sequence in base b (quasi-random)
+template <typename scalar_t = float>
+struct halton {
+  explicit halton(const scalar_t base = 2) : b(base), y(1), n(0), d(1), x(1) {}
+  scalar_t yield() {
+    x = d - n;
+    if (x == 1) {
+      n = 1;
+      d *= b;
+    } else {
+      y = d;
+      while (x <= y) {
+        y /= b;
+        n = (b + 1) * y - x;
+      }
+    }
+    return static_cast<scalar_t>(n / d);
+  }
+  scalar_t operator()() { return yield(); }
+  void reset() { b = 2; y = 1; n = 0; d = 1; x = 1; }
+  std::vector<scalar_t> get_state() const { return {b, y, n, d, x}; }
+  void set_state(scalar_t b_, scalar_t y_, scalar_t n_, scalar_t d_, scalar_t x_) { b = b_; y = y_; n = n_; d = d_; x = x_; }
+
+ private:
+  scalar_t b, y, n, d, x;
+};
+
 // nlsolver.h:1228-1261 — additive recurrence z <- frac(z + alpha), alpha = 0.618034
 template <typename scalar_t = float>
 struct recurrent {

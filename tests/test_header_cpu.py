@@ -21,6 +21,8 @@ int main() {
   dump("recurrent<double>", nlsolver::rng::recurrent<double>());
   dump("recurrent<float>", nlsolver::rng::recurrent<float>());
   dump("splitmix<double>", nlsolver::rng::splitmix<double>());
+  dump("halton<double>", nlsolver::rng::halton<double>());
+  dump("halton<float> base 3", nlsolver::rng::halton<float>(3));
   nlsolver::rng::xorshift<double> g; g(); g(); g.reset(); dump("xorshift reset", g);
 }
 """
@@ -51,3 +53,16 @@ def test_header_generators_reproduce_reference_streams(tmp_path):
     ours = build_and_run(tmp_path, "ours", "nlsolver_b200.hpp", ["-I", os.path.join(ROOT, "include")] + lib)
     theirs = build_and_run(tmp_path, "theirs", "nlsolver.h", ["-I", os.path.dirname(REF)])
     assert ours == theirs
+
+
+def test_c_abi_header_is_plain_c(tmp_path):
+    """include/nls_b200.h must be consumable from C (cgo / FFI generators read it as C)."""
+    src = tmp_path / "abi.c"
+    src.write_text('#include "nls_b200.h"\n'
+                   'int main(void) { nls_de_cfg c; nls_pso_cfg p; nls_status s; (void)c; (void)p; (void)s;\n'
+                   '  return nls_version() == NLS_B200_VERSION ? 0 : 1; }\n')
+    exe = tmp_path / "abi"
+    subprocess.run(["gcc", "-std=c11", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"),
+                    str(src), "-L", os.path.join(ROOT, "nlsolver_b200"), "-lnls_b200",
+                    "-Wl,-rpath," + os.path.join(ROOT, "nlsolver_b200"), "-o", str(exe)], check=True)
+    assert subprocess.run([str(exe)]).returncode == 0
