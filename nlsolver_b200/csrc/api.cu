@@ -556,7 +556,7 @@ int nls_de_export_best(nls_de *de, void *record_dev) {
   return NLS_OK;
 }
 static int de_ensure_topk_scratch(nls_de *de, uint64_t k) {
-  const size_t need = ((de->s.P + 4095) / 4096) * k * 16;
+  const size_t need = std::min<size_t>((de->s.P + 4095) / 4096, 4096) * k * 16;   // one (key, visit) pair per list and rank
   if (need <= de->topk_capacity) return NLS_OK;
   void *p = nullptr;
   int rc = de->mem.alloc(&p, need);

@@ -547,28 +547,43 @@ __global__ void __launch_bounds__(kBlock) de_topk_partial_kernel(DEState s, int 
   }
 }
 
+// Phase 2: every block's candidate list is already in ascending (key, visit) order, so the global top-k is a k-step
+// merge of the lists' heads: each thread looks at the heads of its lists (one load each), a block-wide arg-min picks the
+// winner and advances that list.  (Scanning all candidates every round instead costs k * n_cand dependent L2 reads in a
+// single block — 2 ms for 256 lists of 64, which used to dominate a migration.)
+constexpr u32 kMaxTopkLists = 4096;
 template <class T>
-__global__ void __launch_bounds__(kBlock) de_topk_final_kernel(DEState s, int sign, u32 k, u64 n_cand, const TopKey *cand) {
+__global__ void __launch_bounds__(kBlock) de_topk_final_kernel(DEState s, int sign, u32 k, u32 n_lists, const TopKey *cand) {
   __shared__ TopKey sm[kWarpsPerBlock];
-  TopKey cursor; cursor.key = -CUDART_INF; cursor.visit = kNoVisit;
-  bool started = false;
+  __shared__ u32 sm_src[kWarpsPerBlock];
+  __shared__ u32 heads[kMaxTopkLists];
+  for (u32 b = threadIdx.x; b < n_lists; b += kBlock) heads[b] = 0;
+  __syncthreads();
   for (u32 e = 0; e < k; e++) {
     TopKey best; best.key = CUDART_INF; best.visit = kNoVisit;
-    for (u64 q = threadIdx.x; q < n_cand; q += kBlock) {
-      TopKey c; c.key = cand[q].key; c.visit = cand[q].visit;
-      if (c.visit == kNoVisit) continue;
-      const bool beyond = !started || topkey_less(cursor, c);
-      if (beyond && topkey_less(c, best)) best = c;
+    u32 src = 0xffffffffu;
+    for (u32 b = threadIdx.x; b < n_lists; b += kBlock) {
+      const u32 h = heads[b];
+      if (h >= k) continue;
+      TopKey c; c.key = cand[u64(b) * k + h].key; c.visit = cand[u64(b) * k + h].visit;
+      if (c.visit != kNoVisit && topkey_less(c, best)) { best = c; src = b; }
     }
-    best = topkey_block_min(best, sm);
-    if (threadIdx.x == 0)
+    // block arg-min carrying the source list
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+      TopKey o; o.key = __shfl_down_sync(kFull, best.key, off); o.visit = __shfl_down_sync(kFull, best.visit, off);
+      const u32 os = __shfl_down_sync(kFull, src, off);
+      if (topkey_less(o, best)) { best = o; src = os; }
+    }
+    if (lane == 0) { sm[w] = best; sm_src[w] = src; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int q = 1; q < kWarpsPerBlock; q++) if (topkey_less(sm[q], best)) { best = sm[q]; src = sm_src[q]; }
       s.list[e] = best.visit == kNoVisit ? 0xffffffffu : u32(sign > 0 ? best.visit : s.P - 1 - best.visit);
-    if (best.visit == kNoVisit) {
-      for (u32 r = e + 1 + threadIdx.x; r < k; r += kBlock) s.list[r] = 0xffffffffu;
-      break;
+      if (best.visit != kNoVisit) heads[src] += 1;
     }
-    cursor = best;
-    started = true;
+    __syncthreads();
   }
 }
 
@@ -660,12 +675,14 @@ cudaError_t de_launch_export_best(const DEState &s, void *record, cudaStream_t s
 template <class T>
 cudaError_t de_launch_migrate(const DEState &s, int sign, unsigned long long k, void *rows, void *scores,
                               const LaunchGeom &g, cudaStream_t st) {
-  const u64 slice = 4096;
+  // contiguous slices of >= 4096 agents, at most kMaxTopkLists of them
+  u64 slice = (s.P + kMaxTopkLists - 1) / kMaxTopkLists;
+  if (slice < 4096) slice = 4096;
   const u64 blocks = (s.P + slice - 1) / slice;
-  if (!s.topk_scratch) return cudaErrorInvalidValue;   // sized by the host side: ceil(P / 4096) * k pairs
+  if (!s.topk_scratch) return cudaErrorInvalidValue;   // sized by the host side: up to kMaxTopkLists * k pairs
   TopKey *cand = reinterpret_cast<TopKey *>(s.topk_scratch);
   de_topk_partial_kernel<T><<<static_cast<unsigned int>(blocks), kBlock, 0, st>>>(s, sign, u32(k), slice, cand);
-  de_topk_final_kernel<T><<<1, kBlock, 0, st>>>(s, sign, u32(k), blocks * k, cand);
+  de_topk_final_kernel<T><<<1, kBlock, 0, st>>>(s, sign, u32(k), u32(blocks), cand);
   const unsigned int grid = clamp_grid(k, 4096);
   if (sign > 0) de_gather_kernel<T><<<grid, kBlock, 0, st>>>(s, u32(k), static_cast<T *>(rows), static_cast<T *>(scores));
   else {
