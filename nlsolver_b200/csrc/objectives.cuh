@@ -201,17 +201,21 @@ struct Objective {
   // every lane returns the objective value
   __device__ __forceinline__ T finish(u32 d) {
     a = warp_butterfly_add<T, W>(a);
-    if constexpr (kFullDim > 0) return a;
-    if (OBJ == OBJ_STYBLINSKI_TANG) return a / T(2.0);
-    else if constexpr (OBJ == OBJ_CUSTOM) return CustomObjective<T>::finish(a, d);
-    if (OBJ == OBJ_ACKLEY) {
+    if constexpr (kFullDim > 0) {
+      return a;                                            // closed forms: lane 0's value, the others added 0
+    } else if constexpr (OBJ == OBJ_CUSTOM) {
+      return CustomObjective<T>::finish(a, d);
+    } else if constexpr (OBJ == OBJ_STYBLINSKI_TANG) {
+      return a / T(2.0);
+    } else if constexpr (OBJ == OBJ_ACKLEY) {
       b = warp_butterfly_add<T, W>(b);
       const T inv_d = T(1.0) / T(d);
       const T ra = A::mul(T(-20), t_exp<T>(A::mul(T(-0.2), t_sqrt<T>(A::mul(inv_d, a)))));
       const T rb = -t_exp<T>(A::mul(inv_d, b));
       return A::add(A::add(A::add(ra, rb), T(2.718281828459045235360287)), T(20));
+    } else {
+      return a;
     }
-    return a;
   }
 };
 
