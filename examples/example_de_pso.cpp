@@ -1,4 +1,4 @@
-// example_de_pso.cpp — the DE / PSO sections of the reference's example.cpp (example.cpp:159-215) and the README
+// example_de_pso.cpp — the DE / PSO / SANN sections of the reference's example.cpp (example.cpp:159-223) and the README
 // snippet (README.md:94-110), compiled against the drop-in header.  Apart from the include and the objective type
 // (a device functor tag instead of a host functor) the call sites are the reference's.
 //
@@ -9,7 +9,9 @@
 using nlsolver::DE;
 using nlsolver::DESolver;
 using nlsolver::PSO;
+using nlsolver::SANN;
 using nlsolver::rng::xorshift;
+using nlsolver::rng::xoshiro;
 // the reference example defines its own Rosenbrock functor (example.cpp:41-48); this is its device twin
 using Rosenbrock = nlsolver::test_functions::RosenbrockExample<double>;
 
@@ -53,6 +55,17 @@ int main() {
   gen.reset();
   auto apso_solver = PSO<Rosenbrock, xorshift<double>, double, PSOType::Accelerated>(prob, gen);
   run_solver(apso_solver, {3, 3});
+
+  std::cout << "Simulated Annealing with xoshiro: " << std::endl;   // example.cpp:216-223
+  xoshiro<double> xos_gen;
+  auto sann_solver = SANN<Rosenbrock, xoshiro<double>, double>(prob, xos_gen);
+  run_solver(sann_solver, {5, 5});
+  // what the reference cannot do: 4096 chains from the same start, the best of them is reported
+  std::cout << "Simulated Annealing, 4096 chains: " << std::endl;
+  std::vector<double> sann_init = {5, 5};
+  auto sann_res = sann_solver.minimize_multistart(sann_init, 4096);
+  sann_res.print();
+  print_vector(sann_init);
 
   // a larger problem than the reference example can afford: Rastrigin, d = 100, 64k agents
   std::cout << "DE on Rastrigin d=100, population 65536: " << std::endl;

@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define NLS_B200_VERSION 100
+#define NLS_B200_VERSION 101
 
 #if defined(__GNUC__)
 #define NLS_API __attribute__((visibility("default")))
@@ -210,6 +210,38 @@ NLS_API int nls_xchg_open_peers(nls_xchg *x, const void *handles);
 NLS_API int nls_xchg_destroy(nls_xchg *x);
 NLS_API int nls_pso_attach_exchange(nls_pso *pso, nls_xchg *x);
 NLS_API int nls_pso_step_fused(nls_pso *pso, uint64_t n_generations);
+
+/* ---- simulated annealing as a batch of independent chains ----
+ * nlsolver::SANN (nlsolver.h:2744-2815) is one sequential chain; chains never interact, so many of them — multi-start
+ * from one point, or one start point per chain — run side by side with the reference's loop unchanged inside each.
+ * Chain c draws from tape stream (epoch, chain_offset + c); with n_chains = 1 this is SANN::minimize / maximize. */
+typedef struct nls_sann nls_sann;
+/* Mirrors the constructor of nlsolver::SANN (nlsolver.h:2757-2766). */
+typedef struct {
+  int32_t dtype, objective, minimize;
+  uint32_t flags;
+  uint64_t n_chains, dim;
+  uint64_t max_iter, temperature_iter; /* defaults 5000, 10: temperature_iter - 1 candidates per temperature */
+  double temperature_max;              /* default 10.0 */
+  uint64_t seed;
+  uint64_t chain_offset; /* global id of local chain 0 in the tape key (chains sharded over GPUs); 0 otherwise */
+} nls_sann_cfg;
+/* x0_host: x0_count rows of dim elements; x0_count = 1 (every chain starts there) or n_chains.  Evaluates f(x0). */
+NLS_API int nls_sann_create(nls_ctx *ctx, const nls_sann_cfg *cfg, const void *x0_host, uint64_t x0_count, nls_sann **out);
+/* enqueue up to n_candidates candidates per chain (clamped to what is left of max_iter * (temperature_iter - 1)) */
+NLS_API int nls_sann_step(nls_sann *sa, uint64_t n_candidates);
+/* status of the batch: f_value / best_index = the best chain (lowest best_val, lowest global chain id on ties),
+ * iterations = outer iterations completed, function_calls = n_chains * (1 + candidates evaluated per chain) */
+NLS_API int nls_sann_sync(nls_sann *sa, nls_status *status);
+NLS_API int nls_sann_read_best(nls_sann *sa, void *x_host); /* the best chain's x, dim elements */
+/* per-chain results, any pointer may be NULL: x_best / p_cur n_chains * dim elements (the reference's x and p),
+ * f_best n_chains elements, n_accepted / n_improved n_chains counters */
+NLS_API int nls_sann_read_chains(nls_sann *sa, void *x_best_host, void *f_best_host, void *p_cur_host,
+                                 uint32_t *n_accepted, uint32_t *n_improved);
+NLS_API int nls_sann_destroy(nls_sann *sa);
+/* one-shot: all chains to max_iter; x_best_host receives the best chain's x (dim elements) */
+NLS_API int nls_sann_solve(nls_ctx *ctx, const nls_sann_cfg *cfg, const void *x0_host, uint64_t x0_count,
+                           void *x_best_host, nls_status *status);
 
 #ifdef __cplusplus
 }

@@ -1,7 +1,7 @@
 // nlsolver_b200.hpp — drop-in C++17 header for the DE / PSO part of JSzitas/nlsolver, backed by the B200 engine.
 //
 // Same names, template parameter lists, constructor defaults and method signatures as the reference
-// (nlsolver.h:2377-2477 DE, 2496-2742 PSO, 2054-2097 solver_status, 1263-1288 / 1343-1381 the generators), so call
+// (nlsolver.h:2377-2477 DE, 2496-2742 PSO, 2744-2815 SANN, 2054-2097 solver_status, 1263-1288 / 1343-1381 the generators), so call
 // sites like example.cpp:184-215 or README.md:94-110 compile unchanged apart from the objective type: `Callable`
 // must be one of the device functor tags below (test_functions.h:51-92 names), because the objective runs on the
 // GPU.  Everything here is plain host C++ over the C ABI in nls_b200.h — no CUDA headers, link with -lnls_b200.
@@ -511,6 +511,86 @@ class PSO {
   const scalar_t inertia, cognitive_coef, social_coef;
   const size_t n_particles, max_iter, best_val_no_change;
   const scalar_t eps;
+};
+
+// ------------------------------------------------------------------------------------------------ SANN
+// nlsolver.h:2744-2815.  minimize(x) / maximize(x) run ONE chain from x, as the reference does.  The batch calls are
+// what this engine adds (the reference has no batching concept): one independent chain per start point — or n_chains
+// chains from one point — each the reference's loop on its own draw stream, all resident on the GPU.
+template <typename Callable, typename RNG, typename scalar_t = double>
+class SANN {
+  static_assert(b200::is_objective<Callable>(),
+                "nlsolver_b200: Callable must be a device objective tag (see nlsolver::test_functions) or a loaded "
+                "nlsolver::b200::PluginObjective");
+
+ public:
+  SANN(Callable &f, RNG &generator, const size_t max_iter = 5000, const size_t temperature_iter = 10,
+       const scalar_t temperature_max = 10.0)
+      : generator(generator), f(f), f_evals(0), max_iter(max_iter), temperature_iter(temperature_iter),
+        temperature_max(temperature_max) {}
+  solver_status<scalar_t> minimize(std::vector<scalar_t> &x) { return solve(x, true); }
+  solver_status<scalar_t> maximize(std::vector<scalar_t> &x) { return solve(x, false); }
+  // one chain per row of xs; every row is overwritten with its chain's best point
+  std::vector<solver_status<scalar_t>> minimize_batch(std::vector<std::vector<scalar_t>> &xs) { return batch(xs, true); }
+  std::vector<solver_status<scalar_t>> maximize_batch(std::vector<std::vector<scalar_t>> &xs) { return batch(xs, false); }
+  // n_chains chains from the same start x; x receives the best chain's point, the return value its status
+  solver_status<scalar_t> minimize_multistart(std::vector<scalar_t> &x, const size_t n_chains) { return multistart(x, n_chains, true); }
+  solver_status<scalar_t> maximize_multistart(std::vector<scalar_t> &x, const size_t n_chains) { return multistart(x, n_chains, false); }
+
+ private:
+  nls_sann_cfg config(size_t n_chains, size_t dim, bool minimize) {
+    nls_sann_cfg cfg{};
+    cfg.dtype = b200::dtype_of<scalar_t>();
+    cfg.objective = b200::objective_id(f);
+    cfg.minimize = minimize ? 1 : 0;
+    cfg.n_chains = n_chains;
+    cfg.dim = dim;
+    cfg.max_iter = max_iter;
+    cfg.temperature_iter = temperature_iter;
+    cfg.temperature_max = temperature_max;
+    cfg.seed = b200::seed_from(generator);
+    return cfg;
+  }
+  solver_status<scalar_t> multistart(std::vector<scalar_t> &x, size_t n_chains, bool minimize) {
+    const nls_sann_cfg cfg = config(n_chains, x.size(), minimize);
+    std::vector<scalar_t> best_row(x.size());
+    nls_status st{};
+    b200::check(nls_sann_solve(b200::default_context(), &cfg, x.data(), 1, best_row.data(), &st));
+    x = best_row;
+    f_evals += st.function_calls;                              // a member that is never reset (nlsolver.h:2751, 2783)
+    return solver_status<scalar_t>(static_cast<scalar_t>(st.f_value), st.iterations, f_evals);
+  }
+  solver_status<scalar_t> solve(std::vector<scalar_t> &x, bool minimize) { return multistart(x, 1, minimize); }
+  std::vector<solver_status<scalar_t>> batch(std::vector<std::vector<scalar_t>> &xs, bool minimize) {
+    std::vector<solver_status<scalar_t>> out;
+    if (xs.empty()) return out;
+    const size_t n = xs.size(), d = xs[0].size();
+    std::vector<scalar_t> flat(n * d), fbest(n);
+    for (size_t c = 0; c < n; c++) {
+      if (xs[c].size() != d) throw std::invalid_argument("nlsolver_b200: start points of different sizes");
+      for (size_t j = 0; j < d; j++) flat[c * d + j] = xs[c][j];
+    }
+    const nls_sann_cfg cfg = config(n, d, minimize);
+    nls_sann *h = nullptr;
+    b200::check(nls_sann_create(b200::default_context(), &cfg, flat.data(), n, &h));
+    nls_status st{};
+    int rc = nls_sann_step(h, ~0ull);
+    if (rc == NLS_OK) rc = nls_sann_sync(h, &st);
+    if (rc == NLS_OK) rc = nls_sann_read_chains(h, flat.data(), fbest.data(), nullptr, nullptr, nullptr);
+    nls_sann_destroy(h);
+    b200::check(rc);
+    f_evals += st.function_calls;
+    for (size_t c = 0; c < n; c++) {
+      for (size_t j = 0; j < d; j++) xs[c][j] = flat[c * d + j];
+      out.emplace_back(fbest[c], st.iterations, st.function_calls / n);
+    }
+    return out;
+  }
+  RNG &generator;
+  Callable &f;
+  size_t f_evals;
+  const size_t max_iter, temperature_iter;
+  const scalar_t temperature_max;
 };
 
 // the names README.md:80,99 uses

@@ -1,4 +1,4 @@
-"""nlsolver_b200 — B200 (sm_100a) engine for the DE / PSO population loop of JSzitas/nlsolver.
+"""nlsolver_b200 — B200 (sm_100a) engine for the DE / PSO population loop (and SANN chain batches) of JSzitas/nlsolver.
 
 The product is libnls_b200.so (C ABI: include/nls_b200.h; kernels: nlsolver_b200/csrc/).  This package is the
 Python host binding: `solvers` mirrors the reference's DE / PSO interface, `distributed` shards swarms and islands
@@ -12,3 +12,4 @@ from .solvers import (Beale, Booth, BukinN6, Goldstein_Price, LeviN13, Matyas, M
 from .solvers import (DE, PSO, Ackley, Context, DEPopulation, DESolver, ExchangeWindow, PSOSolver, PSOSwarm, PSOType,  # noqa: F401
                       Rastrigin, RecombinationStrategy, Rosenbrock, RosenbrockExample, SolverStatus, Sphere, de_cfg,
                       default_context, pso_cfg)
+from .solvers import SANN, SANNChains, sann_cfg  # noqa: F401

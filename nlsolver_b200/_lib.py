@@ -38,6 +38,12 @@ class PSOCfg(C.Structure):
                 ("seed", u64), ("particle_offset", u64), ("n_particles_global", u64)]
 
 
+class SANNCfg(C.Structure):
+    _fields_ = [("dtype", i32), ("objective", i32), ("minimize", i32), ("flags", u32),
+                ("n_chains", u64), ("dim", u64), ("max_iter", u64), ("temperature_iter", u64),
+                ("temperature_max", f64), ("seed", u64), ("chain_offset", u64)]
+
+
 class Status(C.Structure):
     _fields_ = [("f_value", f64), ("iterations", u64), ("function_calls", u64), ("best_index", u64),
                 ("val_no_change", u64), ("stopped", i32), ("stop_reason", i32), ("best_valid", i32),
@@ -100,6 +106,13 @@ SYMBOLS = {
     "nls_xchg_destroy": (C.c_int, [P]),
     "nls_pso_attach_exchange": (C.c_int, [P, P]),
     "nls_pso_step_fused": (C.c_int, [P, u64]),
+    "nls_sann_create": (C.c_int, [P, C.POINTER(SANNCfg), P, u64, C.POINTER(P)]),
+    "nls_sann_step": (C.c_int, [P, u64]),
+    "nls_sann_sync": (C.c_int, [P, C.POINTER(Status)]),
+    "nls_sann_read_best": (C.c_int, [P, P]),
+    "nls_sann_read_chains": (C.c_int, [P, P, P, P, P, P]),
+    "nls_sann_destroy": (C.c_int, [P]),
+    "nls_sann_solve": (C.c_int, [P, C.POINTER(SANNCfg), P, u64, P, C.POINTER(Status)]),
 }
 
 _lib = None

@@ -2,9 +2,10 @@
 //
 // Owns every device allocation behind opaque handles, validates arguments (the reference validates nothing:
 // pop_size < 4 loops forever in generate_indices, nlsolver.h:2344-2354), turns CUDA errors into return codes and
-// enqueues the kernels of de_impl.cuh / pso_impl.cuh on the context stream.  No CPU compute path exists here.
+// enqueues the kernels of de_impl.cuh / pso_impl.cuh / sann_impl.cuh on the context stream.  No CPU compute path exists here.
 #include <dlfcn.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -51,6 +52,7 @@ struct ObjectivePlugin {
   unsigned full_dim;
   const DEOps *de_f64, *de_f32;
   const PSOOps *pso_f64, *pso_f32;
+  const SANNOps *sann_f64, *sann_f32;
 };
 constexpr int kFirstPluginId = 100;
 std::vector<const ObjectivePlugin *> &plugin_registry() {
@@ -854,6 +856,209 @@ int nls_pso_solve(nls_ctx *ctx, const nls_pso_cfg *cfg, const void *lower_host, 
   return rc;
 }
 
+/* ================================================================ SANN chains ================================ */
+
+struct nls_sann {
+  nls_ctx *ctx;
+  nls_sann_cfg cfg;
+  SANNState s;
+  LaunchGeom g;
+  const SANNOps *ops;
+  DeviceBuffers mem;
+  size_t elem;
+  u64 steps_done;
+  void *dense;      // [C][d] staging for row read-out
+};
+
+static int sann_validate(const nls_sann_cfg *c, uint64_t x0_count) {
+  if (c->dtype != NLS_F32 && c->dtype != NLS_F64) return fail(NLS_ERR_INVALID, "SANN: unknown dtype %d", c->dtype);
+  if (!objective_known(c->objective)) return fail(NLS_ERR_INVALID, "SANN: unknown objective %d", c->objective);
+  if (const unsigned fd = objective_fixed_dim(c->objective))
+    if (fd != c->dim)
+      return fail(NLS_ERR_INVALID, "SANN: objective %d is a closed form of dimension %u, dim is %llu", c->objective, fd,
+                  static_cast<unsigned long long>(c->dim));
+  if (c->n_chains < 1 || c->dim < 1) return fail(NLS_ERR_INVALID, "SANN: n_chains and dim must be >= 1");
+  if (c->n_chains >= 0xffffffffull || c->dim >= 0xffffffffull) return fail(NLS_ERR_INVALID, "SANN: n_chains and dim must fit 32 bits");
+  if (x0_count != 1 && x0_count != c->n_chains) return fail(NLS_ERR_INVALID, "SANN: x0_count must be 1 or n_chains");
+  if (!(c->temperature_max > 0.0)) return fail(NLS_ERR_INVALID, "SANN: temperature_max must be > 0");
+  if (c->temperature_iter > 1 && c->max_iter > (1ull << 62) / (c->temperature_iter - 1))
+    return fail(NLS_ERR_INVALID, "SANN: max_iter * (temperature_iter - 1) overflows");
+  return NLS_OK;
+}
+
+int nls_sann_destroy(nls_sann *sa) {
+  if (!sa) return NLS_OK;
+  cudaSetDevice(sa->ctx->device);
+  cudaStreamSynchronize(sa->ctx->stream);
+  sa->mem.release();
+  delete sa;
+  return NLS_OK;
+}
+
+// temperature of outer iteration k exactly as the reference evaluates it (nlsolver.h:2792-2793), in scalar_t
+static double sann_temperature(int dtype, double tmax, u64 iter) {
+  if (dtype == NLS_F64) return tmax / std::log(static_cast<double>(iter) + 1.7182818);
+  const float e_minus_1 = static_cast<float>(1.7182818);
+  return static_cast<double>(static_cast<float>(tmax) / std::log(static_cast<float>(iter) + e_minus_1));
+}
+
+static int sann_build(nls_ctx *ctx, const nls_sann_cfg *cfg, const void *x0_host, u64 x0_count, nls_sann *sa) {
+  const u64 C = cfg->n_chains, d = cfg->dim;
+  sa->ctx = ctx;
+  sa->mem.ctx = ctx;
+  sa->cfg = *cfg;
+  sa->elem = elem_size(cfg->dtype);
+  sa->steps_done = 0;
+  sa->ops = cfg->dtype == NLS_F64 ? sann_ops_f64() : sann_ops_f32();
+  if (const ObjectivePlugin *pl = plugin_for(cfg->objective)) sa->ops = cfg->dtype == NLS_F64 ? pl->sann_f64 : pl->sann_f32;
+  sa->g = make_geom(ctx, C);
+  SANNState &s = sa->s;
+  std::memset(&s, 0, sizeof(s));
+  s.C = C; s.d = d; s.stride = round_up(d, 32 / sa->elem);
+  s.seed = cfg->seed; s.offset = cfg->chain_offset;
+  s.inner = cfg->temperature_iter > 1 ? cfg->temperature_iter - 1 : 0;
+  s.total_steps = cfg->max_iter * s.inner;
+  s.tmax = cfg->temperature_max;
+  // scale = 1.0 / temperature_max, a double division rounded to scalar_t (nlsolver.h:2782)
+  s.scale = cfg->dtype == NLS_F64 ? 1.0 / cfg->temperature_max
+                                  : static_cast<double>(static_cast<float>(1.0 / static_cast<double>(static_cast<float>(cfg->temperature_max))));
+  s.fm = cfg->minimize ? 1.0 : -1.0;
+  s.objective = plugin_for(cfg->objective) ? 100 /* OBJ_CUSTOM */ : cfg->objective;
+  const size_t row_bytes = size_t(C) * s.stride * sa->elem;
+  int rc;
+#define NLS_ALLOC(ptr, bytes) if ((rc = sa->mem.alloc(reinterpret_cast<void **>(&(ptr)), (bytes))) != NLS_OK) return rc
+  for (int k = 0; k < 3; k++) NLS_ALLOC(s.buf[k], row_bytes);
+  NLS_ALLOC(s.role, C);
+  NLS_ALLOC(s.best, C * sa->elem);
+  NLS_ALLOC(s.n_acc, C * sizeof(uint32_t));
+  NLS_ALLOC(s.n_imp, C * sizeof(uint32_t));
+  NLS_ALLOC(s.ctrl, sizeof(SANNCtrl));
+  NLS_ALLOC(sa->dense, size_t(C) * d * sa->elem);
+  const u64 tn = std::min<u64>(std::max<u64>(cfg->max_iter, 1), 1u << 16);
+  std::vector<double> table(tn);
+  for (u64 k = 0; k < tn; k++)
+    table[k] = sann_temperature(cfg->dtype, cfg->temperature_max, k);
+  double *tab = nullptr;
+  NLS_ALLOC(tab, tn * sizeof(double));
+  s.t_table = tab; s.t_n = tn;
+  void *x0_dev = nullptr;
+  NLS_ALLOC(x0_dev, size_t(x0_count) * d * sa->elem);
+#undef NLS_ALLOC
+  cudaStream_t st = ctx->stream;
+  NLS_CUDA(cudaMemcpyAsync(tab, table.data(), tn * sizeof(double), cudaMemcpyHostToDevice, st));
+  NLS_CUDA(cudaMemcpyAsync(x0_dev, x0_host, size_t(x0_count) * d * sa->elem, cudaMemcpyHostToDevice, st));
+  NLS_CUDA(cudaMemsetAsync(s.ctrl, 0, sizeof(SANNCtrl), st));
+  NLS_CUDA(sa->ops->init(s, x0_dev, x0_count, sa->g, st));
+  NLS_CUDA(cudaStreamSynchronize(st));               // table / x0 are host temporaries
+  return NLS_OK;
+}
+
+int nls_sann_create(nls_ctx *ctx, const nls_sann_cfg *cfg, const void *x0_host, uint64_t x0_count, nls_sann **out) {
+  if (!ctx || !cfg || !x0_host || !out) return fail(NLS_ERR_INVALID, "nls_sann_create: NULL argument");
+  *out = nullptr;
+  int rc = sann_validate(cfg, x0_count);
+  if (rc != NLS_OK) return rc;
+  NLS_CUDA(cudaSetDevice(ctx->device));
+  nls_sann *sa = new nls_sann();
+  rc = sann_build(ctx, cfg, x0_host, x0_count, sa);
+  if (rc != NLS_OK) { sa->mem.release(); delete sa; return rc; }
+  *out = sa;
+  return NLS_OK;
+}
+
+int nls_sann_step(nls_sann *sa, uint64_t n_candidates) {
+  if (!sa) return fail(NLS_ERR_INVALID, "nls_sann_step: NULL handle");
+  NLS_CUDA(cudaSetDevice(sa->ctx->device));
+  const u64 left = sa->s.total_steps - sa->steps_done;
+  u64 n = std::min<u64>(n_candidates, left);
+  // one launch carries every chain through its candidates; bound a launch to ~2^31 coordinate updates (a few tens of
+  // milliseconds of device time) so that large batches stay responsive to sync / destroy
+  const u64 per_step = std::max<u64>(sa->s.C * sa->s.d, 1);
+  const u64 chunk = std::max<u64>((1ull << 31) / per_step, 1);
+  while (n > 0) {
+    const u64 k = std::min(n, chunk);
+    NLS_CUDA(sa->ops->steps(sa->s, sa->steps_done, k, sa->g, sa->ctx->stream));
+    sa->steps_done += k;
+    n -= k;
+  }
+  return NLS_OK;
+}
+
+int nls_sann_sync(nls_sann *sa, nls_status *status) {
+  if (!sa) return fail(NLS_ERR_INVALID, "nls_sann_sync: NULL handle");
+  NLS_CUDA(cudaSetDevice(sa->ctx->device));
+  cudaStream_t st = sa->ctx->stream;
+  SANNCtrl c;
+  if (status) {
+    NLS_CUDA(sa->ops->best(sa->s, st));
+    NLS_CUDA(cudaMemcpyAsync(&c, sa->s.ctrl, sizeof(c), cudaMemcpyDeviceToHost, st));
+  }
+  NLS_CUDA(cudaStreamSynchronize(st));
+  if (status) {
+    std::memset(status, 0, sizeof(*status));
+    const bool done = sa->steps_done >= sa->s.total_steps;
+    status->f_value = c.best_value;
+    status->iterations = done ? sa->cfg.max_iter : sa->steps_done / sa->s.inner;
+    status->function_calls = sa->s.C * (1 + sa->steps_done);
+    status->best_index = sa->s.offset + c.best_chain;
+    status->stopped = done ? 1 : 0;
+    status->stop_reason = done ? 1 : 0;
+    status->best_valid = c.best_valid;
+  }
+  return NLS_OK;
+}
+
+static int sann_read_rows(nls_sann *sa, int which, u64 first, u64 count, void *host) {
+  cudaStream_t st = sa->ctx->stream;
+  NLS_CUDA(sa->ops->gather(sa->s, which, sa->dense, sa->g, st));
+  const size_t row = sa->s.d * sa->elem;
+  NLS_CUDA(cudaMemcpyAsync(host, static_cast<const char *>(sa->dense) + first * row, count * row, cudaMemcpyDeviceToHost, st));
+  NLS_CUDA(cudaStreamSynchronize(st));
+  return NLS_OK;
+}
+
+int nls_sann_read_best(nls_sann *sa, void *x_host) {
+  if (!sa || !x_host) return fail(NLS_ERR_INVALID, "nls_sann_read_best: NULL argument");
+  NLS_CUDA(cudaSetDevice(sa->ctx->device));
+  cudaStream_t st = sa->ctx->stream;
+  SANNCtrl c;
+  NLS_CUDA(sa->ops->best(sa->s, st));
+  NLS_CUDA(cudaMemcpyAsync(&c, sa->s.ctrl, sizeof(c), cudaMemcpyDeviceToHost, st));
+  NLS_CUDA(cudaStreamSynchronize(st));
+  return sann_read_rows(sa, 0, c.best_chain, 1, x_host);
+}
+
+int nls_sann_read_chains(nls_sann *sa, void *x_best_host, void *f_best_host, void *p_cur_host, uint32_t *n_accepted,
+                         uint32_t *n_improved) {
+  if (!sa) return fail(NLS_ERR_INVALID, "nls_sann_read_chains: NULL handle");
+  NLS_CUDA(cudaSetDevice(sa->ctx->device));
+  cudaStream_t st = sa->ctx->stream;
+  const u64 C = sa->s.C;
+  int rc;
+  if (x_best_host && (rc = sann_read_rows(sa, 0, 0, C, x_best_host)) != NLS_OK) return rc;
+  if (p_cur_host && (rc = sann_read_rows(sa, 1, 0, C, p_cur_host)) != NLS_OK) return rc;
+  if (f_best_host) NLS_CUDA(cudaMemcpyAsync(f_best_host, sa->s.best, C * sa->elem, cudaMemcpyDeviceToHost, st));
+  if (n_accepted) NLS_CUDA(cudaMemcpyAsync(n_accepted, sa->s.n_acc, C * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+  if (n_improved) NLS_CUDA(cudaMemcpyAsync(n_improved, sa->s.n_imp, C * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+  NLS_CUDA(cudaStreamSynchronize(st));
+  return NLS_OK;
+}
+
+int nls_sann_solve(nls_ctx *ctx, const nls_sann_cfg *cfg, const void *x0_host, uint64_t x0_count, void *x_best_host,
+                   nls_status *status) {
+  if (!x_best_host) return fail(NLS_ERR_INVALID, "nls_sann_solve: x_best_host is NULL");
+  nls_sann *sa = nullptr;
+  int rc = nls_sann_create(ctx, cfg, x0_host, x0_count, &sa);
+  if (rc != NLS_OK) return rc;
+  rc = nls_sann_step(sa, ~0ull);
+  nls_status st;
+  if (rc == NLS_OK) rc = nls_sann_sync(sa, &st);
+  if (rc == NLS_OK) rc = nls_sann_read_best(sa, x_best_host);
+  if (rc == NLS_OK && status) *status = st;
+  nls_sann_destroy(sa);
+  return rc;
+}
+
 /* ================================================================ objective plugins =========================== */
 
 int nls_load_objective(const char *plugin_path, int32_t *objective_id) {
@@ -864,7 +1069,7 @@ int nls_load_objective(const char *plugin_path, int32_t *objective_id) {
   entry_t entry = reinterpret_cast<entry_t>(dlsym(h, "nls_objective_plugin_v1"));
   if (!entry) { dlclose(h); return fail(NLS_ERR_INVALID, "nls_load_objective: %s exports no nls_objective_plugin_v1", plugin_path); }
   const ObjectivePlugin *pl = entry();
-  if (!pl || pl->abi != 2 || !pl->de_f64 || !pl->de_f32 || !pl->pso_f64 || !pl->pso_f32) {
+  if (!pl || pl->abi != 3 || !pl->de_f64 || !pl->de_f32 || !pl->pso_f64 || !pl->pso_f32 || !pl->sann_f64 || !pl->sann_f32) {
     dlclose(h);
     return fail(NLS_ERR_INVALID, "nls_load_objective: plugin ABI mismatch (rebuild it against this library's headers)");
   }

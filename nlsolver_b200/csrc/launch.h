@@ -25,6 +25,19 @@ struct PSOOps {
                                    cudaStream_t st);
   cudaError_t (*gather_apply)(const PSOState &s, const XchgWindow &w, int initial, cudaStream_t st);
 };
+struct SANNOps {
+  // x0: device, x0_count rows of d elements (1 = shared start)
+  cudaError_t (*init)(const SANNState &s, const void *x0_dev, unsigned long long x0_count, const LaunchGeom &g,
+                      cudaStream_t st);
+  // candidates step_begin + 1 .. step_begin + n_steps of every chain
+  cudaError_t (*steps)(const SANNState &s, unsigned long long step_begin, unsigned long long n_steps,
+                       const LaunchGeom &g, cudaStream_t st);
+  // which: 0 best points x, 1 current points p -> dense [C][d]
+  cudaError_t (*gather)(const SANNState &s, int which, void *out, const LaunchGeom &g, cudaStream_t st);
+  cudaError_t (*best)(const SANNState &s, cudaStream_t st);
+};
+const SANNOps *sann_ops_f64();
+const SANNOps *sann_ops_f32();
 const DEOps *de_ops_f64();
 const DEOps *de_ops_f32();
 const PSOOps *pso_ops_f64();

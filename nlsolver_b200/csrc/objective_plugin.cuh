@@ -22,19 +22,21 @@
 //       static __device__ T full(const T (&x)[2]) { ... return f; }
 //     };
 //
-// The kernels (donor selection, crossover, repair, reductions, PSO moves) are the engine's own templates instantiated
+// The kernels (donor selection, crossover, repair, reductions, PSO moves, annealing chains) are the engine's own templates instantiated
 // for the functor; the sum runs in the canonical lane order (objectives.cuh), so results are reproducible.
 #pragma once
 #define NLS_PLUGIN_BUILD 1
 #include "de_impl.cuh"
 #include "pso_impl.cuh"
+#include "sann_impl.cuh"
 
-#define NLS_PLUGIN_ABI 2
+#define NLS_PLUGIN_ABI 3
 struct nls_objective_plugin {
   int abi;
   unsigned full_dim;   // 0: separable / pairwise sum of any dimension; D > 0: closed form, the solver's dim must be D
   const nls::DEOps *de_f64, *de_f32;
   const nls::PSOOps *pso_f64, *pso_f32;
+  const nls::SANNOps *sann_f64, *sann_f32;
 };
 
 #define NLS_EXPORT_OBJECTIVE(NAME)                                                                       \
@@ -44,10 +46,13 @@ struct nls_objective_plugin {
   NLS_DEFINE_DE_OPS(float, plugin_de_f32)                                                                \
   NLS_DEFINE_PSO_OPS(double, plugin_pso_f64)                                                             \
   NLS_DEFINE_PSO_OPS(float, plugin_pso_f32)                                                              \
+  NLS_DEFINE_SANN_OPS(double, plugin_sann_f64)                                                           \
+  NLS_DEFINE_SANN_OPS(float, plugin_sann_f32)                                                            \
   }                                                                                                      \
   extern "C" __attribute__((visibility("default"))) const nls_objective_plugin *nls_objective_plugin_v1() { \
     static const nls_objective_plugin p = {NLS_PLUGIN_ABI, nls::plugin_full_dim<NAME<double>>::value,    \
                                            nls::plugin_de_f64(), nls::plugin_de_f32(),                   \
-                                           nls::plugin_pso_f64(), nls::plugin_pso_f32()};                \
+                                           nls::plugin_pso_f64(), nls::plugin_pso_f32(),                 \
+                                           nls::plugin_sann_f64(), nls::plugin_sann_f32()};              \
     return &p;                                                                                           \
   }

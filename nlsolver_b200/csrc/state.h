@@ -88,6 +88,33 @@ struct XchgWindow {
   unsigned long long record_bytes;
 };
 
+// A batch of independent simulated-annealing chains (SANN::solve, nlsolver.h:2778-2815, once per chain).  Each chain
+// owns one row in each of three buffers; two of them hold its current point p and its best point x (the same buffer
+// right after an improvement), the remaining one receives the next candidate — accepting a candidate is a role swap,
+// never a copy.
+struct SANNCtrl {
+  double best_value;
+  unsigned long long best_chain;   // local index of the best chain (lowest value, lowest index on ties)
+  int best_valid, _pad;
+};
+struct SANNState {
+  void *buf[3];            // [C][stride] each
+  uint8_t *role;           // [C] bits 0-1: buffer of p, bits 2-3: buffer of x, bit 4: the last step consumed its Metropolis draw
+  void *best;              // [C] best_val
+  uint32_t *n_acc, *n_imp; // [C] accepted candidates / improvements of the best so far
+  SANNCtrl *ctrl;
+  unsigned long long C, d, stride;
+  unsigned long long seed, offset;
+  unsigned long long inner;       // temperature_iter - 1: candidates per temperature
+  unsigned long long total_steps; // max_iter * inner
+  // temperature of outer iteration k, temperature_max / log(k + 1.7182818) (nlsolver.h:2792-2793), tabulated on the host
+  // with the reference's own libm call in the reference's precision
+  const double *t_table;
+  unsigned long long t_n;
+  double tmax, scale, fm;
+  int objective, _pad;
+};
+
 struct LaunchGeom {
   int sm_count;
   int reduce_blocks;   // grid of the reduction kernels (= number of partials)

@@ -10,6 +10,9 @@ What shards:
     generation the island bests are all-gathered (global status), and every `migrate_every` generations the `migrants`
     best rows travel around the ring rank -> rank + 1 and overwrite the receiver's worst rows.
 
+  * SANN chains never interact: a batch splits into contiguous slices of GLOBAL chain ids with no collective in the
+    loop at all; the batch result (best value, global chain id, its point) is one all-gather of records at the end.
+
 The pure functions at the top (slices, ring, record select) are the host logic the world_size-2 gloo tests cover; the
 compute behind `engine` is any object with the small interface used below (the CUDA handles on GPUs).
 """
@@ -231,6 +234,40 @@ class CudaPSOEngine:
         self.ctx.close()
 
 
+class CudaSANNEngine:
+    """The CUDA slice of a chain batch: nls_sann_* behind the interface ShardedSANN drives."""
+
+    def __init__(self, cfg, x0, device, stream):
+        import torch
+
+        from .solvers import Context, SANNChains
+        self.torch = torch
+        self.ctx = Context(device, stream.cuda_stream)
+        self.chains_h = SANNChains(self.ctx, cfg, x0)
+        self.device = f"cuda:{device}"
+        self.kernel_launches = 1
+
+    def tensor(self, n, dtype):
+        return self.torch.zeros(n, dtype=dtype, device=self.device)
+
+    def step(self, n):
+        self.chains_h.step(n)
+        self.kernel_launches += 1
+
+    def sync(self):
+        return self.chains_h.sync()
+
+    def best(self):
+        return self.chains_h.best()
+
+    def chains(self):
+        return self.chains_h.chains()
+
+    def close(self):
+        self.chains_h.close()
+        self.ctx.close()
+
+
 class _NullStream:
     def __enter__(self):
         return self
@@ -383,6 +420,82 @@ class IslandDE:
         dt = np.float64 if self.cfg.dtype == 1 else np.float32
         raw = self.all.cpu().numpy()[r * self.rb + HEADER_BYTES:(r + 1) * self.rb]
         return raw.view(dt)[:self.cfg.dim].copy()
+
+    def close(self):
+        self.engine.close()
+
+
+# ------------------------------------------------------------------ sharded SANN chains ---------------------------
+class ShardedSANN:
+    """A batch of `cfg.n_chains` annealing chains split across the ranks of `group`: rank r owns the contiguous slice
+    of global chain ids slice_bounds gives it (draw streams are keyed by the global id, so the batch is the same for
+    any world size).  Nothing is exchanged while the chains run."""
+
+    def __init__(self, cfg, x0, device=0, group=None, stream=None, engine_factory=None):
+        import torch
+
+        from . import _lib as L
+        from .solvers import sann_cfg
+        self.torch = torch
+        self.comm = _Comm(group)
+        self.n_global = cfg.n_chains
+        begin, end = slice_bounds(cfg.n_chains, self.comm.world, self.comm.rank)
+        self.begin, self.end = begin, end
+        local = sann_cfg(cfg.dtype, cfg.objective, bool(cfg.minimize), end - begin, cfg.dim, cfg.max_iter,
+                         cfg.temperature_iter, cfg.temperature_max, cfg.seed, cfg.chain_offset + begin, cfg.flags)
+        self.cfg = local
+        x0 = np.asarray(x0)
+        x0_local = x0 if x0.ndim == 1 else x0[begin:end]
+        if engine_factory is None:
+            self.stream = stream or torch.cuda.Stream(device)
+            self._scope = lambda: torch.cuda.stream(self.stream)
+            self.engine = CudaSANNEngine(local, x0_local, device, self.stream)
+        else:
+            self.stream = _NullStream()
+            self._scope = lambda: self.stream
+            self.engine = engine_factory(local, x0_local)
+        self.elem = 8 if cfg.dtype == L.F64 else 4
+        self.rb = record_bytes(self.elem, cfg.dim)
+
+    @property
+    def launches(self):
+        return getattr(self.engine, "kernel_launches", 0)
+
+    def step(self, n=1):
+        """n candidates per chain on every rank (clamped to the end of the schedule)."""
+        with self._scope():
+            self.engine.step(n)
+
+    def run(self):
+        self.step(0xFFFFFFFFFFFFFFFF)
+
+    def sync(self):
+        """This rank's slice status (f_value / best_index: its best chain, global id)."""
+        return self.engine.sync()
+
+    def global_best(self):
+        """(status, point) of the best chain of the whole batch: lowest best_val, lowest global chain id on ties —
+        one all-gather of one record per rank."""
+        st = self.engine.sync()
+        row = self.engine.best()
+        rec = pack_record(st["f_value"], st["best_index"], (0.0, 0.0, 0.0), row, valid=bool(st["best_valid"]))
+        with self._scope():
+            mine = self.engine.tensor(self.rb, self.torch.uint8)
+            allr = self.engine.tensor(self.rb * self.comm.world, self.torch.uint8)
+            mine.copy_(self.torch.from_numpy(rec))
+            self.comm.all_gather(allr, mine)
+        self.stream.synchronize()
+        raw = allr.cpu().numpy()
+        heads = [parse_record(raw[r * self.rb:r * self.rb + HEADER_BYTES]) for r in range(self.comm.world)]
+        win = select_best(heads)   # ranks hold ascending chain ids: strict < in rank order = lowest id on ties
+        out = dict(st)
+        out["function_calls"] = self.n_global * (st["function_calls"] // max(self.end - self.begin, 1))
+        if win >= 0:
+            out["f_value"], out["best_index"] = heads[win]["value"], heads[win]["index"]
+            dt = np.float64 if self.elem == 8 else np.float32
+            row = raw[win * self.rb + HEADER_BYTES:(win + 1) * self.rb].view(dt)[:self.cfg.dim].copy()
+        out["best_rank"] = win
+        return out, row
 
     def close(self):
         self.engine.close()

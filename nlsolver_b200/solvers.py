@@ -1,7 +1,7 @@
 """Host-side mirror of the reference's solver interface for the DE / PSO population loop, over the C ABI.
 
 Names, argument order, defaults and behaviour follow nlsolver::DE (nlsolver.h:2379-2410), nlsolver::PSO
-(nlsolver.h:2498-2589) and nlsolver::solver_status (nlsolver.h:2054-2097): `minimize(x)` / `maximize(x)` overwrite
+(nlsolver.h:2498-2589), nlsolver::SANN (nlsolver.h:2744-2815) and nlsolver::solver_status (nlsolver.h:2054-2097): `minimize(x)` / `maximize(x)` overwrite
 `x` with the best point and return a `SolverStatus`.  The objective is one of the device functors (`Sphere`,
 `Rosenbrock`, `Rastrigin`, `Ackley`, `RosenbrockExample`); the random generator is any callable returning floats in
 [0, 1] — two draws are taken from it per solve to seed the device draw tape, so it advances deterministically.
@@ -273,6 +273,58 @@ class PSOSwarm:
             pass
 
 
+class SANNChains:
+    """Stepwise handle (nls_sann_*): a batch of independent annealing chains resident in HBM."""
+
+    def __init__(self, ctx, cfg, x0):
+        self.ctx, self.cfg = ctx, cfg
+        self.dt = np_dtype(cfg.dtype)
+        x0 = np.ascontiguousarray(x0, dtype=self.dt)
+        count = 1 if x0.ndim == 1 else x0.shape[0]
+        assert x0.size == count * cfg.dim
+        self._h = C.c_void_p()
+        L.check(L.lib().nls_sann_create(ctx.handle, C.byref(cfg), x0.ctypes.data, count, C.byref(self._h)))
+        ctx._adopt(self)
+
+    def step(self, n=1):
+        """Enqueue n candidates per chain (clamped to what is left of max_iter * (temperature_iter - 1))."""
+        L.check(L.lib().nls_sann_step(self._h, n))
+
+    def run(self):
+        L.check(L.lib().nls_sann_step(self._h, 0xFFFFFFFFFFFFFFFF))
+
+    def sync(self):
+        st = L.Status()
+        L.check(L.lib().nls_sann_sync(self._h, C.byref(st)))
+        return st.as_dict()
+
+    def best(self):
+        x = np.zeros(self.cfg.dim, self.dt)
+        L.check(L.lib().nls_sann_read_best(self._h, x.ctypes.data))
+        return x
+
+    def chains(self):
+        """Per-chain results: x_best / p_cur [n_chains, dim], f_best, n_accepted, n_improved [n_chains]."""
+        n, d = self.cfg.n_chains, self.cfg.dim
+        a = {"x_best": np.zeros((n, d), self.dt), "f_best": np.zeros(n, self.dt), "p_cur": np.zeros((n, d), self.dt),
+             "n_accepted": np.zeros(n, np.uint32), "n_improved": np.zeros(n, np.uint32)}
+        L.check(L.lib().nls_sann_read_chains(self._h, a["x_best"].ctypes.data, a["f_best"].ctypes.data,
+                                             a["p_cur"].ctypes.data, a["n_accepted"].ctypes.data,
+                                             a["n_improved"].ctypes.data))
+        return a
+
+    def close(self):
+        if self._h:
+            L.lib().nls_sann_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class ExchangeWindow:
     """Peer-memory exchange window (nls_xchg_*): records and flags in this rank's HBM, mapped by every peer via IPC."""
 
@@ -320,6 +372,12 @@ def pso_cfg(dtype=L.F64, objective=L.SPHERE, pso_type=L.PSO_VANILLA, minimize=Tr
     return L.PSOCfg(dtype, objective, pso_type, int(minimize), n_particles, dim, inertia, cognitive_coef, social_coef,
                     eps, max_iter, best_val_no_change, int(constrained), flags, seed, particle_offset,
                     n_particles_global)
+
+
+def sann_cfg(dtype=L.F64, objective=L.SPHERE, minimize=True, n_chains=1, dim=2, max_iter=5000, temperature_iter=10,
+             temperature_max=10.0, seed=0, chain_offset=0, flags=0):
+    return L.SANNCfg(dtype, objective, int(minimize), flags, n_chains, dim, max_iter, temperature_iter,
+                     temperature_max, seed, chain_offset)
 
 
 class DE:
@@ -397,6 +455,72 @@ class PSO:
 
     def maximize(self, x, lower=None, upper=None):
         return self._solve(x, lower, upper, False)
+
+
+class SANN:
+    """nlsolver::SANN<Callable, RNG, scalar_t> (nlsolver.h:2744-2776): `minimize(x)` runs one chain from x.
+
+    `minimize_batch(xs)` / `maximize_batch(xs)` are the batch form this engine adds: one independent chain per row of
+    `xs` (or `n_chains` chains from one shared start), each the reference loop on its own draw stream."""
+
+    def __init__(self, f, generator, max_iter=5000, temperature_iter=10, temperature_max=10.0, scalar_t=np.float64,
+                 ctx=None):
+        self.f, self.generator = f, generator
+        self.max_iter, self.temperature_iter, self.temperature_max = max_iter, temperature_iter, temperature_max
+        self.scalar_t, self.ctx = scalar_t, ctx
+        self.f_evals = 0          # accumulates over calls, like the reference member (nlsolver.h:2751, 2783)
+
+    def _cfg(self, n_chains, dim, minimize):
+        return sann_cfg(nls_dtype(np.dtype(self.scalar_t)), self.f, minimize, n_chains, dim, self.max_iter,
+                        self.temperature_iter, self.temperature_max, seed_from_generator(self.generator))
+
+    def _solve(self, x, minimize, n_chains=1):
+        ctx = self.ctx or default_context()
+        dt = np.dtype(self.scalar_t)
+        cfg = self._cfg(n_chains, len(x), minimize)
+        x0 = np.ascontiguousarray(x, dtype=dt)
+        out = np.zeros(len(x), dt)
+        st = L.Status()
+        L.check(L.lib().nls_sann_solve(ctx.handle, C.byref(cfg), x0.ctypes.data, 1, out.ctypes.data, C.byref(st)))
+        x[:] = out.tolist() if isinstance(x, list) else out
+        self.f_evals += st.function_calls
+        return SolverStatus(dt.type(st.f_value), st.iterations, self.f_evals)
+
+    def minimize(self, x):
+        return self._solve(x, True)
+
+    def maximize(self, x):
+        return self._solve(x, False)
+
+    def minimize_multistart(self, x, n_chains):
+        """n_chains chains from the same start x; x receives the best chain's point."""
+        return self._solve(x, True, n_chains)
+
+    def maximize_multistart(self, x, n_chains):
+        return self._solve(x, False, n_chains)
+
+    def _batch(self, xs, n_chains, minimize):
+        ctx = self.ctx or default_context()
+        dt = np.dtype(self.scalar_t)
+        xs = np.ascontiguousarray(xs, dtype=dt)
+        n = xs.shape[0] if xs.ndim == 2 else int(n_chains)
+        chains = SANNChains(ctx, self._cfg(n, xs.shape[-1], minimize), xs)
+        try:
+            chains.run()
+            st = chains.sync()
+            res = chains.chains()
+        finally:
+            chains.close()
+        per_chain = st["function_calls"] // n
+        self.f_evals += st["function_calls"]
+        return res["x_best"], [SolverStatus(dt.type(f), st["iterations"], per_chain) for f in res["f_best"]]
+
+    def minimize_batch(self, xs, n_chains=None):
+        """xs: [n_chains, dim] start points, or [dim] with n_chains.  Returns (best points, list of SolverStatus)."""
+        return self._batch(xs, n_chains, True)
+
+    def maximize_batch(self, xs, n_chains=None):
+        return self._batch(xs, n_chains, False)
 
 
 DESolver, PSOSolver = DE, PSO   # the names README.md:80,99 uses

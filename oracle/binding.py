@@ -64,6 +64,18 @@ class PSOOut(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("x_best", "positions", "velocities", "pbest_values", "last_values")]
 
 
+class SANNCfg(C.Structure):
+    _fields_ = [("dtype", i32), ("objective", i32), ("minimize", i32), ("rng_mode", i32),
+                ("n_chains", u64), ("dim", u64), ("max_iter", u64), ("temperature_iter", u64),
+                ("temperature_max", f64), ("seed", u64), ("chain_offset", u64), ("xs_state", u64 * 2),
+                ("x0_count", u64), ("max_steps", u64)]
+
+
+class SANNOut(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in
+                ("x_best", "f_best", "p_cur", "n_accepted", "n_improved", "draws", "iterations", "function_calls")]
+
+
 def np_dtype(dtype):
     return np.float64 if dtype == F64 else np.float32
 
@@ -84,6 +96,9 @@ def _load(path, prefix, with_extras):
     de.argtypes = [C.POINTER(DECfg), C.c_void_p, C.POINTER(DEOut), C.POINTER(Status)]
     pso.argtypes = [C.POINTER(PSOCfg), C.c_void_p, C.c_void_p, C.POINTER(PSOOut), C.POINTER(Status)]
     de.restype = pso.restype = C.c_int
+    sann = getattr(lib, prefix + "sann_run")
+    sann.argtypes = [C.POINTER(SANNCfg), C.c_void_p, C.POINTER(SANNOut), C.POINTER(Status)]
+    sann.restype = C.c_int
     lib.oracle_objective.argtypes = [C.c_int, C.c_int, C.c_void_p, u64]
     lib.oracle_objective.restype = f64
     lib.oracle_tape_key.argtypes = [u64, u64, u64]
@@ -100,6 +115,7 @@ def _load(path, prefix, with_extras):
     if with_extras:
         lib.ref_de_time.argtypes = [C.POINTER(DECfg), C.c_void_p, C.POINTER(f64), C.POINTER(Status)]
         lib.ref_pso_time.argtypes = [C.POINTER(PSOCfg), C.c_void_p, C.POINTER(f64), C.POINTER(Status)]
+        lib.ref_sann_time.argtypes = [C.POINTER(SANNCfg), C.c_void_p, C.POINTER(f64), C.POINTER(Status)]
         lib.ref_objective_nd.argtypes = [C.c_int, C.c_void_p, u64]
         lib.ref_objective_nd.restype = f64
         lib.ref_objective_2d.argtypes = [C.c_int, f64, f64]
@@ -177,6 +193,32 @@ def pso_run(lib, cfg, lower, upper, prefix=None):
                                           C.byref(st))
     if rc != 0:
         raise RuntimeError(f"{prefix}pso_run failed: {rc}")
+    return st.as_dict(), a
+
+
+def sann_cfg(dtype=F64, objective=SPHERE, minimize=True, n_chains=1, dim=2, max_iter=5000, temperature_iter=10,
+             temperature_max=10.0, rng_mode=RNG_TAPE, seed=0, chain_offset=0, xs_state=(0, 0), x0_count=1,
+             max_steps=0):
+    return SANNCfg(dtype, objective, int(minimize), rng_mode, n_chains, dim, max_iter, temperature_iter,
+                   temperature_max, seed, chain_offset, (u64 * 2)(*xs_state), x0_count, max_steps)
+
+
+def sann_run(lib, cfg, x0, prefix=None):
+    """Run a batch of SANN chains; x0 is [dim] (shared start) or [n_chains, dim]. Returns (status, arrays)."""
+    prefix = prefix or ("ref_" if hasattr(lib, "ref_sann_run") else "oracle_")
+    dt = np_dtype(cfg.dtype)
+    n, d = cfg.n_chains, cfg.dim
+    x0 = np.ascontiguousarray(x0, dtype=dt)
+    cfg.x0_count = 1 if x0.ndim == 1 else n
+    assert x0.size == cfg.x0_count * d
+    a = {"x_best": np.zeros((n, d), dt), "f_best": np.zeros(n, dt), "p_cur": np.zeros((n, d), dt),
+         "n_accepted": np.zeros(n, np.uint32), "n_improved": np.zeros(n, np.uint32), "draws": np.zeros(n, np.uint64),
+         "iterations": np.zeros(n, np.uint64), "function_calls": np.zeros(n, np.uint64)}
+    out = SANNOut(**{k: v.ctypes.data for k, v in a.items()})
+    st = Status()
+    rc = getattr(lib, prefix + "sann_run")(C.byref(cfg), x0.ctypes.data, C.byref(out), C.byref(st))
+    if rc != 0:
+        raise RuntimeError(f"{prefix}sann_run failed: {rc}")
     return st.as_dict(), a
 
 

@@ -82,6 +82,30 @@ typedef struct {
   void *x_best, *positions, *velocities, *pbest_values, *last_values;
 } orc_pso_out;
 
+/* ---- SANN as a batch of independent chains (nlsolver.h:2744-2815 is one chain) ----
+ * Tape: chain c draws from stream (epoch e, global chain id); epoch e starts right after the chain's objective call
+ * number e (0 = the initial f(x)) and its draws are numbered from 0 in the order the reference makes them: the
+ * Metropolis draw of the step just evaluated (only if difference > 0), then the 2*d rnorm draws of the next step. */
+typedef struct {
+  int32_t dtype, objective, minimize, rng_mode;
+  uint64_t n_chains, dim;
+  uint64_t max_iter, temperature_iter;   /* reference defaults 5000, 10 */
+  double temperature_max;                /* 10.0 */
+  uint64_t seed, chain_offset;
+  uint64_t xs_state[2];   /* ORC_RNG_XORSHIFT: one generator shared by the chains, run one after the other */
+  uint64_t x0_count;      /* 1: every chain starts from the same x0[d]; n_chains: x0[n_chains*d] */
+  uint64_t max_steps;     /* restatement only: stop after this many inner steps (0 = run to max_iter) */
+} orc_sann_cfg;
+
+typedef struct {
+  void *x_best;                      /* [n_chains*d] best points (the reference's x on return) */
+  void *f_best;                      /* [n_chains] best_val */
+  void *p_cur;                       /* [n_chains*d] current points p (restatement only) */
+  uint32_t *n_accepted, *n_improved; /* [n_chains] (restatement only) */
+  uint64_t *draws;                   /* [n_chains] generator() calls made by the chain */
+  uint64_t *iterations, *function_calls; /* [n_chains] as solver_status reports them */
+} orc_sann_out;
+
 #ifdef __cplusplus
 }
 #endif

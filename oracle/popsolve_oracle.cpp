@@ -513,6 +513,90 @@ void pso_run(const orc_pso_cfg &c, const T *lower, const T *upper, Src &src, con
   src = loop.src;
 }
 
+/* ---------------------------------------------------------------- SANN ----------------------------------- */
+/* One chain of SANN::solve (nlsolver.h:2778-2815).  `src.begin(e, chain)` opens epoch e (see oracle_abi.h); with the
+ * sequential xorshift source it is a no-op.  For T = float the reference's unqualified exp() is the double overload
+ * and the comparison with the float draw runs in double, as do `difference <= 0.0` and `1.0 / temperature_max`. */
+template <class T, class Src>
+void sann_chain(const orc_sann_cfg &c, u64 chain, const T *x0, Src &src, T *x, T *p_out, T *f_best,
+                uint32_t *n_acc_out, uint32_t *n_imp_out, u64 *iters_out, u64 *evals_out) {
+  const size_t d = c.dim;
+  const T fm = c.minimize ? static_cast<T>(1.0) : static_cast<T>(-1.0);
+  const T e_minus_1 = static_cast<T>(1.7182818), tmax = static_cast<T>(c.temperature_max);
+  std::vector<T> best(x0, x0 + d), p = best, ptry = best;
+  T best_val = fm * objective<T>(c.objective, best.data(), d);          /* :2781 */
+  u64 evals = 1, steps = 0, iter = 0;
+  uint32_t n_acc = 0, n_imp = 0;
+  src.begin(0, chain);
+  const T scale = static_cast<T>(1.0 / tmax);                           /* :2782 */
+  bool cut = false;
+  while (iter < c.max_iter && !cut) {                                   /* :2786-2790 */
+    const T t = tmax / std::log(static_cast<T>(iter) + e_minus_1);      /* :2792-2793 */
+    for (size_t j = 1; j < c.temperature_iter; j++) {                   /* :2794 */
+      if (c.max_steps && steps >= c.max_steps) { cut = true; break; }
+      const T current_scale = t * scale;
+      for (size_t i = 0; i < d; i++) {                                  /* :2797-2800 */
+        const T u_log = unit<T>(src.next()), u_cos = unit<T>(src.next());
+        ptry[i] = p[i] + current_scale * rnorm<T>(u_log, u_cos);
+      }
+      const T current_val = fm * objective<T>(c.objective, ptry.data(), d);
+      evals++; steps++;
+      src.begin(evals - 1, chain);
+      const T difference = current_val - best_val;                      /* NB: against best_val, not f(p) */
+      bool accept = difference <= 0.0;                                  /* :2804, short-circuit: no draw if true */
+      if (!accept) accept = static_cast<double>(unit<T>(src.next())) < std::exp(static_cast<double>(-difference / t));
+      if (accept) {
+        p = ptry; n_acc++;
+        if (current_val <= best_val) { best = p; best_val = current_val; n_imp++; }
+      }
+    }
+    if (!cut) iter++;
+  }
+  if (x) std::memcpy(x, best.data(), d * sizeof(T));
+  if (p_out) std::memcpy(p_out, p.data(), d * sizeof(T));
+  *f_best = best_val; *n_acc_out = n_acc; *n_imp_out = n_imp; *iters_out = iter; *evals_out = evals;
+}
+
+template <class T>
+int sann_dispatch(const orc_sann_cfg *c, const void *x0v, const orc_sann_out *out, orc_status *st) {
+  if (c->n_chains < 1 || c->dim < 1 || (c->x0_count != 1 && c->x0_count != c->n_chains)) return -1;
+  const T *x0 = static_cast<const T *>(x0v);
+  const size_t d = c->dim;
+  SeqSource seq(c->xs_state);
+  T best_f = 0; u64 best_chain = 0, iters = 0, evals_total = 0, draws_total = 0;
+  std::vector<T> xb(d), pc(d);
+  for (u64 ch = 0; ch < c->n_chains; ch++) {
+    const T *start = x0 + (c->x0_count == 1 ? 0 : ch * d);
+    T f; uint32_t na, ni; u64 it, ev, draws;
+    if (c->rng_mode == ORC_RNG_TAPE) {
+      TapeSource src(c->seed, c->chain_offset);
+      sann_chain<T>(*c, ch, start, src, xb.data(), pc.data(), &f, &na, &ni, &it, &ev);
+      draws = src.total;
+    } else {
+      const u64 before = seq.total;
+      sann_chain<T>(*c, ch, start, seq, xb.data(), pc.data(), &f, &na, &ni, &it, &ev);
+      draws = seq.total - before;
+    }
+    if (ch == 0 || f < best_f) { best_f = f; best_chain = ch; }
+    iters = it; evals_total += ev; draws_total += draws;
+    if (!out) continue;
+    if (out->x_best) std::memcpy(static_cast<T *>(out->x_best) + ch * d, xb.data(), d * sizeof(T));
+    if (out->p_cur) std::memcpy(static_cast<T *>(out->p_cur) + ch * d, pc.data(), d * sizeof(T));
+    if (out->f_best) static_cast<T *>(out->f_best)[ch] = f;
+    if (out->n_accepted) out->n_accepted[ch] = na;
+    if (out->n_improved) out->n_improved[ch] = ni;
+    if (out->draws) out->draws[ch] = draws;
+    if (out->iterations) out->iterations[ch] = it;
+    if (out->function_calls) out->function_calls[ch] = ev;
+  }
+  if (st) {
+    std::memset(st, 0, sizeof(*st));
+    st->f_value = best_f; st->iterations = iters; st->function_calls = evals_total; st->best_index = best_chain;
+    st->draws_consumed = draws_total; st->best_valid = 1; st->stop_reason = 1;
+  }
+  return 0;
+}
+
 template <class T>
 int de_dispatch(const orc_de_cfg *c, const void *x0, const orc_de_out *out, orc_status *st) {
   if (c->pop_size < 4 || c->dim < 1) return -1;     /* the reference loops forever for pop < 4 (:2344-2354) */
@@ -540,6 +624,10 @@ int oracle_pso_run(const orc_pso_cfg *c, const void *lower, const void *upper, c
                    orc_status *st) {
   return c->dtype == ORC_F64 ? pso_dispatch<double>(c, lower, upper, out, st)
                              : pso_dispatch<float>(c, lower, upper, out, st);
+}
+/* a batch of SANN chains; the batch status reports the best chain (lowest value, lowest chain index on ties) */
+int oracle_sann_run(const orc_sann_cfg *c, const void *x0, const orc_sann_out *out, orc_status *st) {
+  return c->dtype == ORC_F64 ? sann_dispatch<double>(c, x0, out, st) : sann_dispatch<float>(c, x0, out, st);
 }
 /* PSO::minimize(x) without bounds derives lower = -|x|, upper = |x| (nlsolver.h:2553-2563); callers do that. */
 

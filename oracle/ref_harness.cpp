@@ -265,6 +265,100 @@ int pso_run(const orc_pso_cfg *c, const void *lower, const void *upper, const or
   return 0;
 }
 
+/* ------------------------------------------------------------------ SANN probe --------------------------- */
+/* nlsolver::SANN (nlsolver.h:2744-2815) is one chain; a batch is that solver run once per chain.  The tape opens a new
+ * epoch at every objective call (oracle_abi.h), which needs no knowledge of whether the Metropolis draw happened. */
+template <class T>
+struct SANNProbe {
+  const orc_sann_cfg &c;
+  u64 chain = 0, calls = 0, k = 0, total = 0;
+  explicit SANNProbe(const orc_sann_cfg &cfg) : c(cfg) {}
+  T draw() {
+    total++;
+    return to_unit<T>(oracle_tape_draw(oracle_tape_key(c.seed, calls - 1, c.chain_offset + chain), k++));
+  }
+  void evaluated() { calls++; k = 0; }
+};
+template <class T> struct SANNTapeRNG { SANNProbe<T> &p; T operator()() { return p.draw(); } };
+template <class T> struct SANNHook {
+  SANNProbe<T> &p;
+  T operator()(std::vector<T> &x) {
+    const T v = static_cast<T>(oracle_objective(dtype_of<T>(), p.c.objective, x.data(), x.size()));
+    p.evaluated();
+    return v;
+  }
+};
+
+template <class T>
+int sann_run(const orc_sann_cfg *c, const void *x0v, const orc_sann_out *out, orc_status *st) {
+  if (c->n_chains < 1 || c->dim < 1 || (c->x0_count != 1 && c->x0_count != c->n_chains)) return -1;
+  if (c->max_steps) return -3;   /* the reference cannot stop inside a solve */
+  const size_t d = c->dim;
+  const T *x0 = static_cast<const T *>(x0v);
+  const bool tape = c->rng_mode == ORC_RNG_TAPE;
+  nlsolver::rng::xorshift<T> seq;
+  if (c->xs_state[0] | c->xs_state[1]) seq.set_state(c->xs_state[0], c->xs_state[1]);
+  T best_f = 0; u64 best_chain = 0, evals_total = 0, draws_total = 0, iters = 0;
+  for (u64 ch = 0; ch < c->n_chains; ch++) {
+    const T *start = x0 + (c->x0_count == 1 ? 0 : ch * d);
+    std::vector<T> x(start, start + d);
+    SANNProbe<T> probe(*c);
+    probe.chain = ch;
+    SANNHook<T> hook{probe};
+    auto status = [&]() {
+      if (tape) {
+        SANNTapeRNG<T> g{probe};
+        nlsolver::SANN<SANNHook<T>, SANNTapeRNG<T>, T> s(hook, g, c->max_iter, c->temperature_iter,
+                                                        static_cast<T>(c->temperature_max));
+        return c->minimize ? s.minimize(x) : s.maximize(x);
+      }
+      nlsolver::SANN<SANNHook<T>, nlsolver::rng::xorshift<T>, T> s(hook, seq, c->max_iter, c->temperature_iter,
+                                                                  static_cast<T>(c->temperature_max));
+      return c->minimize ? s.minimize(x) : s.maximize(x);
+    }();
+    const auto sum = status.get_summary();
+    const T f = std::get<2>(sum);
+    if (ch == 0 || f < best_f) { best_f = f; best_chain = ch; }
+    iters = std::get<1>(sum); evals_total += std::get<0>(sum); draws_total += probe.total;
+    if (!out) continue;
+    if (out->x_best) std::memcpy(static_cast<T *>(out->x_best) + ch * d, x.data(), d * sizeof(T));
+    if (out->f_best) static_cast<T *>(out->f_best)[ch] = f;
+    if (out->draws) out->draws[ch] = probe.total;
+    if (out->iterations) out->iterations[ch] = std::get<1>(sum);
+    if (out->function_calls) out->function_calls[ch] = std::get<0>(sum);
+  }
+  if (st) {
+    std::memset(st, 0, sizeof(*st));
+    st->f_value = best_f; st->iterations = iters; st->function_calls = evals_total; st->best_index = best_chain;
+    st->draws_consumed = draws_total; st->best_valid = 1; st->stop_reason = 1;
+  }
+  return 0;
+}
+
+/* the reference SANN, its own xorshift<T>, a plain N-D objective: n_chains solves one after the other */
+template <class T>
+int sann_time(const orc_sann_cfg *c, const void *x0v, double *seconds, orc_status *st) {
+  if (c->n_chains < 1 || c->dim < 1 || (c->x0_count != 1 && c->x0_count != c->n_chains)) return -1;
+  const size_t d = c->dim;
+  const T *x0 = static_cast<const T *>(x0v);
+  PlainObjective<T> f{c->objective};
+  nlsolver::rng::xorshift<T> g;
+  T best_f = 0; u64 best_chain = 0, evals_total = 0, iters = 0;
+  const auto t0 = std::chrono::steady_clock::now();
+  for (u64 ch = 0; ch < c->n_chains; ch++) {
+    const T *start = x0 + (c->x0_count == 1 ? 0 : ch * d);
+    std::vector<T> x(start, start + d);
+    nlsolver::SANN<PlainObjective<T>, nlsolver::rng::xorshift<T>, T> s(f, g, c->max_iter, c->temperature_iter,
+                                                                      static_cast<T>(c->temperature_max));
+    const auto sum = (c->minimize ? s.minimize(x) : s.maximize(x)).get_summary();
+    if (ch == 0 || std::get<2>(sum) < best_f) { best_f = std::get<2>(sum); best_chain = ch; }
+    iters = std::get<1>(sum); evals_total += std::get<0>(sum);
+  }
+  *seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  if (st) { std::memset(st, 0, sizeof(*st)); st->f_value = best_f; st->iterations = iters; st->function_calls = evals_total; st->best_index = best_chain; }
+  return 0;
+}
+
 /* ------------------------------------------------------------------ timing runs -------------------------- */
 template <class T>
 int de_time(const orc_de_cfg *c, const void *x0, double *seconds, orc_status *st) {
@@ -324,6 +418,12 @@ int ref_de_run(const orc_de_cfg *c, const void *x0, const orc_de_out *out, orc_s
 }
 int ref_pso_run(const orc_pso_cfg *c, const void *lower, const void *upper, const orc_pso_out *out, orc_status *st) {
   return c->dtype == ORC_F64 ? pso_run<double>(c, lower, upper, out, st) : pso_run<float>(c, lower, upper, out, st);
+}
+int ref_sann_run(const orc_sann_cfg *c, const void *x0, const orc_sann_out *out, orc_status *st) {
+  return c->dtype == ORC_F64 ? sann_run<double>(c, x0, out, st) : sann_run<float>(c, x0, out, st);
+}
+int ref_sann_time(const orc_sann_cfg *c, const void *x0, double *seconds, orc_status *st) {
+  return c->dtype == ORC_F64 ? sann_time<double>(c, x0, seconds, st) : sann_time<float>(c, x0, seconds, st);
 }
 /* the reference solver, its own xorshift<T>, a plain N-D objective, steady_clock around minimize() */
 int ref_de_time(const orc_de_cfg *c, const void *x0, double *seconds, orc_status *st) {

@@ -120,3 +120,47 @@ class OraclePSOEngine:
 
     def close(self):
         self.s.close()
+
+
+class OracleSANNEngine:
+    """A slice of a chain batch on the restatement: the chains are re-run from the start up to the candidates done so
+    far (cheap at test sizes), which is exactly what stepping means for chains that never interact."""
+
+    def __init__(self, cfg, x0):
+        self.cfg, self.x0 = cfg, np.asarray(x0, np.float64)
+        self.total = cfg.max_iter * max(cfg.temperature_iter - 1, 0)
+        self.done = 0
+
+    def tensor(self, n, dtype):
+        return torch.zeros(n, dtype=dtype)
+
+    def step(self, n):
+        self.done = min(self.done + n, self.total)
+
+    def _run(self):
+        c = self.cfg
+        kw = dict(dtype=c.dtype, objective=c.objective, minimize=bool(c.minimize), n_chains=c.n_chains, dim=c.dim,
+                  max_iter=c.max_iter, temperature_iter=c.temperature_iter, temperature_max=c.temperature_max,
+                  seed=c.seed, chain_offset=c.chain_offset)
+        if self.done == 0:
+            kw["max_iter"] = 0
+        elif self.done < self.total:
+            kw["max_steps"] = self.done
+        return B.sann_run(B.oracle(), B.sann_cfg(**kw), self.x0)
+
+    def sync(self):
+        so, ao = self._run()
+        inner = max(self.cfg.temperature_iter - 1, 1)
+        return {"f_value": so["f_value"], "best_index": self.cfg.chain_offset + so["best_index"], "best_valid": 1,
+                "iterations": self.cfg.max_iter if self.done >= self.total else self.done // inner,
+                "function_calls": self.cfg.n_chains * (1 + self.done), "stopped": int(self.done >= self.total)}
+
+    def best(self):
+        so, ao = self._run()
+        return ao["x_best"][so["best_index"]]
+
+    def chains(self):
+        return self._run()[1]
+
+    def close(self):
+        pass

@@ -27,6 +27,21 @@ PSO_GOLDEN = {
     "pso_accel_bounded_rastrigin_f64": (B.F64, B.RASTRIGIN, B.PSO_ACCELERATED, True, True, 40, 8, 40, 5.12, 24),
     "pso_accel_sphere_f32": (B.F32, B.SPHERE, B.PSO_ACCELERATED, True, False, 64, 16, 10, 10.24, 25),
 }
+SANN_GOLDEN = {
+    # name: (dtype, objective, minimize, n_chains, d, max_iter, temperature_iter, temperature_max, start, seed)
+    "sann_rosenbrock_ex_f64": (B.F64, B.ROSENBROCK_EX, True, 12, 2, 400, 10, 10.0, 5.0, 31),
+    "sann_rastrigin_f64": (B.F64, B.RASTRIGIN, True, 9, 37, 120, 6, 4.0, 2.5, 32),
+    "sann_ackley_max_f64": (B.F64, B.ACKLEY, False, 7, 11, 150, 10, 10.0, 1.0, 33),
+    "sann_sphere_f32": (B.F32, B.SPHERE, True, 10, 21, 150, 10, 10.0, 3.0, 34),
+}
+
+
+def sann_start(n_chains, d, start, dtype):
+    # one start point per chain: start * (1 + chain / 8) on even coordinates, -start on odd ones
+    x0 = np.empty((n_chains, d), dtype=B.np_dtype(dtype))
+    x0[:, 0::2] = (start * (1 + np.arange(n_chains) / 8.0))[:, None]
+    x0[:, 1::2] = -start
+    return x0
 
 
 def main():
@@ -53,7 +68,17 @@ def main():
                             upper=up, f_value=st["f_value"], iterations=st["iterations"],
                             function_calls=st["function_calls"], draws_consumed=st["draws_consumed"],
                             best_valid=st["best_valid"], **a)
-    print("wrote", len(DE_GOLDEN) + len(PSO_GOLDEN), "fixtures to", HERE)
+    for name, (dtype, obj, mini, n, d, it, ti, tmax, start, seed) in SANN_GOLDEN.items():
+        cfg = B.sann_cfg(dtype=dtype, objective=obj, minimize=mini, n_chains=n, dim=d, max_iter=it, temperature_iter=ti,
+                         temperature_max=tmax, seed=seed)
+        x0 = sann_start(n, d, start, dtype)
+        st, a = B.sann_run(ref, cfg, x0)
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), kind="sann",
+                            cfg=np.array([dtype, obj, int(mini), n, d, it, ti, seed], dtype=np.int64), tmax=tmax,
+                            x0=x0, f_value=st["f_value"], best_index=st["best_index"],
+                            function_calls_total=st["function_calls"], x_best=a["x_best"], f_best=a["f_best"],
+                            draws=a["draws"], iterations=a["iterations"], function_calls=a["function_calls"])
+    print("wrote", len(DE_GOLDEN) + len(PSO_GOLDEN) + len(SANN_GOLDEN), "fixtures to", HERE)
 
 
 if __name__ == "__main__":

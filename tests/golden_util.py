@@ -27,3 +27,11 @@ def load_pso(path):
     cfg = B.pso_cfg(dtype=dtype, objective=obj, pso_type=ptype, minimize=bool(mini), n_particles=P, dim=d, eps=0.0,
                     max_iter=G, best_val_no_change=1 << 40, constrained=bool(con), seed=seed)
     return cfg, z["upper"], z
+
+
+def load_sann(path):
+    z = np.load(path)
+    dtype, obj, mini, n, d, it, ti, seed = (int(v) for v in z["cfg"])
+    cfg = B.sann_cfg(dtype=dtype, objective=obj, minimize=bool(mini), n_chains=n, dim=d, max_iter=it,
+                     temperature_iter=ti, temperature_max=float(z["tmax"]), seed=seed)
+    return cfg, z["x0"], z

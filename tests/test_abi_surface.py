@@ -22,13 +22,14 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(handle, n), f"{n} declared in include/nls_b200.h but not exported"
     assert sorted(_lib.SYMBOLS) == names, "python binding table and header disagree"
-    assert handle.nls_version() == 100
+    assert handle.nls_version() == 101
 
 
 def test_struct_layouts_match_header_sizes():
     import ctypes as C
     from nlsolver_b200 import _lib
     assert C.sizeof(_lib.DECfg) == 96 and C.sizeof(_lib.PSOCfg) == 112 and C.sizeof(_lib.Status) == 88
+    assert C.sizeof(_lib.SANNCfg) == 72
     assert _lib.lib().nls_record_bytes(_lib.F64, 256) == 48 + 256 * 8
     assert _lib.lib().nls_record_bytes(_lib.F32, 3) == 48 + 16
 
@@ -47,7 +48,7 @@ def test_product_never_imports_the_oracle():
     """The oracle is test infrastructure: nothing under nlsolver_b200/ or include/ may import, include, link or
     dlopen anything under oracle/ (comments may cite it)."""
     bad = re.compile(r"(import\s+oracle|from\s+oracle|#include\s+[\"<][^\">]*oracle|liboracle|libnls_ref|oracle_abi|"
-                     r"oracle_de_run|oracle_pso_run|ref_de_run|ref_pso_run)")
+                     r"oracle_de_run|oracle_pso_run|oracle_sann_run|ref_de_run|ref_pso_run|ref_sann_run)")
     for top in ("nlsolver_b200", "include"):
         for dirpath, dirs, files in os.walk(os.path.join(ROOT, top)):
             dirs[:] = [d for d in dirs if d not in ("build", "__pycache__")]

@@ -17,7 +17,7 @@ import torch.multiprocessing as mp
 import nlsolver_b200 as nb
 from nlsolver_b200 import distributed as D
 from oracle import binding as B
-from tests.cpu_engines import OracleDEEngine, OraclePSOEngine, oracle_de_cfg
+from tests.cpu_engines import OracleDEEngine, OraclePSOEngine, OracleSANNEngine, oracle_de_cfg
 
 
 def free_port():
@@ -157,3 +157,32 @@ def test_islands_two_ranks_before_and_after_migration():
                 cfg = oracle_de_cfg(nb.de_cfg(**dict(DE_KW, agent_offset=rank * DE_KW["pop_size"], max_iter=gens)))
                 so, ao = B.de_run(B.oracle(), cfg, np.full(DE_KW["dim"], 4.096))
                 assert np.array_equal(out[rank][1], ao["rows"])
+
+
+# ------------------------------------------------------------------ sharded SANN chains ---------------------------
+SANN_KW = dict(objective=nb.RASTRIGIN, n_chains=11, dim=5, max_iter=30, temperature_iter=10, seed=21)
+
+
+def _sharded_sann(rank, world, kw, x0, first):
+    job = D.ShardedSANN(nb.sann_cfg(**kw), x0, engine_factory=OracleSANNEngine)
+    job.step(first)
+    mid = job.sync()
+    job.run()
+    st, row = job.global_best()
+    return mid, st, row, job.engine.chains(), (job.begin, job.end)
+
+
+@pytest.mark.parametrize("shared", [True, False])
+def test_sharded_sann_two_ranks_equals_one_batch(shared):
+    kw = SANN_KW
+    x0 = np.full(kw["dim"], 2.5) if shared else np.random.default_rng(3).uniform(-3, 3, size=(kw["n_chains"], kw["dim"]))
+    so, ao = B.sann_run(B.oracle(), B.sann_cfg(**kw), x0)
+    out = run_ranks(_sharded_sann, 2, kw, x0, 100)
+    whole_x, whole_f = np.zeros_like(ao["x_best"]), np.zeros_like(ao["f_best"])
+    for rank, (mid, st, row, chains, (b, e)) in out.items():
+        assert mid["function_calls"] == (e - b) * 101 and mid["iterations"] == 100 // 9 and not mid["stopped"]
+        assert (st["f_value"], st["best_index"]) == (so["f_value"], so["best_index"])      # same answer on every rank
+        assert st["function_calls"] == so["function_calls"] and st["iterations"] == kw["max_iter"]
+        assert np.array_equal(row, ao["x_best"][so["best_index"]])
+        whole_x[b:e], whole_f[b:e] = chains["x_best"], chains["f_best"]
+    assert np.array_equal(whole_x, ao["x_best"]) and np.array_equal(whole_f, ao["f_best"])

@@ -15,6 +15,32 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
+class Xoshiro:
+    """rng::xoshiro<double> (nlsolver.h:1289-1341) as a Python callable, quirks included (s[2] = s[3] = 0 after seeding,
+    rotation by 45)."""
+
+    def __init__(self):
+        m = (1 << 64) - 1
+        z = (12374563468 + 0x9E3779B97F4A7C15) & m
+        z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & m
+        z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & m
+        s0 = z ^ (z >> 31)
+        self.s = [s0, s0 >> 32, 0, 0]
+
+    def __call__(self):
+        m = (1 << 64) - 1
+        s = self.s
+        result = (s[0] + s[3]) & m
+        t = (s[1] << 17) & m
+        s[2] ^= s[0]
+        s[3] ^= s[1]
+        s[1] ^= s[2]
+        s[0] ^= s[3]
+        s[2] ^= t
+        s[3] = ((s[3] << 45) & m) | (s[3] >> 19)
+        return float(np.float64(result) / np.float64(2.0 ** 64))
+
+
 def parse(out):
     """-> list of (title, calls, iterations, f_value string, x strings) per printed solver block."""
     blocks = []
@@ -31,7 +57,7 @@ def test_example_program_matches_python_mirror(tmp_path):
                     "-lnls_b200", "-Wl,-rpath," + os.path.join(ROOT, "nlsolver_b200"), "-o", str(exe)], check=True)
     out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout
     blocks = parse(out)
-    assert len(blocks) >= 5, out
+    assert len(blocks) >= 7, out
     gen = XorShift()                      # example: DE-best with a fresh xorshift, x0 = {2, 7}
     x = [2.0, 7.0]
     st = nb.DE(nb.RosenbrockExample, gen, recombination=nb.RecombinationStrategy.best).minimize(x)
@@ -48,6 +74,18 @@ def test_example_program_matches_python_mirror(tmp_path):
     st = nb.PSO(nb.RosenbrockExample, gen).minimize(x)
     title, calls, iters, fval, xs = blocks[2]
     assert (calls, iters) == (st.function_calls_used, st.iteration) and fval == "%g" % st.f_value
+    gen = Xoshiro()                       # example.cpp:216-223: SANN with a fresh xoshiro, x0 = {5, 5}
+    x = [5.0, 5.0]
+    sann = nb.SANN(nb.RosenbrockExample, gen)
+    st = sann.minimize(x)
+    title, calls, iters, fval, xs = blocks[5]
+    assert "Annealing" in title and (calls, iters) == (st.function_calls_used, st.iteration) == (45001, 5000)
+    assert fval == "%g" % st.f_value and xs == "".join("%g," % v for v in x)
+    x = [5.0, 5.0]                        # 4096 chains on the same solver object: f_evals keeps accumulating
+    st = sann.minimize_multistart(x, 4096)
+    title, calls, iters, fval, xs = blocks[6]
+    assert (calls, iters) == (st.function_calls_used, st.iteration) == (4097 * 45001, 5000)
+    assert fval == "%g" % st.f_value and xs == "".join("%g," % v for v in x)
     # the big Rastrigin run at the end re-evaluates its result on the host with the header's own functor
     m = re.search(r"With final function value of ([^\n]+)\nhost re-evaluation of the returned point: ([^\n]+)", out)
     assert m and abs(float(m.group(1)) - float(m.group(2))) <= 1e-5 * abs(float(m.group(2)))

@@ -137,6 +137,36 @@ def test_pso_with_plugin_objective_matches_oracle(ctx, plugin_ids):
     sw.close()
 
 
+@pytest.mark.parametrize("name,d", [("StyblinskiTang", 9), ("Chain", 40)])
+def test_sann_chains_with_plugin_objective_match_oracle(ctx, plugin_ids, name, d):
+    install(name)
+    n, it = 12, 40
+    x0 = np.random.default_rng(d).uniform(-3, 3, size=(n, d))
+    ch = nb.SANNChains(ctx, nb.sann_cfg(objective=plugin_ids[name], n_chains=n, dim=d, max_iter=it, seed=17), x0)
+    ch.run()
+    st = ch.sync()
+    res = ch.chains()
+    ch.close()
+    so, ao = B.sann_run(B.oracle(), B.sann_cfg(objective=B.CUSTOM, n_chains=n, dim=d, max_iter=it, seed=17), x0)
+    assert np.array_equal(res["n_accepted"], ao["n_accepted"]) and np.array_equal(res["n_improved"], ao["n_improved"])
+    assert rel_close(res["f_best"], ao["f_best"], 1e-12) and rel_close(res["x_best"], ao["x_best"], 1e-12)
+    assert st["best_index"] == so["best_index"]
+
+
+def test_sann_chains_with_closed_form_plugin_match_oracle(ctx, plugin_ids):
+    B.set_custom_full(quad5)
+    n, it = 10, 60
+    x0 = np.random.default_rng(5).uniform(-3, 3, size=(n, 5))
+    ch = nb.SANNChains(ctx, nb.sann_cfg(objective=plugin_ids["Quad5"], n_chains=n, dim=5, max_iter=it, seed=23), x0)
+    ch.run()
+    ch.sync()
+    res = ch.chains()
+    ch.close()
+    so, ao = B.sann_run(B.oracle(), B.sann_cfg(objective=B.CUSTOM, n_chains=n, dim=5, max_iter=it, seed=23), x0)
+    assert np.array_equal(res["n_accepted"], ao["n_accepted"]) and rel_close(res["x_best"], ao["x_best"], 1e-12)
+    assert rel_close(res["f_best"], ao["f_best"], 1e-12)
+
+
 def test_plugin_objective_through_the_solver_mirror(plugin_ids):
     """DE(...).minimize with a plugin id as the Callable: converges to the known minimum x_j = -2.903534."""
     class Gen:

@@ -59,7 +59,7 @@ def test_c_abi_header_is_plain_c(tmp_path):
     """include/nls_b200.h must be consumable from C (cgo / FFI generators read it as C)."""
     src = tmp_path / "abi.c"
     src.write_text('#include "nls_b200.h"\n'
-                   'int main(void) { nls_de_cfg c; nls_pso_cfg p; nls_status s; (void)c; (void)p; (void)s;\n'
+                   'int main(void) { nls_de_cfg c; nls_pso_cfg p; nls_sann_cfg a; nls_status s; (void)c; (void)p; (void)a; (void)s;\n'
                    '  return nls_version() == NLS_B200_VERSION ? 0 : 1; }\n')
     exe = tmp_path / "abi"
     subprocess.run(["gcc", "-std=c11", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"),

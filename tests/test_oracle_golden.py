@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 
 from oracle import binding as B
-from tests.golden_util import golden_files, load_de, load_pso
+from tests.golden_util import golden_files, load_de, load_pso, load_sann
 
 
 def bits(a):
@@ -30,4 +30,14 @@ def test_pso_oracle_reproduces_reference_fixture(oracle_lib, path):
     for k in ("f_value", "iterations", "function_calls", "draws_consumed", "best_valid"):
         assert st[k] == z[k].item(), k
     for k in ("x_best", "positions", "pbest_values", "last_values"):
+        assert np.array_equal(bits(a[k]), bits(z[k])), k
+
+
+@pytest.mark.parametrize("path", golden_files("sann_"), ids=os.path.basename)
+def test_sann_oracle_reproduces_reference_fixture(oracle_lib, path):
+    cfg, x0, z = load_sann(path)
+    st, a = B.sann_run(oracle_lib, cfg, x0)
+    assert st["f_value"] == z["f_value"].item() and st["best_index"] == z["best_index"].item()
+    assert st["function_calls"] == z["function_calls_total"].item()
+    for k in ("x_best", "f_best", "draws", "iterations", "function_calls"):
         assert np.array_equal(bits(a[k]), bits(z[k])), k

@@ -189,3 +189,65 @@ def test_pso_stop_rules_match_reference(oracle_lib, ref_lib):
         for k in ("f_value", "iterations", "function_calls", "draws_consumed"):
             assert so[k] == sr[k], k
         assert same_bits(ao["x_best"], ar["x_best"])
+
+
+# ---------------------------------------------------------------- SANN chains ---------------
+def test_sann_default_xorshift_known_answer(oracle_lib):
+    # nlsolver::SANN<Rosenbrock (example.cpp:41-48), xorshift<double>> with its defaults from {5, 5}: values produced by
+    # the unmodified reference (oracle/_ref) and frozen here so that the check also runs where the reference cannot
+    cfg = B.sann_cfg(objective=B.ROSENBROCK_EX, n_chains=1, dim=2, rng_mode=B.RNG_XORSHIFT)
+    st, a = B.sann_run(oracle_lib, cfg, np.array([5.0, 5.0]))
+    assert (st["iterations"], st["function_calls"]) == (5000, 45001)
+    assert float(st["f_value"]).hex() == "0x1.18098474b13bep-12"
+    assert [float(v).hex() for v in a["x_best"][0]] == ["0x1.f7ab827808a3fp-1", "0x1.ef8dddf306125p-1"]
+
+
+SANN_CASES = [
+    # dtype, objective, minimize, n_chains, d, max_iter, temperature_iter, temperature_max
+    (B.F64, B.SPHERE, True, 6, 7, 200, 10, 10.0),
+    (B.F64, B.ROSENBROCK, True, 5, 2, 300, 10, 10.0),
+    (B.F64, B.RASTRIGIN, True, 4, 67, 60, 5, 3.0),
+    (B.F64, B.ACKLEY, False, 6, 5, 150, 10, 10.0),
+    (B.F64, B.STYBLINSKI_TANG, True, 3, 9, 100, 2, 1.0),
+    (B.F64, B.BEALE, True, 4, 2, 200, 10, 10.0),
+    (B.F32, B.SPHERE, True, 6, 7, 200, 10, 10.0),
+    (B.F32, B.RASTRIGIN, False, 4, 16, 100, 10, 10.0),
+    (B.F64, B.SPHERE, True, 2, 3, 50, 1, 10.0),     # temperature_iter = 1: no candidate is ever evaluated
+    (B.F64, B.SPHERE, True, 2, 3, 0, 10, 10.0),     # max_iter = 0
+]
+
+
+@pytest.mark.parametrize("dtype,obj,minimize,n,d,it,ti,tmax", SANN_CASES)
+def test_sann_restatement_equals_reference_on_tape(oracle_lib, ref_lib, dtype, obj, minimize, n, d, it, ti, tmax):
+    rng = np.random.default_rng(100 + d)
+    for x0 in (np.linspace(-2.0, 3.0, d), rng.uniform(-3, 3, size=(n, d))):   # shared start / one start per chain
+        cfg = dict(dtype=dtype, objective=obj, minimize=minimize, n_chains=n, dim=d, max_iter=it, temperature_iter=ti,
+                   temperature_max=tmax, seed=77 + d, chain_offset=5)
+        so, ao = B.sann_run(oracle_lib, B.sann_cfg(**cfg), x0)
+        sr, ar = B.sann_run(ref_lib, B.sann_cfg(**cfg), x0)
+        for k in ("f_value", "iterations", "function_calls", "draws_consumed", "best_index"):
+            assert so[k] == sr[k], (k, so[k], sr[k])
+        for k in ("x_best", "f_best", "draws", "iterations", "function_calls"):
+            assert same_bits(ao[k], ar[k]), k
+        assert (ao["function_calls"] == 1 + it * max(ti - 1, 0)).all()
+
+
+def test_sann_sequential_xorshift_matches_reference(oracle_lib, ref_lib):
+    # chains run one after the other on ONE shared generator, like repeated minimize() calls on the same RNG object
+    for dtype in (B.F64, B.F32):
+        cfg = dict(dtype=dtype, objective=B.ROSENBROCK_EX, n_chains=3, dim=2, max_iter=800, rng_mode=B.RNG_XORSHIFT)
+        so, ao = B.sann_run(oracle_lib, B.sann_cfg(**cfg), np.array([2.0, 7.0]))
+        sr, ar = B.sann_run(ref_lib, B.sann_cfg(**cfg), np.array([2.0, 7.0]))
+        assert so["f_value"] == sr["f_value"] and so["function_calls"] == sr["function_calls"]
+        assert same_bits(ao["x_best"], ar["x_best"]) and same_bits(ao["f_best"], ar["f_best"])
+
+
+def test_sann_restatement_cut_points_compose(oracle_lib):
+    # max_steps cuts a chain without disturbing it: the state after k candidates is a prefix of the full run's history
+    cfg = dict(objective=B.RASTRIGIN, n_chains=3, dim=9, max_iter=40, temperature_iter=10, seed=9)
+    full, af = B.sann_run(oracle_lib, B.sann_cfg(**cfg), np.full(9, 2.0))
+    cut, ac = B.sann_run(oracle_lib, B.sann_cfg(max_steps=360, **cfg), np.full(9, 2.0))
+    assert same_bits(af["x_best"], ac["x_best"]) and same_bits(af["p_cur"], ac["p_cur"])
+    part, ap = B.sann_run(oracle_lib, B.sann_cfg(max_steps=100, **cfg), np.full(9, 2.0))
+    assert (ap["function_calls"] == 101).all() and (ap["n_accepted"] <= af["n_accepted"]).all()
+    assert (ap["f_best"] >= af["f_best"]).all()
