@@ -97,13 +97,15 @@ __global__ void __launch_bounds__(kBlock, NLS_PSO_MINBLOCKS) sann_steps_kernel(S
     u32 pi = role & 3u, xi = (role >> 2) & 3u, shift = (role >> 4) & 1u;
     T best = static_cast<const T *>(s.best)[c];
     u32 n_acc = s.n_acc[c], n_imp = s.n_imp[c];
+    // candidate number n (1-based) belongs to outer iteration (n - 1) / inner and draws from epoch n - 1; both are
+    // carried along instead of being re-derived per candidate (a 64-bit division and two mix64 rounds each)
+    u64 iter = step_begin / s.inner, in_iter = step_begin % s.inner;
+    u64 key = tape_key(tape_gen_key(s.seed, step_begin), gc);
     for (u64 n = step_begin + 1; n <= step_begin + n_steps; n++) {
-      const u64 iter = (n - 1) / s.inner;
       // cooling schedule (nlsolver.h:2792-2793); e - 1 is the reference's truncated literal
       const T t = iter < s.t_n ? static_cast<T>(s.t_table[iter])
                                : tmax / t_log<T>(A::add(static_cast<T>(iter), static_cast<T>(1.7182818)));
       const T cs = A::mul(t, scale);
-      const u64 key = tape_key(tape_gen_key(s.seed, n - 1), gc);
       const u32 fi = (pi == xi) ? (pi + 1u) % 3u : 3u - pi - xi;
       const T *prow = static_cast<const T *>(sann_buf(s, pi)) + c * s.stride;
       T *trow = static_cast<T *>(sann_buf(s, fi)) + c * s.stride;
@@ -135,9 +137,10 @@ __global__ void __launch_bounds__(kBlock, NLS_PSO_MINBLOCKS) sann_steps_kernel(S
       const T diff = A::sub(val, best);                  // against best_val, not f(p) (:2803)
       bool accept = diff <= T(0);
       shift = 0;
-      if (!accept) {                                     // Metropolis draw: first draw of the epoch this call opened
-        const u64 key_next = tape_key(tape_gen_key(s.seed, n), gc);
-        const T u = unit<T>(tape_draw(key_next, 0));
+      key = tape_key(tape_gen_key(s.seed, n), gc);       // the objective call above opened epoch n
+      if (++in_iter == s.inner) { in_iter = 0; iter++; }
+      if (!accept) {                                     // Metropolis draw: first draw of the new epoch
+        const T u = unit<T>(tape_draw(key, 0));
         shift = 1;
         // the reference's unqualified exp() is the double overload for float too; the compare runs in double
         accept = static_cast<double>(u) < exp(static_cast<double>(-diff / t));
