@@ -1,6 +1,7 @@
 """Multi-GPU parity check over NCCL (run under torchrun on N GPUs of one box):
   * ShardedPSO over N ranks == the single-GPU swarm (bit for bit) == the oracle (1e-12);
-  * IslandDE over N ranks with ring migration == the harness-level restatement on the oracle steppers.
+  * IslandDE over N ranks with ring migration == the harness-level restatement on the oracle steppers;
+  * ShardedSANN over N ranks == the oracle batch (slices by global chain id, batch best by one all-gather).
 Prints one line per check on rank 0; exits non-zero on mismatch."""
 import os
 import sys
@@ -94,6 +95,28 @@ def main():
         print(f"island DE x{world}: every island and the global best equal the restatement = {bool(flag.item())}", flush=True)
     ok &= bool(flag.item())
     isl.close()
+
+    # ---- SANN chains sharded by global chain id: no exchange while the chains run, one all-gather for the batch best ----
+    n, ds, it = 1000 + 3, 24, 30
+    skw = dict(objective=nb.RASTRIGIN, n_chains=n, dim=ds, max_iter=it, seed=99)
+    xs = np.random.default_rng(4).uniform(-3, 3, size=(n, ds))
+    job = D.ShardedSANN(nb.sann_cfg(**skw), xs, device=local)
+    job.run()
+    gst, grow = job.global_best()
+    part = job.engine.chains()
+    so, ao = B.sann_run(B.oracle(), B.sann_cfg(**skw), xs)
+    rel = np.max(np.abs(part["x_best"] - ao["x_best"][job.begin:job.end])
+                 / np.max(np.abs(ao["x_best"][job.begin:job.end]), axis=1, keepdims=True))
+    mine = (rel < 1e-12 and np.array_equal(part["n_accepted"], ao["n_accepted"][job.begin:job.end])
+            and gst["best_index"] == so["best_index"] and abs(gst["f_value"] - so["f_value"]) <= 1e-12 * abs(so["f_value"])
+            and gst["function_calls"] == so["function_calls"]
+            and np.max(np.abs(grow - ao["x_best"][so["best_index"]])) <= 1e-12 * np.max(np.abs(grow)))
+    flag = torch.tensor([1 if mine else 0], device=f"cuda:{local}")
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        print(f"sharded SANN x{world}: every slice and the batch best equal the oracle = {bool(flag.item())}", flush=True)
+    ok &= bool(flag.item())
+    job.close()
     dist.barrier()
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)
