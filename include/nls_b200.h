@@ -120,6 +120,9 @@ NLS_API int nls_ctx_destroy(nls_ctx *ctx);
 /* A context caches the device buffers of destroyed solver handles for the next solve of the same shape (allocating
  * and freeing multi-GB populations costs hundreds of milliseconds); nls_ctx_trim returns them to the driver. */
 NLS_API int nls_ctx_trim(nls_ctx *ctx);
+/* Debug aid: with NLS_B200_GUARD=1 in the environment every device buffer is allocated between two 256-byte guard zones
+ * that are verified when its solver handle is destroyed; returns how many buffers were found overwritten so far. */
+NLS_API unsigned long long nls_debug_guard_violations(void);
 NLS_API int nls_ctx_device(const nls_ctx *ctx);
 NLS_API int nls_ctx_sm_count(const nls_ctx *ctx);
 

@@ -68,6 +68,7 @@ SYMBOLS = {
     "nls_ctx_create": (C.c_int, [C.c_int, P, C.POINTER(P)]),
     "nls_ctx_destroy": (C.c_int, [P]),
     "nls_ctx_trim": (C.c_int, [P]),
+    "nls_debug_guard_violations": (C.c_ulonglong, []),
     "nls_ctx_device": (C.c_int, [P]),
     "nls_ctx_sm_count": (C.c_int, [P]),
     "nls_de_solve": (C.c_int, [P, C.POINTER(DECfg), P, P, C.POINTER(Status)]),
