@@ -118,7 +118,12 @@ template <class C> struct plugin_full_dim<C, std::void_t<decltype(C::full_dim)>>
 
 // W = lanes that cooperate on one agent (32, or a smaller power of two when d <= W * V so that one step covers the
 // row); `lane` arguments are lane indices INSIDE the group.
-template <class T, int OBJ, int W = 32>
+// S = accumulator slots per lane.  The canonical order has 32 accumulators, term j going to accumulator (j / V) % 32.
+// A group of W < 32 lanes that sweeps a LONGER row (d > W * V) keeps S = 32 / W of them per lane: sweep k of the row
+// feeds slot k % S, i.e. canonical accumulator slot * W + lane, and finish() runs the upper butterfly stages (offsets
+// 16 ... W) between slots before the shuffles — the same pairs are added in the same stage order, so the result is
+// bit-identical to the 32-lane evaluation.  S = 1 is the plain case (W = 32, or one sweep).
+template <class T, int OBJ, int W = 32, int S = 1>
 struct Objective {
   static constexpr int V = Vec<T>::V;
   static constexpr unsigned custom_full_dim() {
@@ -132,19 +137,23 @@ struct Objective {
   }
   static constexpr bool kPairwise = (OBJ == OBJ_ROSENBROCK || OBJ == OBJ_ROSENBROCK_EX) || custom_pairwise();
   typedef Ar<T> A;
-  T a, b, carry;
+  static_assert(S == 1 || S * W == 32, "S slots of W lanes must tile the 32 canonical accumulators");
+  T acc_a[S], acc_b[S], carry;
 
   __device__ __forceinline__ void begin(int lane, u32 d) {
+#pragma unroll
+    for (int k = 0; k < S; k++) { acc_a[k] = T(0); acc_b[k] = T(0); }
     // Rastrigin's leading `2*10` (10*d in N-D) seeds lane 0's accumulator so that d = 2 gives (20 + t0) + t1
-    a = (OBJ == OBJ_RASTRIGIN && lane == 0) ? A::mul(T(10), T(d)) : T(0);
-    if constexpr (OBJ == OBJ_CUSTOM && kFullDim == 0) a = lane == 0 ? CustomObjective<T>::lane0_seed(d) : T(0);
-    b = T(0);
+    acc_a[0] = (OBJ == OBJ_RASTRIGIN && lane == 0) ? A::mul(T(10), T(d)) : T(0);
+    if constexpr (OBJ == OBJ_CUSTOM && kFullDim == 0) acc_a[0] = lane == 0 ? CustomObjective<T>::lane0_seed(d) : T(0);
     carry = T(0);
   }
 
   // x[q] is coordinate j0 + q of the agent; coordinates >= d are padding and contribute nothing.
-  // Must be called by all 32 lanes (the pairwise forms shuffle).
-  __device__ __forceinline__ void step(const T (&x)[V], u32 j0, u32 d, int lane) {
+  // Must be called by all 32 lanes (the pairwise forms shuffle).  `slot` = sweep number % S (a constant after unrolling).
+  __device__ __forceinline__ void step(const T (&x)[V], u32 j0, u32 d, int lane, int slot = 0) {
+    T &a = acc_a[slot];
+    T &b = acc_b[slot];
     if constexpr (kFullDim > 0) {
       // gather the whole vector into every lane of the group (coordinate k sits in lane k / V, slot k % V); the
       // group's first lane evaluates the closed form, the others contribute 0 to the butterfly
@@ -200,7 +209,17 @@ struct Objective {
 
   // every lane returns the objective value
   __device__ __forceinline__ T finish(u32 d) {
-    a = warp_butterfly_add<T, W>(a);
+    // butterfly stages with offsets >= W pair accumulators of the same lane: slot ^ (offset / W)
+#pragma unroll
+    for (int off = S / 2; off >= 1; off >>= 1) {
+      T ta[S], tb[S];
+#pragma unroll
+      for (int k = 0; k < S; k++) { ta[k] = A::add(acc_a[k], acc_a[k ^ off]); tb[k] = A::add(acc_b[k], acc_b[k ^ off]); }
+#pragma unroll
+      for (int k = 0; k < S; k++) { acc_a[k] = ta[k]; acc_b[k] = tb[k]; }
+    }
+    T a = warp_butterfly_add<T, W>(acc_a[0]);
+    T b = acc_b[0];
     if constexpr (kFullDim > 0) {
       return a;                                            // closed forms: lane 0's value, the others added 0
     } else if constexpr (OBJ == OBJ_CUSTOM) {

@@ -17,8 +17,11 @@
 // evaluated — made only when difference > 0, the reference's short-circuit `||` (:2804) — then the 2*d rnorm draws of
 // the next candidate.
 #pragma once
+#include <cstdlib>
+
 #include "objectives.cuh"
 #include "pso_impl.cuh"   // rnorm_from, launch helpers
+
 
 namespace nls {
 
@@ -78,8 +81,14 @@ __global__ void __launch_bounds__(kBlock) sann_init_kernel(SANNState s, const T 
 }
 
 // ------------------------------------------------------------------------------------------------ candidates
-template <class T, int OBJ, int W>
-__global__ void __launch_bounds__(kBlock, NLS_PSO_MINBLOCKS) sann_steps_kernel(SANNState s, u64 step_begin, u64 n_steps) {
+// S = accumulator slots per lane (objectives.cuh): 1 when one sweep of W lanes covers the row, 32 / W when a narrow group
+// sweeps a longer row.  Narrow groups pay the per-candidate work (epoch key, Metropolis test with its exp and division,
+// role bookkeeping — about 230 instructions) once per WARP for 32 / W chains instead of once per chain.
+#ifndef NLS_SANN_SLOT_MINBLOCKS
+#define NLS_SANN_SLOT_MINBLOCKS 2   // S > 1 keeps S accumulators per lane and an S-times unrolled sweep: no spills at 128 registers
+#endif
+template <class T, int OBJ, int W, int S>
+__global__ void __launch_bounds__(kBlock, S == 1 ? NLS_PSO_MINBLOCKS : NLS_SANN_SLOT_MINBLOCKS) sann_steps_kernel(SANNState s, u64 step_begin, u64 n_steps) {
   constexpr int V = Vec<T>::V;
   constexpr u32 kStride = W * V;
   constexpr int G = 32 / W;
@@ -109,11 +118,14 @@ __global__ void __launch_bounds__(kBlock, NLS_PSO_MINBLOCKS) sann_steps_kernel(S
       const u32 fi = (pi == xi) ? (pi + 1u) % 3u : 3u - pi - xi;
       const T *prow = static_cast<const T *>(sann_buf(s, pi)) + c * s.stride;
       T *trow = static_cast<T *>(sann_buf(s, fi)) + c * s.stride;
-      Objective<T, OBJ, W> obj;
+      Objective<T, OBJ, W, S> obj;
       obj.begin(lane, d);
       u32 j0 = lane * V;
       u64 st = tape_state(key, u64(shift) + 2 * u64(j0));   // coordinate j: draws shift + 2j (log), shift + 2j + 1 (cos)
-      for (u32 sw = 0; sw < n_sweeps; sw++) {
+      for (u32 sw0 = 0; sw0 < n_sweeps; sw0 += S) {
+#pragma unroll
+      for (int slot = 0; slot < S; slot++) {
+        if (sw0 + slot >= n_sweeps) break;
         const bool in = j0 < d;
         const u32 jl = in ? j0 : 0u;                     // lanes past the row end recompute coordinate 0, unused
         T x[V];
@@ -129,9 +141,10 @@ __global__ void __launch_bounds__(kBlock, NLS_PSO_MINBLOCKS) sann_steps_kernel(S
             if (j0 + q >= d) x[q] = T(0);                // padding inside the last vector stays zero
           st_own(trow + j0, x);
         }
-        obj.step(x, j0, d, lane);
+        obj.step(x, j0, d, lane, slot);
         j0 += kStride;
         st += kGolden * (2 * kStride);
+      }
       }
       const T val = A::mul(fm, obj.finish(d));
       const T diff = A::sub(val, best);                  // against best_val, not f(p) (:2803)
@@ -207,24 +220,40 @@ cudaError_t sann_launch_init(const SANNState &s, const void *x0, u64 x0_count, c
 #undef NLS_CALL
   return cudaGetLastError();
 }
-template <class T, int O, int W>
+template <class T, int O, int W, int S>
 void sann_launch_steps_w(const SANNState &s, u64 b, u64 n, const LaunchGeom &g, cudaStream_t st) {
   const u64 per_block = u64(kWarpsPerBlock) * (32 / W);
   const u64 want = (s.C + per_block - 1) / per_block;
-  sann_steps_kernel<T, O, W><<<pso_clamp_grid(want, u64(g.sm_count) * pso_blocks_per_sm(sann_steps_kernel<T, O, W>)),
-                               kBlock, 0, st>>>(s, b, n);
+  sann_steps_kernel<T, O, W, S><<<pso_clamp_grid(want, u64(g.sm_count) * pso_blocks_per_sm(sann_steps_kernel<T, O, W, S>)),
+                                  kBlock, 0, st>>>(s, b, n);
+}
+// Lane-group width for a row of `row_bytes`.  Narrow groups amortise the per-candidate work over 32 / W chains per warp,
+// but every resident chain keeps two hot rows (p and the candidate): 4 lanes while those fit L1 (measured on B200:
+// d = 20 fp64 +65 % over one 16-lane sweep), 8 lanes while they fit L2 (d = 64: +32 %, d = 256: +4 %), a full warp per
+// chain beyond that (d = 1000: 8 lanes would spill the hot rows to HBM, -8 %).  NLS_SANN_LANES=4|8|16|32 overrides.
+inline int sann_lanes_for(u64 row_bytes) {
+  if (const char *e = std::getenv("NLS_SANN_LANES")) {
+    const int v = std::atoi(e);
+    if (v == 4 || v == 8 || v == 16 || v == 32) return v;
+  }
+  return row_bytes <= 320 ? 4 : (row_bytes <= 2304 ? 8 : 32);
 }
 template <class T, int O>
 void sann_launch_steps_t(const SANNState &s, u64 b, u64 n, const LaunchGeom &g, cudaStream_t st) {
   const u64 vecs = (s.d + Vec<T>::V - 1) / Vec<T>::V;
-  if constexpr (closed_form_dim(O) > 0) {
-    sann_launch_steps_w<T, O, 4>(s, b, n, g, st);
+  if constexpr (Objective<T, O>::kFullDim > 0) {         // closed forms: short fixed vectors, one sweep of 4 lanes
+    sann_launch_steps_w<T, O, 4, 1>(s, b, n, g, st);
     return;
+  } else {
+    const int single = vecs <= 4 ? 4 : (vecs <= 8 ? 8 : (vecs <= 16 ? 16 : 32));   // narrowest one-sweep group
+    const int want = sann_lanes_for(s.d * sizeof(T));
+    const int lanes = want < single ? want : single;
+    const bool multi = lanes < single;                   // several sweeps per candidate: S = 32 / lanes slots
+    if (lanes == 4) { if (multi) sann_launch_steps_w<T, O, 4, 8>(s, b, n, g, st); else sann_launch_steps_w<T, O, 4, 1>(s, b, n, g, st); }
+    else if (lanes == 8) { if (multi) sann_launch_steps_w<T, O, 8, 4>(s, b, n, g, st); else sann_launch_steps_w<T, O, 8, 1>(s, b, n, g, st); }
+    else if (lanes == 16) { if (multi) sann_launch_steps_w<T, O, 16, 2>(s, b, n, g, st); else sann_launch_steps_w<T, O, 16, 1>(s, b, n, g, st); }
+    else sann_launch_steps_w<T, O, 32, 1>(s, b, n, g, st);
   }
-  if (vecs <= 4) sann_launch_steps_w<T, O, 4>(s, b, n, g, st);
-  else if (vecs <= 8) sann_launch_steps_w<T, O, 8>(s, b, n, g, st);
-  else if (vecs <= 16) sann_launch_steps_w<T, O, 16>(s, b, n, g, st);
-  else sann_launch_steps_w<T, O, 32>(s, b, n, g, st);
 }
 template <class T>
 cudaError_t sann_launch_steps(const SANNState &s, u64 b, u64 n, const LaunchGeom &g, cudaStream_t st) {

@@ -108,6 +108,33 @@ def test_sann_chains_match_reference_fixture(ctx, path):
     assert np.array_equal(z["draws"], 2 * cfg.dim * steps + (steps - res["n_improved"].astype(np.uint64)))
 
 
+@pytest.mark.parametrize("lanes", [4, 8, 16, 32])
+@pytest.mark.parametrize("dtype,obj,d", [(B.F64, B.RASTRIGIN, 67), (B.F64, B.ROSENBROCK, 45), (B.F64, B.ACKLEY, 150),
+                                         (B.F32, B.SPHERE, 200), (B.F64, B.STYBLINSKI_TANG, 20)])
+def test_sann_lane_group_width_never_changes_a_decision(ctx, oracle_lib, monkeypatch, lanes, dtype, obj, d):
+    """The lane-group width is a tuning choice (NLS_SANN_LANES overrides the row-size policy): narrow groups sweep a long
+    row in several passes with 32 / W accumulator slots per lane, which reproduces the canonical 32-accumulator summation
+    order bit for bit — so every width must give the same chains."""
+    monkeypatch.setenv("NLS_SANN_LANES", str(lanes))
+    n, it, seed = 19, 25, 300 + d
+    x0 = start_points(n, d, False, seed)
+    ch = gpu_chains(ctx, dtype, obj, True, n, d, it, 10, 10.0, seed, x0)
+    ch.run()
+    ch.sync()
+    res = ch.chains()
+    ch.close()
+    so, ao = oracle_chains(oracle_lib, dtype, obj, True, n, d, it, 10, 10.0, seed, x0)
+    assert_chains_match(res, ao, tol_of(dtype))
+    monkeypatch.setenv("NLS_SANN_LANES", "32")
+    ch = gpu_chains(ctx, dtype, obj, True, n, d, it, 10, 10.0, seed, x0)
+    ch.run()
+    ch.sync()
+    wide = ch.chains()
+    ch.close()
+    for k in ("x_best", "p_cur", "f_best"):
+        assert np.array_equal(bits(res[k]), bits(wide[k])), k      # identical bits, not merely within tolerance
+
+
 def test_sann_stepwise_equals_one_shot_and_oracle_cut_points(ctx, oracle_lib):
     dtype, obj, n, d, it, ti, tmax, seed = B.F64, B.RASTRIGIN, 13, 19, 40, 10, 10.0, 5
     x0 = start_points(n, d, False, seed)
