@@ -13,6 +13,8 @@
  * throws across this boundary.  There is NO CPU fallback: without a CUDA device nls_ctx_create fails.
  *
  * Threading: one solve at a time per solver handle; handles and contexts are independent of one another.
+ * nls_load_objective is not synchronised against concurrent handle creation: load plugins before starting solver threads.
+ * Lifetime: destroy every solver handle (nls_de / nls_pso / nls_sann / nls_xchg) before the context it was created on.
  */
 #ifndef NLS_B200_H_
 #define NLS_B200_H_
