@@ -903,7 +903,7 @@ struct nls_sann {
   DeviceBuffers mem;
   size_t elem;
   u64 steps_done;
-  void *dense;      // [C][d] staging for row read-out
+  void *dense;      // [C][d] staging for the per-chain read-out, allocated on first use
 };
 
 static int sann_validate(const nls_sann_cfg *c, uint64_t x0_count) {
@@ -969,7 +969,7 @@ static int sann_build(nls_ctx *ctx, const nls_sann_cfg *cfg, const void *x0_host
   NLS_ALLOC(s.n_acc, C * sizeof(uint32_t));
   NLS_ALLOC(s.n_imp, C * sizeof(uint32_t));
   NLS_ALLOC(s.ctrl, sizeof(SANNCtrl));
-  NLS_ALLOC(sa->dense, size_t(C) * d * sa->elem);
+  sa->dense = nullptr;
   const u64 tn = std::min<u64>(std::max<u64>(cfg->max_iter, 1), 1u << 16);
   std::vector<double> table(tn);
   for (u64 k = 0; k < tn; k++)
@@ -1046,6 +1046,10 @@ int nls_sann_sync(nls_sann *sa, nls_status *status) {
 
 static int sann_read_rows(nls_sann *sa, int which, u64 first, u64 count, void *host) {
   cudaStream_t st = sa->ctx->stream;
+  if (!sa->dense) {
+    int rc = sa->mem.alloc(&sa->dense, size_t(sa->s.C) * sa->s.d * sa->elem);
+    if (rc != NLS_OK) return rc;
+  }
   NLS_CUDA(sa->ops->gather(sa->s, which, sa->dense, sa->g, st));
   const size_t row = sa->s.d * sa->elem;
   NLS_CUDA(cudaMemcpyAsync(host, static_cast<const char *>(sa->dense) + first * row, count * row, cudaMemcpyDeviceToHost, st));
@@ -1061,7 +1065,11 @@ int nls_sann_read_best(nls_sann *sa, void *x_host) {
   NLS_CUDA(sa->ops->best(sa->s, st));
   NLS_CUDA(cudaMemcpyAsync(&c, sa->s.ctrl, sizeof(c), cudaMemcpyDeviceToHost, st));
   NLS_CUDA(cudaStreamSynchronize(st));
-  return sann_read_rows(sa, 0, c.best_chain, 1, x_host);
+  // the best chain's x is one contiguous row of the buffer its role byte names: no gather of the whole batch
+  const char *row = static_cast<const char *>(sa->s.buf[c.best_buf % 3]) + c.best_chain * sa->s.stride * sa->elem;
+  NLS_CUDA(cudaMemcpyAsync(x_host, row, sa->s.d * sa->elem, cudaMemcpyDeviceToHost, st));
+  NLS_CUDA(cudaStreamSynchronize(st));
+  return NLS_OK;
 }
 
 int nls_sann_read_chains(nls_sann *sa, void *x_best_host, void *f_best_host, void *p_cur_host, uint32_t *n_accepted,

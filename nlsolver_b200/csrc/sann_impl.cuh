@@ -205,6 +205,7 @@ __global__ void __launch_bounds__(kBlock) sann_best_kernel(SANNState s) {
     for (int k = 1; k < kWarpsPerBlock; k++) ml = minloc_merge(ml, sm[k]);
     s.ctrl->best_valid = ml.i != ~0ull;
     s.ctrl->best_chain = ml.i != ~0ull ? ml.i : 0;
+    s.ctrl->best_buf = (s.role[ml.i != ~0ull ? ml.i : 0] >> 2) & 3;
     s.ctrl->best_value = ml.i != ~0ull ? ml.v : static_cast<double>(best[0]);
   }
 }

@@ -95,7 +95,8 @@ struct XchgWindow {
 struct SANNCtrl {
   double best_value;
   unsigned long long best_chain;   // local index of the best chain (lowest value, lowest index on ties)
-  int best_valid, _pad;
+  int best_valid;
+  int best_buf;                    // which of the three row buffers holds that chain's x
 };
 struct SANNState {
   void *buf[3];            // [C][stride] each
