@@ -53,7 +53,17 @@ def main():
             print(f"generation {st['iterations']:4d}: best {st['f_value']:.6g}, accepted so far {st['accepted_total']}")
     pop.close()
 
-    # 4. multi-GPU (under torchrun): one global swarm sharded across the ranks, exchange over peer memory
+    # 4. simulated annealing: one chain as in the reference, then 65536 independent chains from the same start
+    x = [5.0, 5.0]
+    status = nb.SANN(nb.RosenbrockExample, gen).minimize(x)
+    sann = nb.SANN(nb.Rastrigin, gen, max_iter=500)
+    x8 = [3.3] * 8
+    many = sann.minimize_multistart(x8, 1 << 16)
+    if rank == 0:
+        print("SANN, one chain, Rosenbrock:", status.f_value, x)
+        print("SANN, 65536 chains, Rastrigin d=8: best", many.f_value, "after", many.function_calls_used, "objective calls")
+
+    # 5. multi-GPU (under torchrun): one global swarm sharded across the ranks, exchange over peer memory
     if world > 1:
         from nlsolver_b200 import distributed as D
         D.init_from_env("nccl")
