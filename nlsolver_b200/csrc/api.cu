@@ -1010,7 +1010,7 @@ int nls_sann_step(nls_sann *sa, uint64_t n_candidates) {
   // one launch carries every chain through its candidates; bound a launch to ~2^31 coordinate updates (a few tens of
   // milliseconds of device time) so that large batches stay responsive to sync / destroy
   const u64 per_step = std::max<u64>(sa->s.C * sa->s.d, 1);
-  const u64 chunk = std::max<u64>((1ull << 31) / per_step, 1);
+  const u64 chunk = std::min<u64>(std::max<u64>((1ull << 31) / per_step, 1), 1ull << 20);   // tiny batches: <= ~1 s
   while (n > 0) {
     const u64 k = std::min(n, chunk);
     NLS_CUDA(sa->ops->steps(sa->s, sa->steps_done, k, sa->g, sa->ctx->stream));
