@@ -186,3 +186,15 @@ def test_sharded_sann_two_ranks_equals_one_batch(shared):
         assert np.array_equal(row, ao["x_best"][so["best_index"]])
         whole_x[b:e], whole_f[b:e] = chains["x_best"], chains["f_best"]
     assert np.array_equal(whole_x, ao["x_best"]) and np.array_equal(whole_f, ao["f_best"])
+
+
+def test_sharded_sann_three_ranks_uneven_slices():
+    kw = dict(SANN_KW, n_chains=10, objective=nb.ACKLEY, minimize=False)     # slices of 4, 3, 3 chains; maximize
+    x0 = np.random.default_rng(8).uniform(-2, 2, size=(10, kw["dim"]))
+    so, ao = B.sann_run(B.oracle(), B.sann_cfg(**kw), x0)
+    out = run_ranks(_sharded_sann, 3, kw, x0, 50)
+    assert sorted(e - b for _, _, _, _, (b, e) in out.values()) == [3, 3, 4]
+    for rank, (mid, st, row, chains, (b, e)) in out.items():
+        assert (st["f_value"], st["best_index"]) == (so["f_value"], so["best_index"])
+        assert np.array_equal(row, ao["x_best"][so["best_index"]])
+        assert np.array_equal(chains["f_best"], ao["f_best"][b:e]) and np.array_equal(chains["p_cur"], ao["p_cur"][b:e])

@@ -212,6 +212,9 @@ SANN_CASES = [
     (B.F64, B.BEALE, True, 4, 2, 200, 10, 10.0),
     (B.F32, B.SPHERE, True, 6, 7, 200, 10, 10.0),
     (B.F32, B.RASTRIGIN, False, 4, 16, 100, 10, 10.0),
+    (B.F64, B.SHEKEL, True, 3, 4, 150, 10, 10.0),
+    (B.F64, B.LEVI_N13, False, 3, 2, 150, 10, 5.0),
+    (B.F32, B.ROSENBROCK_EX, True, 5, 2, 300, 10, 10.0),
     (B.F64, B.SPHERE, True, 2, 3, 50, 1, 10.0),     # temperature_iter = 1: no candidate is ever evaluated
     (B.F64, B.SPHERE, True, 2, 3, 0, 10, 10.0),     # max_iter = 0
 ]

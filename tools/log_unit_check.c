@@ -31,9 +31,10 @@ static double log_unit(double x) {
   return fma(dk, ln2_hi, -((hfsq - fma(s, hfsq + R, dk * ln2_lo)) - f));
 }
 static uint64_t mix64(uint64_t z){ z=(z^(z>>30))*0xBF58476D1CE4E5B9ull; z=(z^(z>>27))*0x94D049BB133111EBull; return z^(z>>31);}
-int main(void) {
+int main(int argc, char **argv) {
   double maxulp = 0; uint64_t worst = 0; long n = 0, exact = 0;
-  for (uint64_t c = 1; c <= 40000000ull; c++) {
+  const uint64_t count = argc > 1 ? strtoull(argv[1], 0, 10) : 40000000ull;
+  for (uint64_t c = 1; c <= count; c++) {
     uint64_t raw = mix64(c * 0x9E3779B97F4A7C15ull);
     if (c % 7 == 0) raw >>= (c % 60);          // small values too
     if (raw == 0) continue;
