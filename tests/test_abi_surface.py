@@ -63,3 +63,34 @@ def test_seed_from_generator_consumes_two_draws():
     draws = iter([0.5, 0.25, 0.9])
     seed = seed_from_generator(lambda: next(draws))
     assert seed == (0x80000000 << 32) | 0x40000000 and next(draws) == 0.9
+
+
+def test_null_arguments_are_rejected_before_any_cuda_call():
+    """Argument validation is host logic: it must answer NLS_ERR_INVALID (and leave a message) even without a GPU."""
+    import ctypes as C
+    from nlsolver_b200 import _lib
+    h = _lib.lib()
+    out = C.c_void_p()
+    st = _lib.Status()
+    calls = [
+        lambda: h.nls_ctx_create(0, None, None),
+        lambda: h.nls_de_create(None, None, None, C.byref(out)),
+        lambda: h.nls_pso_create(None, None, None, None, C.byref(out)),
+        lambda: h.nls_sann_create(None, None, None, 1, C.byref(out)),
+        lambda: h.nls_de_solve(None, None, None, None, C.byref(st)),
+        lambda: h.nls_pso_solve(None, None, None, None, None, C.byref(st)),
+        lambda: h.nls_sann_solve(None, None, None, 1, None, C.byref(st)),
+        lambda: h.nls_de_step(None, 1), lambda: h.nls_pso_step(None, 1), lambda: h.nls_sann_step(None, 1),
+        lambda: h.nls_de_sync(None, None), lambda: h.nls_pso_sync(None, None), lambda: h.nls_sann_sync(None, None),
+        lambda: h.nls_sann_read_best(None, None), lambda: h.nls_sann_read_chains(None, None, None, None, None, None),
+        lambda: h.nls_load_objective(None, None),
+        lambda: h.nls_xchg_create(None, 64, 1, 0, C.byref(out)),
+    ]
+    for k, call in enumerate(calls):
+        assert call() == -1, f"call {k} did not return NLS_ERR_INVALID"
+        assert h.nls_last_error(), f"call {k} left no message"
+    # destroying nothing is fine, as free(NULL) is
+    assert h.nls_de_destroy(None) == 0 and h.nls_pso_destroy(None) == 0 and h.nls_sann_destroy(None) == 0
+    assert h.nls_ctx_destroy(None) == 0 and h.nls_xchg_destroy(None) == 0
+    assert h.nls_load_objective(b"/nonexistent/libobjective.so", C.byref(C.c_int32())) == -1
+    assert b"nonexistent" in h.nls_last_error()
