@@ -3,7 +3,6 @@ and refuses to run without a CUDA device (no CPU fallback)."""
 import os
 import re
 
-import numpy as np
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))

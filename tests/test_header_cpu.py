@@ -2,7 +2,6 @@
 the reference's streams (the latter only where /root/reference exists: the reference header is compiled in place)."""
 import os
 import subprocess
-import sys
 
 import pytest
 
