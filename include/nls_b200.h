@@ -119,9 +119,14 @@ NLS_API int nls_version(void);
 /* stream: a cudaStream_t to enqueue on (e.g. torch's current stream), or NULL for a stream owned by the context */
 NLS_API int nls_ctx_create(int device, void *stream, nls_ctx **out);
 NLS_API int nls_ctx_destroy(nls_ctx *ctx);
-/* A context caches the device buffers of destroyed solver handles for the next solve of the same shape (allocating
- * and freeing multi-GB populations costs hundreds of milliseconds); nls_ctx_trim returns them to the driver. */
+/* A context caches the device buffers of destroyed solver handles for the next solve (allocating and freeing multi-GB
+ * populations costs hundreds of milliseconds).  The cache is bounded: at most `bytes` (nls_ctx_set_pool_limit; 0 = the
+ * default: no more than the largest single solver handle released so far), oldest buffers evicted first; a cached
+ * buffer also serves a smaller request if less than half of it would be wasted.  nls_ctx_trim returns everything to
+ * the driver now — call it before another CUDA user of the process (a framework allocator, NCCL) needs the memory. */
 NLS_API int nls_ctx_trim(nls_ctx *ctx);
+NLS_API int nls_ctx_set_pool_limit(nls_ctx *ctx, uint64_t bytes);
+NLS_API uint64_t nls_ctx_pool_bytes(const nls_ctx *ctx);
 /* Debug aid: with NLS_B200_GUARD=1 in the environment every device buffer is allocated between two 256-byte guard zones
  * that are verified when its solver handle is destroyed; returns how many buffers were found overwritten so far. */
 NLS_API unsigned long long nls_debug_guard_violations(void);

@@ -68,6 +68,8 @@ SYMBOLS = {
     "nls_ctx_create": (C.c_int, [C.c_int, P, C.POINTER(P)]),
     "nls_ctx_destroy": (C.c_int, [P]),
     "nls_ctx_trim": (C.c_int, [P]),
+    "nls_ctx_set_pool_limit": (C.c_int, [P, u64]),
+    "nls_ctx_pool_bytes": (u64, [P]),
     "nls_debug_guard_violations": (C.c_ulonglong, []),
     "nls_ctx_device": (C.c_int, [P]),
     "nls_ctx_sm_count": (C.c_int, [P]),
@@ -128,7 +130,12 @@ def lib():
                               "(there is no CPU fallback)")
         handle = C.CDLL(LIB_PATH)
         for name, (restype, argtypes) in SYMBOLS.items():
-            fn = getattr(handle, name)
+            try:
+                fn = getattr(handle, name)
+            except AttributeError:
+                if os.environ.get("NLS_B200_LIB"):   # an older experimental build (A/B timing) may lack newer symbols
+                    continue
+                raise
             fn.restype, fn.argtypes = restype, argtypes
         _lib = handle
     return _lib

@@ -6,11 +6,13 @@
 #include <dlfcn.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <utility>
 #include <vector>
@@ -51,18 +53,22 @@ size_t elem_size(int dtype) { return dtype == NLS_F64 ? 8 : 4; }
 struct ObjectivePlugin {
   int abi;
   unsigned full_dim;
+  unsigned de_state_bytes, pso_state_bytes, sann_state_bytes, _pad;
   const DEOps *de_f64, *de_f32;
   const PSOOps *pso_f64, *pso_f32;
   const SANNOps *sann_f64, *sann_f32;
 };
 constexpr int kFirstPluginId = 100;
-std::vector<const ObjectivePlugin *> &plugin_registry() {
-  static std::vector<const ObjectivePlugin *> r;
-  return r;
-}
+constexpr int kPluginAbi = 4;
+constexpr int kMaxPlugins = 256;
+// fixed-capacity registry: entries are written once under the mutex and published by the count, so lookups from solver
+// threads never see a reallocating container
+std::mutex g_plugin_mutex;
+const ObjectivePlugin *g_plugins[kMaxPlugins];
+std::atomic<int> g_plugin_count{0};
 const ObjectivePlugin *plugin_for(int objective) {
   const int k = objective - kFirstPluginId;
-  return (k >= 0 && k < int(plugin_registry().size())) ? plugin_registry()[k] : nullptr;
+  return (k >= 0 && k < g_plugin_count.load(std::memory_order_acquire)) ? g_plugins[k] : nullptr;
 }
 bool objective_known(int objective) {
   return (objective >= 0 && objective < NLS_OBJECTIVE_COUNT) || plugin_for(objective) != nullptr;
@@ -101,10 +107,20 @@ struct nls_ctx {
   cudaStream_t stream;
   bool own_stream;
   int sm_count;
-  // Device buffers released by destroyed solver handles, kept for the next solve of the same shape: cudaMalloc /
-  // cudaFree of multi-GB populations cost hundreds of milliseconds, which would dominate repeated minimize() calls.
-  std::vector<std::pair<void *, size_t>> pool;
+  // Device buffers released by destroyed solver handles, kept for the next solve: cudaMalloc / cudaFree of multi-GB
+  // populations cost hundreds of milliseconds, which would dominate repeated minimize() calls.  The pool is bounded:
+  // it never holds more than `pool_limit` bytes (nls_ctx_set_pool_limit), by default no more than the largest single
+  // solver handle released so far, and the oldest entries go first — a sequence of solves of different shapes cannot
+  // pin every population it ever used.
+  std::vector<std::pair<void *, size_t>> pool;   // oldest first
   size_t pool_bytes = 0;
+  size_t pool_limit = 0;        // 0: automatic (the largest single handle released so far)
+  size_t largest_handle = 0;
+  void evict_to(size_t cap) {
+    size_t k = 0;
+    while (pool_bytes > cap && k < pool.size()) { cudaFree(pool[k].first); pool_bytes -= pool[k].second; k++; }
+    pool.erase(pool.begin(), pool.begin() + k);
+  }
 };
 
 namespace {
@@ -136,15 +152,23 @@ struct DeviceBuffers {
       held.push_back({*out, bytes});
       return NLS_OK;
     }
-    if (ctx)
-      for (size_t k = 0; k < ctx->pool.size(); k++)
-        if (ctx->pool[k].second == bytes) {
-          *out = ctx->pool[k].first;
-          ctx->pool_bytes -= bytes;
-          ctx->pool.erase(ctx->pool.begin() + k);
-          held.push_back({*out, bytes});
-          return NLS_OK;
-        }
+    if (ctx) {
+      // best fit: the smallest cached buffer that holds the request without wasting more than half of itself
+      size_t best = ctx->pool.size();
+      for (size_t k = 0; k < ctx->pool.size(); k++) {
+        const size_t have = ctx->pool[k].second;
+        if (have >= bytes && have - bytes <= std::max<size_t>(bytes, size_t(1) << 20) &&
+            (best == ctx->pool.size() || have < ctx->pool[best].second))
+          best = k;
+      }
+      if (best < ctx->pool.size()) {
+        *out = ctx->pool[best].first;
+        held.push_back(ctx->pool[best]);          // remembered with its true size
+        ctx->pool_bytes -= ctx->pool[best].second;
+        ctx->pool.erase(ctx->pool.begin() + best);
+        return NLS_OK;
+      }
+    }
     cudaError_t e = cudaMalloc(out, bytes);
     if (e == cudaErrorMemoryAllocation && ctx && !ctx->pool.empty()) {   // make room: drop the cached buffers, retry
       cudaGetLastError();
@@ -158,6 +182,9 @@ struct DeviceBuffers {
     return NLS_OK;
   }
   void release() {
+    size_t total = 0;
+    for (auto &b : held) total += b.second;
+    if (ctx && !guard_mode()) ctx->largest_handle = std::max(ctx->largest_handle, total);
     for (auto &b : held) {
       if (guard_mode()) {
         char *base = static_cast<char *>(b.first) - kGuardBytes;
@@ -176,6 +203,7 @@ struct DeviceBuffers {
       else cudaFree(b.first);
     }
     held.clear();
+    if (ctx) ctx->evict_to(ctx->pool_limit ? ctx->pool_limit : ctx->largest_handle);
   }
 };
 
@@ -312,6 +340,14 @@ int nls_ctx_trim(nls_ctx *ctx) {
   ctx->pool_bytes = 0;
   return NLS_OK;
 }
+int nls_ctx_set_pool_limit(nls_ctx *ctx, uint64_t bytes) {
+  if (!ctx) return fail(NLS_ERR_INVALID, "nls_ctx_set_pool_limit: NULL context");
+  NLS_CUDA(cudaSetDevice(ctx->device));
+  ctx->pool_limit = bytes;
+  if (bytes) ctx->evict_to(bytes);
+  return NLS_OK;
+}
+uint64_t nls_ctx_pool_bytes(const nls_ctx *ctx) { return ctx ? ctx->pool_bytes : 0; }
 unsigned long long nls_debug_guard_violations(void) { return g_guard_violations; }
 int nls_ctx_device(const nls_ctx *ctx) { return ctx ? ctx->device : -1; }
 int nls_ctx_sm_count(const nls_ctx *ctx) { return ctx ? ctx->sm_count : -1; }
@@ -388,15 +424,14 @@ static int de_build(nls_ctx *ctx, const nls_de_cfg *cfg, const void *x0_host, nl
   NLS_ALLOC(s.dec, P * sizeof(uint4));
   NLS_ALLOC(s.rej, P * sizeof(uint32_t));
   NLS_ALLOC(s.list, P * sizeof(uint32_t));
-  NLS_ALLOC(s.pend[0], P * sizeof(uint32_t));
-  NLS_ALLOC(s.pend[1], P * sizeof(uint32_t));
   NLS_ALLOC(s.ctrl, sizeof(DECtrl));
   NLS_ALLOC(s.part_min, de->g.reduce_blocks * sizeof(double));
   NLS_ALLOC(s.part_idx, de->g.reduce_blocks * sizeof(unsigned long long));
   NLS_ALLOC(s.part_mom, de->g.reduce_blocks * sizeof(Moments));
   if (cfg->flags & NLS_FLAG_RECORD_MASKS) NLS_ALLOC(s.masks, P * d);
   NLS_ALLOC(de->record, nls_record_bytes(cfg->dtype, d));
-  de->staging_bytes = std::min<size_t>(size_t(P) * d * de->elem, size_t(256) << 20);
+  // read-back staging: up to 256 MB, but never less than one row (rows are gathered whole)
+  de->staging_bytes = std::max<size_t>(std::min<size_t>(size_t(P) * d * de->elem, size_t(256) << 20), size_t(d) * de->elem);
   NLS_ALLOC(de->staging, de->staging_bytes);
   NLS_ALLOC(x0_dev, d * de->elem);
 #undef NLS_ALLOC
@@ -547,7 +582,7 @@ int nls_de_read_population(nls_de *de, void *rows_host) {
 
 int nls_de_read_rows(nls_de *de, uint64_t first, uint64_t count, void *rows_host) {
   if (!de || !rows_host) return fail(NLS_ERR_INVALID, "nls_de_read_rows: NULL argument");
-  if (first + count > de->s.P) return fail(NLS_ERR_INVALID, "nls_de_read_rows: range exceeds the population");
+  if (count > de->s.P || first > de->s.P - count) return fail(NLS_ERR_INVALID, "nls_de_read_rows: range exceeds the population");
   NLS_CUDA(cudaSetDevice(de->ctx->device));
   NLS_CUDA(cudaStreamSynchronize(de->ctx->stream));
   return de_read_rows(de, first, count, rows_host);
@@ -654,6 +689,7 @@ static int pso_validate(const nls_pso_cfg *c) {
                   static_cast<unsigned long long>(c->dim));
   if (c->pso_type != NLS_PSO_VANILLA && c->pso_type != NLS_PSO_ACCELERATED) return fail(NLS_ERR_INVALID, "PSO: unknown type %d", c->pso_type);
   if (c->n_particles < 1 || c->dim < 1) return fail(NLS_ERR_INVALID, "PSO: n_particles and dim must be >= 1");
+  if (c->n_particles >= 0xffffffffull || c->dim >= 0xffffffffull) return fail(NLS_ERR_INVALID, "PSO: n_particles (per shard) and dim must fit 32 bits");
   const u64 pg = c->n_particles_global ? c->n_particles_global : c->n_particles;
   if (c->particle_offset + c->n_particles > pg) return fail(NLS_ERR_INVALID, "PSO: shard exceeds the global swarm");
   if (c->pso_type == NLS_PSO_VANILLA && !(c->flags & NLS_FLAG_SOCIAL_INDEX_J) && pg > c->dim)
@@ -1113,12 +1149,20 @@ int nls_load_objective(const char *plugin_path, int32_t *objective_id) {
   entry_t entry = reinterpret_cast<entry_t>(dlsym(h, "nls_objective_plugin_v1"));
   if (!entry) { dlclose(h); return fail(NLS_ERR_INVALID, "nls_load_objective: %s exports no nls_objective_plugin_v1", plugin_path); }
   const ObjectivePlugin *pl = entry();
-  if (!pl || pl->abi != 3 || !pl->de_f64 || !pl->de_f32 || !pl->pso_f64 || !pl->pso_f32 || !pl->sann_f64 || !pl->sann_f32) {
+  // the ABI number is the first field of every plugin generation, so it is checked before anything else is read; the
+  // state structs travel by value into the plugin's launchers, so their sizes must match this build exactly
+  if (!pl || pl->abi != kPluginAbi || pl->de_state_bytes != sizeof(DEState) || pl->pso_state_bytes != sizeof(PSOState) ||
+      pl->sann_state_bytes != sizeof(SANNState) || !pl->de_f64 || !pl->de_f32 || !pl->pso_f64 || !pl->pso_f32 ||
+      !pl->sann_f64 || !pl->sann_f32) {
     dlclose(h);
     return fail(NLS_ERR_INVALID, "nls_load_objective: plugin ABI mismatch (rebuild it against this library's headers)");
   }
-  plugin_registry().push_back(pl);    // the handle stays open for the life of the process
-  *objective_id = kFirstPluginId + int(plugin_registry().size()) - 1;
+  std::lock_guard<std::mutex> lock(g_plugin_mutex);
+  const int n = g_plugin_count.load(std::memory_order_relaxed);
+  if (n >= kMaxPlugins) { dlclose(h); return fail(NLS_ERR_STATE, "nls_load_objective: at most %d plugins per process", kMaxPlugins); }
+  g_plugins[n] = pl;                  // the handle stays open for the life of the process
+  g_plugin_count.store(n + 1, std::memory_order_release);
+  *objective_id = kFirstPluginId + n;
   return NLS_OK;
 }
 

@@ -10,18 +10,21 @@
 //   K2  de_generation_kernel : every agent builds and scores its trial against the PRE-generation rows (full HBM
 //                              bandwidth, no ordering), records donors / dim / rejects, accepts greedily; an accepted
 //                              trial is written to the agent's row in the OTHER buffer, so pre-generation rows stay.
-//   K2r de_repair_kernel     : cooperative kernel.  The "donor r < i" relation is a shallow DAG (depth ~17 at 2^20).
-//                              Round by round, an agent whose lower donors are all final becomes final; if any of
-//                              them was accepted, its trial is re-evaluated against the now-known rows.  Each agent
-//                              is therefore evaluated at most twice and the result equals the sequential loop.
+//   K2r de_repair_kernel     : cooperative kernel, a fixed-point iteration over the "donor r < i" relation: in
+//                              iteration k an agent is re-evaluated iff one of its lower donors changed its visible
+//                              state (accept flag / accepted row) in iteration k - 1, against the rows as they stand.
+//                              Two grid barriers per iteration (scan, re-evaluate); it stops when an iteration
+//                              changed nothing, and the state then equals the sequential loop's (see below).
 //                              Returns at once when the speculative pass accepted nothing.
 //   K3  de_commit_kernel     : commits accepted trials (score, row-location bit), then the population reduction:
 //                              min-loc with the reference's tie rule (nlsolver.h:2432-2437), the std_err statistic
 //                              (nlsolver.h:2037-2052) and the stop test (nlsolver.h:2439-2447), last block finalises.
 #pragma once
 #include <cooperative_groups.h>
+#include <cstdlib>
 #include <math_constants.h>
 
+#include "de_bulk.cuh"
 #include "objectives.cuh"
 #include "reduce.cuh"
 #include "launch.h"
@@ -30,47 +33,58 @@
 namespace nls {
 namespace cg = cooperative_groups;
 
+// fin[i] of an agent whose visible state never changed in this generation (see de_repair_kernel)
+constexpr uint16_t kNeverChanged = 0xFFFFu;
+
 
 // ------------------------------------------------------------------------------------------------ row pass
-template <class T, bool RESOLVED>
-__device__ __forceinline__ const T *de_row_of(const DEState &s, u64 r, u64 i) {
-  u32 w = s.where[r];
-  if (RESOLVED && r < i && s.acc[r]) w ^= 1u;   // a lower donor whose trial was accepted already holds its new row
-  return static_cast<const T *>(s.buf[w]) + r * s.stride;
-}
-
 // One sweep over the d coordinates of agent i's trial (propose_new_agent, nlsolver.h:2357-2375):
 //   trial[j] = mut ? A[r1][j] + F * (A[r2][j] - A[r3][j]) : A[r0][j],   mut = (draw_j < CR) || (j == dim)
-// EVAL accumulates the objective; WRITE stores the trial into `dst`.  Each lane owns V consecutive coordinates per
-// step (one 128-bit load per row); U steps are issued back to back so 4*U loads per lane are in flight.  Lanes past
-// the end of the row read coordinate 0 instead (always valid, one cached line) and are masked out downstream.
+// EVAL accumulates the objective; WRITE stores the trial into `dst`.  W lanes cooperate on the agent (`lane` is the
+// index inside that group); each lane owns V consecutive coordinates per step (one 128-bit load per row) and U steps
+// are issued back to back, so 4 * U loads per lane are in flight.  Lanes past the end of the row read coordinate 0
+// instead (always valid, one cached line) and are masked out downstream.
+//   S = accumulator slots per lane (objectives.cuh): a group of W < 32 lanes that sweeps a row LONGER than one step
+// (d > W * V) keeps S = 32 / W canonical accumulators per lane, step k feeding slot k.  The whole row must then fit
+// the one unrolled iteration (d <= U * W * V, U <= S) so that the slot is a compile-time constant.
+//   SKIP_BASE (long rows): the base row is only loaded where a coordinate of the lane keeps it, which needs the draws
+// before the loads.  Short rows load all four rows FIRST and draw while the loads are in flight: a skipped 16-byte
+// piece saves no DRAM traffic there (128-byte lines), and the ~25 integer instructions per draw are the only
+// independent work a lane has to cover the load latency with.
+//   SHARED_BASE: the base row is the single best row (best recombination, speculative pass): read-only for the launch
+// and shared by every agent, so it goes through L1 instead of being re-fetched from L2 per agent.
 // Tuning (B200, fp64 d=1000 Rastrigin, P=2^20, K2 time): U=2 / 2 blocks per SM 6.29 ms; U=2 / 3 blocks 5.68 ms;
-// U=1 / 4 blocks (64 registers, 32 warps per SM, no spills) 5.63 ms — occupancy beats per-warp unrolling here.
-#ifndef NLS_DE_UNROLL
-#define NLS_DE_UNROLL 1
-#endif
-// W lanes cooperate on the agent (`lane` is the index inside that group); W < 32 requires d <= W * V.
-// SHARED_BASE: the base row is the single best row (best recombination, speculative pass): read-only for the launch and
-// shared by every agent, so it goes through L1 instead of being re-fetched from L2 per agent.
-template <class T, int OBJ, bool EVAL, bool WRITE, int W = 32, bool SHARED_BASE = false>
+// U=1 / 4 blocks (64 registers, 32 warps per SM, no spills) 5.63 ms — occupancy beats per-warp unrolling for long rows.
+template <class T, int OBJ, bool EVAL, bool WRITE, int W = 32, bool SHARED_BASE = false, int U = 1, int S = 1,
+          bool SKIP_BASE = true>
 __device__ __forceinline__ T de_sweep(const DEState &s, const T *p0, const T *p1, const T *p2, const T *p3, T *dst,
                                       u64 sbase, u32 dim, u64 i, int lane) {
   constexpr int V = Vec<T>::V;
-  constexpr int U = NLS_DE_UNROLL;
   constexpr u32 kStride = W * V;                       // coordinates per group step
+  static_assert(S == 1 || U <= S, "with accumulator slots the row is one unrolled iteration: step u feeds slot u");
   typedef Ar<T> A;
   const u32 d = static_cast<u32>(s.d);
   const T F = static_cast<T>(s.F);
   const u64 cr_le = s.cr_le;
   const bool cr_any = !s.cr_none;
   const u32 n_steps = (d + kStride - 1) / kStride;
-  Objective<T, OBJ, W> obj;
+  Objective<T, OBJ, W, S> obj;
   if (EVAL) obj.begin(lane, d);
   u32 j0 = lane * V;                                   // first coordinate of this lane in the current step
   u64 st = sbase + kGolden * j0;                       // draw-stream state of coordinate j0
   for (u32 step = 0; step < n_steps; step += U) {
     T x1[U][V], x2[U][V], x3[U][V], x0[U][V];
     bool mut[U][V];
+    if (!SKIP_BASE) {
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        const u32 jj = j0 + u * kStride;
+        const u32 jl = jj < d ? jj : 0u;
+        ld_row(p1 + jl, x1[u]); ld_row(p2 + jl, x2[u]); ld_row(p3 + jl, x3[u]);
+        if (SHARED_BASE) ld_row_shared(p0 + jl, x0[u]);
+        else ld_row(p0 + jl, x0[u]);
+      }
+    }
 #pragma unroll
     for (int u = 0; u < U; u++) {
       const u32 jj = j0 + u * kStride;
@@ -80,11 +94,13 @@ __device__ __forceinline__ T de_sweep(const DEState &s, const T *p0, const T *p1
         mut[u][q] = (cr_any && mix64(st + kGolden * (u * kStride + q)) <= cr_le) || (jj + q == dim);
         all_mut &= mut[u][q];
       }
-      const u32 jl = jj < d ? jj : 0u;
-      ld_row(p1 + jl, x1[u]); ld_row(p2 + jl, x2[u]); ld_row(p3 + jl, x3[u]);
-      if (!all_mut) {                                  // the base row is only touched where a coordinate keeps it
-        if (SHARED_BASE) ld_row_shared(p0 + jl, x0[u]);
-        else ld_row(p0 + jl, x0[u]);
+      if (SKIP_BASE) {
+        const u32 jl = jj < d ? jj : 0u;
+        ld_row(p1 + jl, x1[u]); ld_row(p2 + jl, x2[u]); ld_row(p3 + jl, x3[u]);
+        if (!all_mut) {                                // the base row is only touched where a coordinate keeps it
+          if (SHARED_BASE) ld_row_shared(p0 + jl, x0[u]);
+          else ld_row(p0 + jl, x0[u]);
+        }
       }
     }
 #pragma unroll
@@ -96,7 +112,7 @@ __device__ __forceinline__ T de_sweep(const DEState &s, const T *p0, const T *p1
         t[q] = mut[u][q] ? A::add(x1[u][q], A::mul(F, A::sub(x2[u][q], x3[u][q]))) : x0[u][q];
       if (WRITE && jj < d) st_row(dst + jj, t);
       if (EVAL) {
-        obj.step(t, jj, d, lane);
+        obj.step(t, jj, d, lane, S == 1 ? 0 : u);
         if (s.masks != nullptr) {
 #pragma unroll
           for (int q = 0; q < V; q++)
@@ -108,27 +124,6 @@ __device__ __forceinline__ T de_sweep(const DEState &s, const T *p0, const T *p1
     st += kGolden * (U * kStride);
   }
   return EVAL ? obj.finish(d) : T(0);
-}
-
-// Build, score and greedily select agent i's trial (loop body nlsolver.h:2459-2471).
-template <class T, int OBJ, bool RESOLVED>
-__device__ __forceinline__ void de_trial(const DEState &s, u64 i, u64 key, u64 r0, u64 r1, u64 r2, u64 r3, u32 dim,
-                                         u32 rej, int lane) {
-  const T *p0 = de_row_of<T, RESOLVED>(s, r0, i);
-  const T *p1 = de_row_of<T, RESOLVED>(s, r1, i);
-  const T *p2 = de_row_of<T, RESOLVED>(s, r2, i);
-  const T *p3 = de_row_of<T, RESOLVED>(s, r3, i);
-  T *dst = static_cast<T *>(s.buf[s.where[i] ^ 1u]) + i * s.stride;
-  const u64 sbase = tape_state(key, 4 + rej);           // draws 0..2+rej: indices, 3+rej: dim, then one per coordinate
-  const T raw = de_sweep<T, OBJ, true, false>(s, p0, p1, p2, p3, dst, sbase, dim, i, lane);
-  const T score = Ar<T>::mul(static_cast<T>(s.fm), raw);
-  const bool ok = score < static_cast<const T *>(s.score)[i];   // strict <, NaN never accepted (nlsolver.h:2466)
-  if (ok)   // re-stream the (L2-warm) donor rows and materialise the trial; ~a few % of agents
-    de_sweep<T, OBJ, false, true>(s, p0, p1, p2, p3, dst, sbase, dim, i, lane);
-  if (lane == 0) {
-    static_cast<T *>(s.tscore)[i] = score;
-    s.acc[i] = ok;
-  }
 }
 
 // ------------------------------------------------------------------------------------------------ K1 init
@@ -181,30 +176,134 @@ __device__ __forceinline__ void de_select_donors(u64 key, u64 P, u64 fixed, u64 
   for (;;) { r3 = index_from<T>(tape_draw(key, k++), P); if (r3 != fixed && r3 != r1 && r3 != r2) break; rej++; }
 }
 
-#ifndef NLS_DE_MINBLOCKS
-#define NLS_DE_MINBLOCKS 4
-#endif
 // What the lane-parallel prologue hands to the cooperative part, one entry per agent of the tile (shared memory).
 struct __align__(16) DETileEntry {
   unsigned long long key;      // draw stream of (generation, agent)
-  unsigned int r1, r2, r3;     // donors ids[1..3]
+  const void *p0, *p1, *p2, *p3;   // the rows of ids[0..3] this evaluation reads
+  double score;                // scores[i] (T widened)
+  unsigned int agent;          // local agent index i
   unsigned int dim;            // forced crossover coordinate
   unsigned int rej;            // rejected index proposals
-  unsigned int wbits;          // where[] of ids[0], r1, r2, r3 and of the agent itself (bits 0..4)
-  double score;                // scores[i] (T widened)
+  unsigned int flags;          // bit 0: where[i] (an accepted trial goes to the OTHER buffer); bit 1: acc[i] before
 };
+static_assert(sizeof(DETileEntry) == 64, "four 128-bit shared-memory loads per entry");
 
-// A warp owns a TILE of 32 consecutive agents:
-//   prologue  — one agent per lane: stream key, donor selection, forced coordinate, row-location bits, current score;
+// The lane-parallel prologue of a tile of the speculative pass: lane l prepares agent first + l (generate_indices,
+// nlsolver.h:2331-2355, the forced coordinate, the addresses of the four PRE-generation rows), stores the entry in
+// shared memory and the decisions in global memory.
+template <class T>
+__device__ __forceinline__ void de_tile_prologue(const DEState &s, DETileEntry *tile_entries, u64 gen_key, u64 best_id,
+                                                 bool random_mode, u64 first, int tile_size, int lane) {
+  const u64 mine = first + lane;
+  if (lane < tile_size && mine < s.P) {
+    const char *buf0 = static_cast<const char *>(s.buf[0]), *buf1 = static_cast<const char *>(s.buf[1]);
+    const u64 row_bytes = s.stride * sizeof(T);
+    DETileEntry e;
+    e.key = tape_key(gen_key, s.offset + mine);
+    const u64 fixed = random_mode ? mine : best_id;
+    u64 r1, r2, r3;
+    de_select_donors<T>(e.key, s.P, fixed, r1, r2, r3, e.rej);
+    e.dim = static_cast<u32>(index_from<T>(tape_draw(e.key, 3 + e.rej), s.d));
+    const u32 w0 = s.where[fixed], w1 = s.where[r1], w2 = s.where[r2], w3 = s.where[r3];
+    e.p0 = (w0 ? buf1 : buf0) + fixed * row_bytes;
+    e.p1 = (w1 ? buf1 : buf0) + r1 * row_bytes;
+    e.p2 = (w2 ? buf1 : buf0) + r2 * row_bytes;
+    e.p3 = (w3 ? buf1 : buf0) + r3 * row_bytes;
+    e.score = static_cast<double>(static_cast<const T *>(s.score)[mine]);
+    e.agent = u32(mine);
+    e.flags = s.where[mine];
+    tile_entries[lane] = e;
+    s.dec[mine] = make_uint4(u32(r1), u32(r2), u32(r3), e.dim);
+    s.rej[mine] = e.rej;
+  }
+}
+
+// The prologue of a tile of the repair: lane l prepares list entry first + l from the recorded decisions, with the
+// rows RESOLVED — a lower donor (r < i) whose trial currently counts as accepted contributes its new row.
+template <class T>
+__device__ __forceinline__ void de_tile_prologue_repair(const DEState &s, DETileEntry *tile_entries, u64 gen_key,
+                                                        u64 best_id, bool random_mode, u64 first, u32 n_list,
+                                                        int tile_size, int lane) {
+  const u64 slot = first + lane;
+  if (lane < tile_size && slot < n_list) {
+    const char *buf0 = static_cast<const char *>(s.buf[0]), *buf1 = static_cast<const char *>(s.buf[1]);
+    const u64 row_bytes = s.stride * sizeof(T);
+    const u64 mine = s.list[slot];
+    const uint4 dc = s.dec[mine];
+    DETileEntry e;
+    e.key = tape_key(gen_key, s.offset + mine);
+    e.rej = s.rej[mine];
+    e.dim = dc.w;
+    const u64 r[4] = {random_mode ? mine : best_id, dc.x, dc.y, dc.z};
+    const void *p[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      u32 w = s.where[r[q]];
+      if (r[q] < mine && s.acc[r[q]]) w ^= 1u;
+      p[q] = (w ? buf1 : buf0) + r[q] * row_bytes;
+    }
+    e.p0 = p[0]; e.p1 = p[1]; e.p2 = p[2]; e.p3 = p[3];
+    e.score = static_cast<double>(static_cast<const T *>(s.score)[mine]);
+    e.agent = u32(mine);
+    e.flags = u32(s.where[mine]) | (u32(s.acc[mine]) << 1);
+    tile_entries[lane] = e;
+  }
+}
+
+// The cooperative part of a tile: the prepared agents, 32 / W at a time, W lanes streaming the rows of one agent
+// (de_sweep: trial, objective, greedy selection — loop body nlsolver.h:2459-2471); an accepted trial (a few % of the
+// agents) is re-streamed from the L2-warm rows and written to the agent's row in the other buffer.  The first lane of a
+// group stores the trial score and accept flag and hands the outcome to `done(entry, ok)`.
+template <class T, int OBJ, int W, int U, int S, bool SKIP_BASE, class Done>
+__device__ __forceinline__ void de_tile_body(const DEState &s, const DETileEntry *tile_entries, int n_here,
+                                             bool shared_base, int lane, Done done) {
+  constexpr int G = 32 / W;                              // agents streamed at a time
+  const int grp = lane / W, sub = lane % W;
+  for (int a0 = 0; a0 < n_here; a0 += G) {
+    const bool active = a0 + grp < n_here;               // idle groups redo the first agent, nothing is stored
+    const DETileEntry e = tile_entries[active ? a0 + grp : a0];   // broadcast read inside the group
+    const u64 i = e.agent;
+    const T *p0 = static_cast<const T *>(e.p0), *p1 = static_cast<const T *>(e.p1);
+    const T *p2 = static_cast<const T *>(e.p2), *p3 = static_cast<const T *>(e.p3);
+    const u64 sbase = tape_state(e.key, 4 + e.rej);     // draws 0..2+rej: indices, 3+rej: dim, then one per coordinate
+    // (warp-uniform branch: in the speculative pass of best mode every base row is the pre-generation best row)
+    const T raw = shared_base
+                      ? de_sweep<T, OBJ, true, false, W, true, U, S, SKIP_BASE>(s, p0, p1, p2, p3, nullptr, sbase, e.dim, i, sub)
+                      : de_sweep<T, OBJ, true, false, W, false, U, S, SKIP_BASE>(s, p0, p1, p2, p3, nullptr, sbase, e.dim, i, sub);
+    const T sc = Ar<T>::mul(static_cast<T>(s.fm), raw);
+    const bool ok = active && sc < static_cast<T>(e.score);   // strict <, NaN never accepted (nlsolver.h:2466)
+    if (ok) {
+      T *dst = static_cast<T *>(s.buf[(e.flags & 1u) ^ 1u]) + i * s.stride;
+      de_sweep<T, OBJ, false, true, W, false, U, S, SKIP_BASE>(s, p0, p1, p2, p3, dst, sbase, e.dim, i, sub);
+    }
+    if (active && sub == 0) {
+      static_cast<T *>(s.tscore)[i] = sc;
+      s.acc[i] = ok;
+      done(e, ok);
+    }
+  }
+}
+
+// A warp owns a TILE of up to 32 consecutive agents:
+//   prologue  — one agent per lane: stream key, donor selection, forced coordinate, row addresses, current score;
 //               the per-agent scalar work and its dependent loads run 32 agents wide instead of 32 times redundantly;
-//   body      — the 32 agents one after the other, all lanes streaming the rows of one agent (de_sweep);
-//   epilogue  — one agent per lane again: coalesced stores of trial score / accept flag.
+//   body      — the agents of the tile, 32 / W at a time, W lanes streaming the rows of one agent (de_sweep); the
+//               first lane of a group stores the agent's trial score / accept flag / repair stamp.
 // The tile size (2^tile_shift <= 32 agents) is chosen by the launcher so that every warp gets many tiles: with 32-agent
 // tiles a population of 2^18 would give 1.7 tiles per resident warp and a 15 % tail.
-// W lanes per agent in the body: 32, or 16 / 8 / 4 when one step of W lanes covers the row (d <= W * V) — then the warp
-// streams 32 / W agents of the tile at a time instead of leaving lanes idle.
-template <class T, int OBJ, int W>
-__global__ void __launch_bounds__(kBlock, NLS_DE_MINBLOCKS) de_generation_kernel(DEState s, int tile_shift) {
+// Lane-group shapes (de_launch_k2): W = 4 / 8 lanes with one step when it covers the row; W = 8 / 16 / 32 lanes with
+// U = 2 steps and S = 32 / W accumulator slots for rows of up to 16 / 32 / 64 vectors (fp32 d = 64, fp64 d = 64, ...) —
+// twice the loads in flight per lane and the per-agent overhead spread over twice the coordinates; W = 32, U = 1 with
+// the base-row skip for long rows.
+#ifndef NLS_DE_BULK_STAGES
+#define NLS_DE_BULK_STAGES 3
+#endif
+#ifndef NLS_DE_BULK_STEPS
+#define NLS_DE_BULK_STEPS 2
+#endif
+template <int U> struct DEBlocksPerSM { static constexpr int value = U >= 2 ? 3 : 4; };
+template <class T, int OBJ, int W, int U, int S, bool SKIP_BASE>
+__global__ void __launch_bounds__(kBlock, DEBlocksPerSM<U>::value) de_generation_kernel(DEState s, int tile_shift) {
   __shared__ DETileEntry tile_mem[kWarpsPerBlock][32];
   DECtrl *ctrl = s.ctrl;
   if (ctrl->stop) return;
@@ -214,86 +313,163 @@ __global__ void __launch_bounds__(kBlock, NLS_DE_MINBLOCKS) de_generation_kernel
   const u64 gen_key = tape_gen_key(s.seed, ctrl->iter + 1), best_id = ctrl->best_id;
   const bool random_mode = s.strategy != 0;             // NLS_DE_RANDOM = 1: ids[0] = i; best: ids[0] = best_id
   const u64 P = s.P, tile_size = 1ull << tile_shift, n_tiles = (P + tile_size - 1) >> tile_shift;
-  const T *score = static_cast<const T *>(s.score);
+  u32 n_ok = 0;
   for (u64 tile = warp; tile < n_tiles; tile += n_warps) {
-    const u64 first = tile << tile_shift, mine = first + lane;
-    const bool own = lane < int(tile_size) && mine < P;   // this lane carries an agent in the prologue / epilogue
-    // ---- prologue
-    bool level0 = true;
-    if (own) {
-      DETileEntry e;
-      e.key = tape_key(gen_key, s.offset + mine);
-      const u64 fixed = random_mode ? mine : best_id;
-      u64 r1, r2, r3;
-      de_select_donors<T>(e.key, P, fixed, r1, r2, r3, e.rej);
-      e.dim = static_cast<u32>(index_from<T>(tape_draw(e.key, 3 + e.rej), s.d));
-      e.r1 = u32(r1); e.r2 = u32(r2); e.r3 = u32(r3);
-      e.wbits = u32(s.where[fixed]) | (u32(s.where[r1]) << 1) | (u32(s.where[r2]) << 2) | (u32(s.where[r3]) << 3) |
-                (u32(s.where[mine]) << 4);
-      e.score = static_cast<double>(score[mine]);
-      tile_entries[lane] = e;
-      s.dec[mine] = make_uint4(e.r1, e.r2, e.r3, e.dim);
-      s.rej[mine] = e.rej;
-      // agents without a lower donor are final as they stand: repair round 1 is decided here
-      level0 = r1 > mine && r2 > mine && r3 > mine && (random_mode || best_id >= mine);
-      s.fin[mine] = level0 ? 1 : 0;
-    }
-    {   // everybody else goes on the repair's first pending list (order is irrelevant)
-      const u32 vote = __ballot_sync(kFull, own && !level0);
-      if (vote) {
-        u32 slot = 0;
-        if (lane == 0) slot = atomicAdd(&ctrl->pending[1], __popc(vote));   // consumed by repair round 2
-        slot = __shfl_sync(kFull, slot, 0);
-        if (own && !level0) s.pend[0][slot + __popc(vote & ((1u << lane) - 1u))] = u32(mine);
+    const u64 first = tile << tile_shift;
+    de_tile_prologue<T>(s, tile_entries, gen_key, best_id, random_mode, first, int(tile_size), lane);
+    __syncwarp();
+    const int n_here = (P - first) < tile_size ? int(P - first) : int(tile_size);
+    de_tile_body<T, OBJ, W, U, S, SKIP_BASE>(s, tile_entries, n_here, !random_mode, lane, [&](const DETileEntry &e, bool ok) {
+      s.fin[e.agent] = ok ? uint16_t(0) : kNeverChanged;     // pass 0 of the repair's fixed-point iteration
+      n_ok += ok;
+    });
+    __syncwarp();                                          // tile_entries is rewritten by the next tile's prologue
+  }
+  n_ok = __reduce_add_sync(kFull, n_ok);
+  if (lane == 0 && n_ok) atomicAdd(&ctrl->spec_accepted, n_ok);
+}
+
+// ------------------------------------------------------------------------------------------------ K2, TMA-staged
+// The same generation pass for long rows, the four rows of every agent staged through shared memory by bulk copies
+// (de_bulk.cuh).  One warp per agent; kSteps sweep steps per chunk; a ring of kStages chunks per warp that runs across
+// the agents of the tile.  The base row is staged whole like the donors (in best mode it is the single best row and
+// comes out of L2; in random mode that costs the ~3 % of traffic the LDG version saves by skipping fully mutated
+// 128-byte lines).  An accepted trial is materialised by the ordinary second sweep.
+template <class T, int OBJ, int kStages, int kSteps>
+__global__ void __launch_bounds__(kBlock, 2) de_generation_bulk_kernel(DEState s, int tile_shift) {
+  constexpr int V = Vec<T>::V;
+  constexpr u32 kStride = 32 * V;                        // coordinates per sweep step
+  constexpr u32 kChunkBytes = 512u * kSteps;             // per row and stage
+  constexpr u32 kStageBytes = 4u * kChunkBytes;
+  extern __shared__ __align__(128) unsigned char bulk_smem[];
+  __shared__ DETileEntry tile_mem[kWarpsPerBlock][32];
+  __shared__ __align__(8) unsigned long long bars[kWarpsPerBlock][kStages];
+  typedef Ar<T> A;
+  DECtrl *ctrl = s.ctrl;
+  if (ctrl->stop) return;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  DETileEntry *tile_entries = tile_mem[wib];
+  unsigned long long *bar = bars[wib];
+  unsigned char *ring = bulk_smem + size_t(wib) * kStages * kStageBytes;
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < kStages; k++) mbar_init(bar + k, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  const u64 warp = (u64(blockIdx.x) * kBlock + threadIdx.x) >> 5, n_warps = (u64(gridDim.x) * kBlock) >> 5;
+  const u64 gen_key = tape_gen_key(s.seed, ctrl->iter + 1), best_id = ctrl->best_id;
+  const bool random_mode = s.strategy != 0;
+  const u64 P = s.P, tile_size = 1ull << tile_shift, n_tiles = (P + tile_size - 1) >> tile_shift;
+  const u32 d = static_cast<u32>(s.d);
+  const u32 row_bytes = static_cast<u32>(s.stride * sizeof(T));
+  const u32 n_chunks = (row_bytes + kChunkBytes - 1) / kChunkBytes;
+  const T F = static_cast<T>(s.F);
+  const u64 cr_le = s.cr_le;
+  const bool cr_any = !s.cr_none;
+  u32 phases = 0;                                        // parity each stage's barrier completes with next
+  u32 n_ok = 0;
+  for (u64 tile = warp; tile < n_tiles; tile += n_warps) {
+    const u64 first = tile << tile_shift;
+    de_tile_prologue<T>(s, tile_entries, gen_key, best_id, random_mode, first, int(tile_size), lane);
+    __syncwarp();
+    const int n_here = (P - first) < tile_size ? int(P - first) : int(tile_size);
+    // producer cursor: (agent of the tile, chunk of its rows, stage); the ring is empty at a tile boundary
+    int pa = 0;
+    u32 pc = 0, pstage = 0, cstage = 0;
+    auto produce = [&]() {
+      if (pa >= n_here) return;
+      if (lane == 0) {
+        const DETileEntry &pe = tile_entries[pa];
+        const u32 off = pc * kChunkBytes;
+        const u32 bytes = row_bytes - off < kChunkBytes ? row_bytes - off : kChunkBytes;
+        unsigned char *st = ring + pstage * kStageBytes;
+        fence_proxy_async();
+        mbar_arrive_expect_tx(bar + pstage, 4u * bytes);
+        bulk_load(st, static_cast<const char *>(pe.p0) + off, bytes, bar + pstage);
+        bulk_load(st + kChunkBytes, static_cast<const char *>(pe.p1) + off, bytes, bar + pstage);
+        bulk_load(st + 2 * kChunkBytes, static_cast<const char *>(pe.p2) + off, bytes, bar + pstage);
+        bulk_load(st + 3 * kChunkBytes, static_cast<const char *>(pe.p3) + off, bytes, bar + pstage);
+      }
+      pstage = pstage + 1 == kStages ? 0 : pstage + 1;
+      if (++pc == n_chunks) { pc = 0; pa++; }
+    };
+#pragma unroll
+    for (int k = 0; k < kStages - 1; k++) produce();
+    for (int a = 0; a < n_here; a++) {
+      const DETileEntry e = tile_entries[a];
+      const u64 i = e.agent;
+      Objective<T, OBJ, 32, 1> obj;
+      obj.begin(lane, d);
+      u32 j0 = lane * V;
+      u64 st = tape_state(e.key, 4 + e.rej) + kGolden * j0;
+      for (u32 c = 0; c < n_chunks; c++) {
+        produce();                                         // refills the stage that was consumed one iteration ago
+        mbar_wait(bar + cstage, (phases >> cstage) & 1u);
+        phases ^= 1u << cstage;
+        const unsigned char *sb = ring + cstage * kStageBytes + lane * 16;
+#pragma unroll
+        for (int u = 0; u < kSteps; u++) {
+          const u32 jj = j0 + u * kStride;
+          T x0[V], x1[V], x2[V], x3[V], t[V];
+          lds_row(sb + u * 512, x0);
+          lds_row(sb + kChunkBytes + u * 512, x1);
+          lds_row(sb + 2 * kChunkBytes + u * 512, x2);
+          lds_row(sb + 3 * kChunkBytes + u * 512, x3);
+#pragma unroll
+          for (int q = 0; q < V; q++) {
+            const bool mut = (cr_any && mix64(st + kGolden * (u * kStride + q)) <= cr_le) || (jj + q == e.dim);
+            t[q] = mut ? A::add(x1[q], A::mul(F, A::sub(x2[q], x3[q]))) : x0[q];
+            if (s.masks != nullptr && jj + q < d) s.masks[i * d + jj + q] = mut;
+          }
+          obj.step(t, jj, d, lane);
+        }
+        j0 += kSteps * kStride;
+        st += kGolden * (kSteps * kStride);
+        __syncwarp();                                      // every lane has read the stage before it is refilled
+        cstage = cstage + 1 == kStages ? 0 : cstage + 1;
+      }
+      const T sc = A::mul(static_cast<T>(s.fm), obj.finish(d));
+      const bool ok = sc < static_cast<T>(e.score);        // strict <, NaN never accepted (nlsolver.h:2466)
+      if (ok)
+        de_sweep<T, OBJ, false, true, 32, false, 1, 1, true>(s, static_cast<const T *>(e.p0), static_cast<const T *>(e.p1),
+                                                             static_cast<const T *>(e.p2), static_cast<const T *>(e.p3),
+                                                             static_cast<T *>(s.buf[(e.flags & 1u) ^ 1u]) + i * s.stride,
+                                                             tape_state(e.key, 4 + e.rej), e.dim, i, lane);
+      if (lane == 0) {
+        static_cast<T *>(s.tscore)[i] = sc;
+        s.acc[i] = ok;
+        s.fin[i] = ok ? uint16_t(0) : kNeverChanged;
+        n_ok += ok;
       }
     }
     __syncwarp();
-    // ---- body
-    const int n_here = (P - first) < tile_size ? int(P - first) : int(tile_size);
-    T my_score = T(0);
-    bool my_ok = false;
-    constexpr int G = 32 / W;                              // agents streamed at a time
-    const int grp = lane / W, sub = lane % W;
-    for (int a0 = 0; a0 < n_here; a0 += G) {
-      const bool active = a0 + grp < n_here;               // idle groups redo the first agent, results discarded
-      const int a = active ? a0 + grp : a0;
-      const DETileEntry e = tile_entries[a];               // broadcast read inside the group
-      const u64 i = first + a;
-      const u64 r0 = random_mode ? i : best_id;
-      const T *p0 = static_cast<const T *>(s.buf[e.wbits & 1u]) + r0 * s.stride;
-      const T *p1 = static_cast<const T *>(s.buf[(e.wbits >> 1) & 1u]) + u64(e.r1) * s.stride;
-      const T *p2 = static_cast<const T *>(s.buf[(e.wbits >> 2) & 1u]) + u64(e.r2) * s.stride;
-      const T *p3 = static_cast<const T *>(s.buf[(e.wbits >> 3) & 1u]) + u64(e.r3) * s.stride;
-      T *dst = static_cast<T *>(s.buf[((e.wbits >> 4) & 1u) ^ 1u]) + i * s.stride;
-      const u64 sbase = tape_state(e.key, 4 + e.rej);
-      // (warp-uniform branch: in best mode every agent's base row is the pre-generation best row)
-      const T raw = random_mode ? de_sweep<T, OBJ, true, false, W, false>(s, p0, p1, p2, p3, dst, sbase, e.dim, i, sub)
-                                : de_sweep<T, OBJ, true, false, W, true>(s, p0, p1, p2, p3, dst, sbase, e.dim, i, sub);
-      const T sc = Ar<T>::mul(static_cast<T>(s.fm), raw);
-      const bool ok = active && sc < static_cast<T>(e.score);   // strict <, NaN never accepted (nlsolver.h:2466)
-      if (ok) de_sweep<T, OBJ, false, true, W>(s, p0, p1, p2, p3, dst, sbase, e.dim, i, sub);
-      // hand the outcome of agent a0 + g to lane a0 + g (its owner in the epilogue)
-#pragma unroll
-      for (int g = 0; g < G; g++) {
-        const T sc_g = __shfl_sync(kFull, sc, g * W);
-        const bool ok_g = __shfl_sync(kFull, int(ok), g * W) != 0;
-        if (lane == a0 + g) { my_score = sc_g; my_ok = ok_g; }
-      }
-    }
-    // ---- epilogue
-    if (own) {
-      static_cast<T *>(s.tscore)[mine] = my_score;
-      s.acc[mine] = my_ok;
-    }
-    const u32 n_ok = __popc(__ballot_sync(kFull, my_ok));
-    if (lane == 0 && n_ok) atomicAdd(&ctrl->spec_accepted, n_ok);
-    __syncwarp();                                          // tile_entries is rewritten by the next tile's prologue
   }
+  if (lane == 0 && n_ok) atomicAdd(&ctrl->spec_accepted, n_ok);
 }
 
 // ------------------------------------------------------------------------------------------------ K2r repair
-template <class T, int OBJ>
-__global__ void __launch_bounds__(kBlock) de_repair_kernel(DEState s) {
+// Exact in-place semantics as a fixed point.  After the speculative pass (iteration 0) fin[i] holds the last iteration
+// in which agent i's VISIBLE state — its accept flag and, if accepted, its new row — may have changed (kNeverChanged:
+// the agent was never accepted).  Iteration k >= 1 re-evaluates every agent that has a lower donor r (r < i, the only
+// donors whose new state the sequential loop lets i see, nlsolver.h:2466-2471) with fin[r] == k - 1, against the rows
+// as they stand (RESOLVED lookup), and stamps fin[i] = k if it was or now is accepted.  The iteration stops when nothing
+// was stamped.
+//   Why this equals the sequential loop: let L be the last iteration in which a lower donor of i was stamped.  In
+// iteration L + 1 agent i is re-evaluated (fin[r] == L is stable: a re-stamp would be a later change), and no lower
+// donor changes visibly while it reads them, so it sees exactly the final states of everything below it; by induction
+// over i those are the sequential loop's states.  Evaluations made EARLIER than that may have read rows in flux (a
+// donor re-evaluated in the same iteration) — their results are garbage by design and always overwritten, because the
+// donor that was in flux stamps itself and so re-triggers its dependents.  With no lower donor ever stamped, the
+// speculative result stands.  Cost: two grid barriers per iteration; the hit sets shrink geometrically (about 1.5 a P,
+// then 3 a of that, ...) and the number of iterations is bounded by the depth of the "donor r < i" DAG (~17 at 2^20).
+// Each iteration is two phases with a grid barrier after each: SCAN (one thread per agent: which agents have a lower
+// donor stamped in the previous iteration?  hits go to a list through warp-aggregated atomics) and RE-EVALUATE (the
+// listed agents spread evenly over all lane groups of the grid — a tile-local loop left most warps idle behind the few
+// that drew several hits: 9.6 % issue utilisation at a 5 % hit rate).
+template <class T, int OBJ, int W, int U, int S, bool SKIP_BASE>
+__global__ void __launch_bounds__(kBlock, DEBlocksPerSM<U>::value) de_repair_kernel(DEState s) {
+  __shared__ DETileEntry tile_mem[kWarpsPerBlock][32];
   cg::grid_group grid = cg::this_grid();
   DECtrl *ctrl = s.ctrl;
   if (ctrl->stop) return;                                // uniform over the grid: only K3 changes it
@@ -301,126 +477,67 @@ __global__ void __launch_bounds__(kBlock) de_repair_kernel(DEState s) {
   // sequential one (induction over the agent index) — nothing to repair.
   if (*reinterpret_cast<volatile unsigned int *>(&ctrl->spec_accepted) == 0) return;
   const int lane = threadIdx.x & 31;
+  DETileEntry *tile_entries = tile_mem[threadIdx.x >> 5];
   const u64 tid = u64(blockIdx.x) * kBlock + threadIdx.x, n_threads = u64(gridDim.x) * kBlock;
   const u64 warp = tid >> 5, n_warps = n_threads >> 5;
   const u64 gen_key = tape_gen_key(s.seed, ctrl->iter + 1), best_id = ctrl->best_id;
   const bool best_mode = s.strategy == 0;
-  u32 reruns = 0, round = 2;                             // round 1 (agents without lower donors) was decided by K2
-  // Round r consumes the pending list produced by round r - 1 (buffer pend[r & 1], length pending[(r - 1) % 3]; K2
-  // produced the first one) and produces pend[(r & 1) ^ 1] / pending[r % 3] plus the re-evaluation list
-  // list / list_count[r % 3].  Three counter slots let thread 0 recycle slot (r + 1) % 3 between the two barriers of
-  // round r: its last reader finished a round ago, its next writer starts after the second barrier.
-  for (;; round++) {
-    const u32 cur = round % 3u, prev = (round + 2u) % 3u, nxt = (round + 1u) % 3u;
-    const u32 *pin = s.pend[round & 1u];
-    u32 *pout = s.pend[(round & 1u) ^ 1u];
-    // phase A: classify the pending agents.  A donor is "final for this round" iff it was finalised in an EARLIER
-    // round (0 < fin < round), which makes the outcome independent of the order in which threads run.
-    const u32 n_in = *reinterpret_cast<volatile unsigned int *>(&ctrl->pending[prev]);
-    // Phase A is a chain of dependent L2 reads per entry (list -> donors -> their state -> their donors -> state), so
-    // each thread walks UA entries at once with the loads of one level issued together (predicated, no branches).
-    constexpr int UA = 2;
-    for (u64 base = warp * (32 * UA); base < n_in; base += n_warps * (32 * UA)) {
-      u32 ii[UA];
-      bool valid[UA], wait[UA], dirty[UA];
-      uint4 dc[UA];
+  const u64 P = s.P;
+  u32 k = 1;
+  for (;; k++) {
+    const u32 want = k - 1, cur = k % 3u;
+    // ---- scan
+    for (u64 base = warp << 5; base < P; base += n_threads) {
+      const u64 mine = base + lane;
+      bool hit = false;
+      if (mine < P) {
+        const uint4 dc = s.dec[mine];
+        const u32 don[4] = {dc.x, dc.y, dc.z, u32(best_id)};
 #pragma unroll
-      for (int u = 0; u < UA; u++) {
-        const u64 idx = base + u * 32 + lane;
-        valid[u] = idx < n_in;
-        ii[u] = valid[u] ? pin[idx] : 0u;
-      }
-#pragma unroll
-      for (int u = 0; u < UA; u++) dc[u] = s.dec[ii[u]];
-      // level 1: the (up to four) lower donors of the entry
-      u32 don[UA][4], f1[UA][4];
-      bool low[UA][4];
-#pragma unroll
-      for (int u = 0; u < UA; u++) {
-        don[u][0] = dc[u].x; don[u][1] = dc[u].y; don[u][2] = dc[u].z; don[u][3] = u32(best_id);
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-          low[u][k] = valid[u] && don[u][k] < ii[u] && (k < 3 || best_mode);
-          f1[u][k] = low[u][k] ? u32(s.fin[don[u][k]]) : 1u;
+        for (int q = 0; q < 4; q++) {
+          const bool low = don[q] < mine && (q < 3 || best_mode);
+          // (predicated load: the stamp of a donor that is not lower is never needed)
+          const u32 f = low ? u32(__ldcg(s.fin + don[q])) : 0x10000u;
+          hit |= f == want;
         }
       }
-      // A donor is "settled" iff it was finalised in an EARLIER round (0 < fin < round): everything read here was
-      // written before this round's barrier, so the outcome does not depend on the order in which threads run.
-      u32 a1[UA][4];
-      uint4 dd[UA][4];
-      bool deep[UA][4];
-#pragma unroll
-      for (int u = 0; u < UA; u++)
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-          const bool settled = f1[u][k] != 0 && f1[u][k] < round;
-          deep[u][k] = low[u][k] && !settled;
-          a1[u][k] = low[u][k] ? u32(s.acc[don[u][k]]) : 0u;        // speculative / settled accept flag of the donor
-          dd[u][k] = deep[u][k] ? s.dec[don[u][k]] : make_uint4(0, 0, 0, 0);
-        }
-      // level 2: a donor r that is still pending is looked through — if all of ITS lower donors are settled and none of
-      // them was accepted, r becomes final this round WITHOUT re-evaluation, i.e. with the accept flag it already has,
-      // and the entry can rely on that now instead of waiting a round (two DAG levels per barrier).
-#pragma unroll
-      for (int u = 0; u < UA; u++) {
-        wait[u] = false; dirty[u] = false;
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-          bool clean = true;
-          if (deep[u][k]) {
-            const u32 r = don[u][k];
-            const u32 q[4] = {dd[u][k].x, dd[u][k].y, dd[u][k].z, u32(best_id)};
-#pragma unroll
-            for (int m = 0; m < 4; m++) {
-              const bool lowq = q[m] < r && (m < 3 || best_mode);
-              const u32 fq = lowq ? u32(s.fin[q[m]]) : 1u;
-              const u32 aq = lowq ? u32(s.acc[q[m]]) : 0u;
-              clean &= (fq != 0 && fq < round) && aq == 0;
-            }
-          }
-          if (low[u][k]) {
-            if (deep[u][k] && !clean) wait[u] = true;
-            else dirty[u] |= a1[u][k] != 0;
-          }
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < UA; u++) {
-        const bool w_ = valid[u] && wait[u];
-        const bool rerun = valid[u] && !wait[u] && dirty[u];
-        if (valid[u] && !wait[u]) s.fin[ii[u]] = uint16_t(round);
-        const u32 vote_w = __ballot_sync(kFull, w_), vote_r = __ballot_sync(kFull, rerun);
-        if (vote_w | vote_r) {
-          u32 slot_w = 0, slot_r = 0;
-          if (lane == 0) {
-            if (vote_w) slot_w = atomicAdd(&ctrl->pending[cur], __popc(vote_w));
-            if (vote_r) slot_r = atomicAdd(&ctrl->list_count[cur], __popc(vote_r));
-          }
-          slot_w = __shfl_sync(kFull, slot_w, 0);
-          slot_r = __shfl_sync(kFull, slot_r, 0);
-          const u32 below = (1u << lane) - 1u;
-          if (w_) pout[slot_w + __popc(vote_w & below)] = ii[u];
-          if (rerun) s.list[slot_r + __popc(vote_r & below)] = ii[u];
-        }
+      const u32 vote = __ballot_sync(kFull, hit);
+      if (vote) {
+        u32 slot = 0;
+        if (lane == 0) slot = atomicAdd(&ctrl->list_count[cur], __popc(vote));
+        slot = __shfl_sync(kFull, slot, 0);
+        if (hit) s.list[slot + __popc(vote & ((1u << lane) - 1u))] = u32(mine);
       }
     }
     grid.sync();
     const u32 n_list = *reinterpret_cast<volatile unsigned int *>(&ctrl->list_count[cur]);
-    const u32 n_out = *reinterpret_cast<volatile unsigned int *>(&ctrl->pending[cur]);
-    if (tid == 0) { ctrl->pending[nxt] = 0; ctrl->list_count[nxt] = 0; }
-    // phase B: re-evaluate the listed agents against rows that are now known
-    for (u64 e = warp; e < n_list; e += n_warps) {
-      const u64 i = s.list[e];
-      const uint4 dc = s.dec[i];
-      const u64 key = tape_key(gen_key, s.offset + i);
-      de_trial<T, OBJ, true>(s, i, key, best_mode ? best_id : i, dc.x, dc.y, dc.z, dc.w, s.rej[i], lane);
+    // recycle the counter slots iteration k + 2 will use: their last readers passed an earlier barrier, their next
+    // writers start after the barrier that ends this iteration
+    if (tid == 0) { ctrl->list_count[(k + 2u) % 3u] = 0; ctrl->changed[(k + 2u) % 3u] = 0; }
+    if (n_list == 0) break;
+    // ---- re-evaluate: tiles of the list, sized so that every warp gets work (a short list is spread thin)
+    int shift = 5;
+    while (shift > 0 && ((u64(n_list) + (1ull << shift) - 1) >> shift) < 4ull * n_warps) shift--;
+    const u64 tile_size = 1ull << shift, n_tiles = (u64(n_list) + tile_size - 1) >> shift;
+    u32 n_changed = 0;
+    for (u64 tile = warp; tile < n_tiles; tile += n_warps) {
+      const u64 first = tile << shift;
+      de_tile_prologue_repair<T>(s, tile_entries, gen_key, best_id, !best_mode, first, n_list, int(tile_size), lane);
+      __syncwarp();
+      const int n_here = (n_list - first) < tile_size ? int(n_list - first) : int(tile_size);
+      de_tile_body<T, OBJ, W, U, S, SKIP_BASE>(s, tile_entries, n_here, false, lane, [&](const DETileEntry &e, bool ok) {
+        if ((e.flags >> 1) | u32(ok)) { s.fin[e.agent] = uint16_t(k); n_changed++; }
+      });
+      __syncwarp();
     }
-    if (warp == 0) reruns += n_list;
-    if (n_out == 0) break;
-    if (round >= 65000u) { if (tid == 0) ctrl->error = 1; break; }
-    grid.sync();   // phase B's rows / accept flags and the recycled counters are visible to the next round
+    n_changed = __reduce_add_sync(kFull, n_changed);
+    if (lane == 0 && n_changed) atomicAdd(&ctrl->changed[cur], n_changed);
+    if (tid == 0) ctrl->reruns += n_list;
+    grid.sync();
+    if (*reinterpret_cast<volatile unsigned int *>(&ctrl->changed[cur]) == 0) break;
+    if (k >= 65000u) { if (tid == 0) ctrl->error = 1; break; }
   }
-  if (tid == 0) { ctrl->reruns += reruns; ctrl->rounds += round - 1; }
+  if (tid == 0) ctrl->rounds += k;
 }
 
 // ------------------------------------------------------------------------------------------------ K3 commit + reduce
@@ -457,7 +574,7 @@ __global__ void __launch_bounds__(kBlock) de_commit_kernel(DEState s, int mode) 
     ctrl->accepted += ctrl->acc_partial;
     ctrl->acc_partial = 0;
     ctrl->spec_accepted = 0;
-    ctrl->pending[0] = ctrl->pending[1] = ctrl->pending[2] = 0;
+    ctrl->changed[0] = ctrl->changed[1] = ctrl->changed[2] = 0;
     ctrl->list_count[0] = ctrl->list_count[1] = ctrl->list_count[2] = 0;
     if (ctrl->error) reason = reason ? reason : 4;
     ctrl->stop_reason = reason;
@@ -705,26 +822,80 @@ cudaError_t de_launch_init(const DEState &s, const void *x0_dev, const LaunchGeo
   return de_launch_commit<T>(s, 1, g, st);
 }
 
-template <class T, int O, int W>
+template <class T, int O, int W, int U, int S, bool SKIP_BASE>
 void de_launch_k2_w(const DEState &s, const LaunchGeom &g, cudaStream_t st) {
   const u64 want = (s.P + kWarpsPerBlock - 1) / kWarpsPerBlock;
-  const unsigned int grid = clamp_grid(want, u64(g.sm_count) * blocks_per_sm(de_generation_kernel<T, O, W>));
+  auto kernel = de_generation_kernel<T, O, W, U, S, SKIP_BASE>;
+  const unsigned int grid = clamp_grid(want, u64(g.sm_count) * blocks_per_sm(kernel));
   int shift = 5;                                       // largest tile that still gives >= 8 tiles per warp
   while (shift > 0 && ((s.P + (1ull << shift) - 1) >> shift) < 8ull * grid * kWarpsPerBlock) shift--;
-  de_generation_kernel<T, O, W><<<grid, kBlock, 0, st>>>(s, shift);
+  kernel<<<grid, kBlock, 0, st>>>(s, shift);
 }
-// lanes per agent: the smallest of 4 / 8 / 16 whose single step covers the row, else the whole warp
+// NLS_DE_BULK in the environment overrides the staging policy: 0 never, 1 best recombination only (the default),
+// 2 both recombination modes, 3 both and for every row length (tests)
+inline int de_bulk_mode() {
+  const char *e = std::getenv("NLS_DE_BULK");
+  return e ? std::atoi(e) : 1;
+}
+template <class T, int O, int kStages, int kSteps>
+void de_launch_k2_bulk(const DEState &s, const LaunchGeom &g, cudaStream_t st) {
+  auto kernel = de_generation_bulk_kernel<T, O, kStages, kSteps>;
+  constexpr size_t smem = size_t(kWarpsPerBlock) * kStages * 4 * 512 * kSteps;
+  static const int per_sm = [&] {
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    int n = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, kBlock, smem);
+    return n < 1 ? 1 : n;
+  }();
+  const u64 want = (s.P + kWarpsPerBlock - 1) / kWarpsPerBlock;
+  const unsigned int grid = clamp_grid(want, u64(g.sm_count) * per_sm);
+  int shift = 5;                                       // largest tile that still gives >= 8 tiles per warp
+  while (shift > 0 && ((s.P + (1ull << shift) - 1) >> shift) < 8ull * grid * kWarpsPerBlock) shift--;
+  kernel<<<grid, kBlock, smem, st>>>(s, shift);
+}
+// lane-group shape by row length in 128-bit vectors (see de_generation_kernel)
 template <class T, int O>
 void de_launch_k2(const DEState &s, const LaunchGeom &g, cudaStream_t st) {
   const u64 vecs = (s.d + Vec<T>::V - 1) / Vec<T>::V;   // 128-bit vectors per row
+  if constexpr (closed_form_dim(O) == 0) {
+    const int mode = de_bulk_mode();
+    const bool long_row = vecs > 64;
+    if (mode >= 3 || (long_row && (mode == 2 || (mode == 1 && s.strategy == 0)))) {
+      de_launch_k2_bulk<T, O, NLS_DE_BULK_STAGES, NLS_DE_BULK_STEPS>(s, g, st);
+      return;
+    }
+  }
   if constexpr (closed_form_dim(O) > 0) {               // fixed short vectors: only the 4-lane variant exists
-    de_launch_k2_w<T, O, 4>(s, g, st);
+    de_launch_k2_w<T, O, 4, 1, 1, false>(s, g, st);
     return;
   }
-  if (vecs <= 4) de_launch_k2_w<T, O, 4>(s, g, st);
-  else if (vecs <= 8) de_launch_k2_w<T, O, 8>(s, g, st);
-  else if (vecs <= 16) de_launch_k2_w<T, O, 16>(s, g, st);
-  else de_launch_k2_w<T, O, 32>(s, g, st);
+  if (vecs <= 4) de_launch_k2_w<T, O, 4, 1, 1, false>(s, g, st);
+  else if (vecs <= 8) de_launch_k2_w<T, O, 8, 1, 1, false>(s, g, st);
+  else if (vecs <= 16) de_launch_k2_w<T, O, 8, 2, 4, false>(s, g, st);
+  else if (vecs <= 32) de_launch_k2_w<T, O, 16, 2, 2, false>(s, g, st);
+  else if (vecs <= 64) de_launch_k2_w<T, O, 32, 2, 1, false>(s, g, st);
+  else de_launch_k2_w<T, O, 32, 1, 1, true>(s, g, st);
+}
+
+template <class T, int O, int W, int U, int S, bool SKIP_BASE>
+cudaError_t de_launch_repair_w(const DEState &s, const LaunchGeom &g, cudaStream_t st) {
+  DEState arg = s;
+  void *args[] = {&arg};
+  auto kernel = de_repair_kernel<T, O, W, U, S, SKIP_BASE>;
+  const unsigned int grid = clamp_grid((s.P + kBlock - 1) / kBlock, u64(g.sm_count) * blocks_per_sm(kernel));
+  return cudaLaunchCooperativeKernel(reinterpret_cast<void *>(kernel), dim3(grid), dim3(kBlock), args, 0, st);
+}
+// same lane-group shapes as the speculative pass (de_launch_k2); long rows always take the LDG sweep
+template <class T, int O>
+cudaError_t de_launch_repair(const DEState &s, const LaunchGeom &g, cudaStream_t st) {
+  const u64 vecs = (s.d + Vec<T>::V - 1) / Vec<T>::V;
+  if constexpr (closed_form_dim(O) > 0) return de_launch_repair_w<T, O, 4, 1, 1, false>(s, g, st);
+  if (vecs <= 4) return de_launch_repair_w<T, O, 4, 1, 1, false>(s, g, st);
+  if (vecs <= 8) return de_launch_repair_w<T, O, 8, 1, 1, false>(s, g, st);
+  if (vecs <= 16) return de_launch_repair_w<T, O, 8, 2, 4, false>(s, g, st);
+  if (vecs <= 32) return de_launch_repair_w<T, O, 16, 2, 2, false>(s, g, st);
+  if (vecs <= 64) return de_launch_repair_w<T, O, 32, 2, 1, false>(s, g, st);
+  return de_launch_repair_w<T, O, 32, 1, 1, true>(s, g, st);
 }
 
 // one generation: K2, K2r (cooperative), K3
@@ -737,14 +908,7 @@ cudaError_t de_launch_generation(const DEState &s, const LaunchGeom &g, cudaStre
   e = cudaGetLastError();                                                                                           \
   if (e != cudaSuccess) return e;                                                                                   \
   if (ev) cudaEventRecord(ev[1], st);                                                                               \
-  {                                                                                                                 \
-    DEState arg = s;                                                                                                \
-    void *args[] = {&arg};                                                                                          \
-    const unsigned int grid = clamp_grid((s.P + kBlock - 1) / kBlock,                                               \
-                                         u64(g.sm_count) * blocks_per_sm(de_repair_kernel<T, O>));                  \
-    e = cudaLaunchCooperativeKernel(reinterpret_cast<void *>(de_repair_kernel<T, O>), dim3(grid), dim3(kBlock),     \
-                                    args, 0, st);                                                                   \
-  }
+  e = de_launch_repair<T, O>(s, g, st);
   NLS_OBJ_SWITCH(s.objective, NLS_CALL)
 #undef NLS_CALL
   if (e != cudaSuccess) return e;

@@ -30,10 +30,12 @@
 #include "pso_impl.cuh"
 #include "sann_impl.cuh"
 
-#define NLS_PLUGIN_ABI 3
+#define NLS_PLUGIN_ABI 4
 struct nls_objective_plugin {
   int abi;
   unsigned full_dim;   // 0: separable / pairwise sum of any dimension; D > 0: closed form, the solver's dim must be D
+  // the launchers below take the state structs BY VALUE: a plugin built against other headers must not load
+  unsigned de_state_bytes, pso_state_bytes, sann_state_bytes, _pad;
   const nls::DEOps *de_f64, *de_f32;
   const nls::PSOOps *pso_f64, *pso_f32;
   const nls::SANNOps *sann_f64, *sann_f32;
@@ -51,6 +53,8 @@ struct nls_objective_plugin {
   }                                                                                                      \
   extern "C" __attribute__((visibility("default"))) const nls_objective_plugin *nls_objective_plugin_v1() { \
     static const nls_objective_plugin p = {NLS_PLUGIN_ABI, nls::plugin_full_dim<NAME<double>>::value,    \
+                                           unsigned(sizeof(nls::DEState)), unsigned(sizeof(nls::PSOState)), \
+                                           unsigned(sizeof(nls::SANNState)), 0u,                           \
                                            nls::plugin_de_f64(), nls::plugin_de_f32(),                   \
                                            nls::plugin_pso_f64(), nls::plugin_pso_f32(),                 \
                                            nls::plugin_sann_f64(), nls::plugin_sann_f32()};              \

@@ -21,8 +21,8 @@ struct DECtrl {
   unsigned int acc_partial;     // accepted trials of the generation being committed
   unsigned int spec_accepted;   // trials accepted by the speculative pass K2 (0 => nothing to repair)
   unsigned int _pad2;
-  unsigned int pending[3];      // repair: pending-list length produced in round r, slot r % 3 (K2 fills slot 1)
-  unsigned int list_count[3];   // repair: agents to re-evaluate in round r, slot r % 3
+  unsigned int changed[3];      // repair: agents whose visible state changed in iteration k, slot k % 3
+  unsigned int list_count[3];   // repair: agents to re-evaluate in iteration k, slot k % 3
   Moments score_moments;        // moments of the scores at the last scan (island exchange record)
 };
 
@@ -32,12 +32,11 @@ struct DEState {
   void *score;           // [P] scores[i]
   void *tscore;          // [P] trial score of the generation in flight
   uint8_t *acc;          // [P] trial accepted (in flight) / decisions of the last generation
-  uint16_t *fin;         // [P] repair round in which the agent's outcome became final (0 = pending)
+  uint16_t *fin;         // [P] repair: last iteration in which the agent's accept flag / accepted row changed (0xFFFF: never)
   uint4 *dec;            // [P] {ids[1], ids[2], ids[3], dim}
   uint32_t *rej;         // [P] rejected index proposals (draw offset of the crossover draws = 4 + rej)
   uint8_t *masks;        // [P*d] crossover mask of the last generation, or NULL
-  uint32_t *list;        // [P] repair: agents to re-evaluate in the current round
-  uint32_t *pend[2];     // [P] each: ping-pong lists of agents whose outcome is not final yet
+  uint32_t *list;        // [P] repair: agents to re-evaluate in the current iteration; migration: the top-k picks
   void *topk_scratch;    // migration top-k candidates: ceil(P / 4096) * k (key, visit) pairs
   DECtrl *ctrl;
   // reduction partials [n_partials]

@@ -19,6 +19,18 @@ NLS_EXPORT_OBJECTIVE({name})
 """
 
 
+def headers_digest():
+    """Content hash of every header a plugin compiles against (csrc/*.cuh, csrc/*.h, include/nls_b200.h): a cached
+    plugin built from other kernel templates or state layouts is never reused."""
+    h = hashlib.sha256()
+    csrc = os.path.join(HERE, "csrc")
+    names = sorted(n for n in os.listdir(csrc) if n.endswith((".cuh", ".h")))
+    for path in [os.path.join(csrc, n) for n in names] + [os.path.join(ROOT, "include", "nls_b200.h")]:
+        with open(path, "rb") as f:
+            h.update(path.encode() + b"\0" + f.read())
+    return h.hexdigest()
+
+
 def compile_objective(source, name, out_dir=None, nvcc="nvcc", extra_flags=()):
     """source: C++ text defining `template <class T> struct <name>` with pairwise / lane0_seed / term / finish.
     extra_flags: e.g. ("-fmad=false",) to keep the functor free of FMA contraction (bit-reproducible against a host
@@ -26,7 +38,8 @@ def compile_objective(source, name, out_dir=None, nvcc="nvcc", extra_flags=()):
     out_dir = out_dir or os.path.join(os.path.expanduser("~"), ".cache", "nlsolver_b200", "objectives")
     os.makedirs(out_dir, exist_ok=True)
     text = TEMPLATE.format(source=source, name=name)
-    tag = hashlib.sha256((text + str(L.lib().nls_version()) + repr(tuple(extra_flags))).encode()).hexdigest()[:16]
+    tag = hashlib.sha256((text + str(L.lib().nls_version()) + repr(tuple(extra_flags)) + headers_digest()).encode()
+                         ).hexdigest()[:16]
     cu, so = os.path.join(out_dir, f"{name}_{tag}.cu"), os.path.join(out_dir, f"lib{name}_{tag}.so")
     if not os.path.exists(so):
         with open(cu, "w") as f:

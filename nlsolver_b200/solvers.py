@@ -98,6 +98,14 @@ class Context:
         """Return the cached device buffers of finished solves to the driver."""
         L.check(L.lib().nls_ctx_trim(self._h))
 
+    def set_pool_limit(self, n_bytes):
+        """Bound the cache of released device buffers (0: the default, the largest single handle released so far)."""
+        L.check(L.lib().nls_ctx_set_pool_limit(self._h, n_bytes))
+
+    @property
+    def pool_bytes(self):
+        return L.lib().nls_ctx_pool_bytes(self._h)
+
     def close(self):
         if self._h:
             for child in list(self._children):

@@ -202,3 +202,32 @@ def test_std_err_stop_rule_is_exact_at_the_threshold(ctx, oracle_lib):
         assert (st["iterations"], st["stop_reason"]) == (want["iterations"], want["stop_reason"]), (eps, st, want)
         assert st["f_value"] == want["f_value"]
         pop.close()
+
+
+BULK_CASES = [
+    # dtype, objective, strategy, P, d, G, scale, F   (rows of 1 .. 63 chunks of 1 KB, ragged last chunks, short rows)
+    (B.F64, B.RASTRIGIN, B.DE_RANDOM, 512, 1000, 3, 10.24, 0.8),
+    (B.F64, B.ROSENBROCK, B.DE_BEST, 300, 777, 5, 4.096, 0.8),
+    (B.F64, B.SPHERE, B.DE_RANDOM, 400, 1000, 6, 10.24, 0.2),      # trials are accepted: second sweep + repair
+    (B.F64, B.ROSENBROCK, B.DE_BEST, 96, 4096, 3, 4.096, 0.8),     # the config-4 row
+    (B.F64, B.ACKLEY, B.DE_BEST, 100, 130, 4, 32.768, 0.8),
+    (B.F32, B.SPHERE, B.DE_RANDOM, 200, 3, 6, 10.24, 0.8),         # one 16-byte piece per row
+    (B.F32, B.ROSENBROCK, B.DE_BEST, 150, 513, 4, 4.096, 0.5),
+]
+
+
+@pytest.mark.parametrize("dtype,obj,strategy,P,d,G,scale,F", BULK_CASES)
+def test_de_tma_staged_generation_matches_oracle(ctx, oracle_lib, monkeypatch, dtype, obj, strategy, P, d, G, scale, F):
+    """The generation pass with the rows staged through shared memory by bulk copies (de_generation_bulk_kernel;
+    NLS_DE_BULK=3 forces it for every shape) gives the decisions / rows of the LDG pass: same oracle, same tolerances."""
+    monkeypatch.setenv("NLS_DE_BULK", "3")
+    seed = 0x1234ABCD ^ (P * 7919 + d)
+    x0 = np.full(d, scale)
+    tol = tolerance(dtype, obj)
+    pop = gpu_de(ctx, dtype, obj, strategy, True, P, d, seed, x0, f=F)
+    for g in range(1, G + 1):
+        pop.step(1)
+        st = pop.sync()
+        so, ao = oracle_de(oracle_lib, dtype, obj, strategy, True, P, d, g, seed, x0, f=F)
+        compare_generation(pop, st, so, ao, tol, g, check_decisions=True)
+    pop.close()

@@ -24,7 +24,11 @@ def pso_tol(dtype, obj, ptype):
     exact = ptype == B.PSO_VANILLA and obj in (B.SPHERE, B.ROSENBROCK, B.ROSENBROCK_EX)
     if exact:
         return 0.0
-    return 1e-12 if dtype == B.F64 else 2e-5
+    if dtype == B.F64:
+        return 1e-12
+    # fp32: rnorm is evaluated in double and rounded once, as the reference's rnorm<float> does (nlsolver.h:2479-2485
+    # under libstdc++), so with a + - * objective results agree to 2 ulp of float; cosf / expf objectives keep 2e-5
+    return 2.4e-7 if obj in (B.SPHERE, B.ROSENBROCK, B.ROSENBROCK_EX) else 2e-5
 
 
 CASES = [

@@ -23,8 +23,12 @@ def ctx():
     c.close()
 
 
-def tol_of(dtype):
-    return 1e-12 if dtype == B.F64 else 2e-5
+def tol_of(dtype, obj=None):
+    if dtype == B.F64:
+        return 1e-12
+    # fp32 proposals: rnorm in double, rounded once, like the reference's rnorm<float> (2 ulp of float with a + - *
+    # objective); objectives that call cosf / expf keep the looser fp32 tolerance
+    return 2.4e-7 if obj in (B.SPHERE, B.ROSENBROCK, B.ROSENBROCK_EX) else 2e-5
 
 
 def start_points(n, d, shared, seed):
@@ -81,12 +85,12 @@ def test_sann_chains_match_oracle(ctx, oracle_lib, dtype, obj, minimize, n, d, i
     best = ch.best()
     ch.close()
     so, ao = oracle_chains(oracle_lib, dtype, obj, minimize, n, d, it, ti, tmax, seed, x0, offset=3)
-    assert_chains_match(res, ao, tol_of(dtype))
+    assert_chains_match(res, ao, tol_of(dtype, obj))
     assert st["iterations"] == it and st["stopped"] == 1 and st["stop_reason"] == 1
     assert st["function_calls"] == so["function_calls"] == n * (1 + it * max(ti - 1, 0))
     assert st["best_index"] == 3 + so["best_index"]
-    assert rel_close(st["f_value"], so["f_value"], tol_of(dtype))
-    assert rel_close(best[None, :], ao["x_best"][so["best_index"]][None, :], tol_of(dtype))
+    assert rel_close(st["f_value"], so["f_value"], tol_of(dtype, obj))
+    assert rel_close(best[None, :], ao["x_best"][so["best_index"]][None, :], tol_of(dtype, obj))
 
 
 @pytest.mark.parametrize("path", golden_files("sann_"), ids=os.path.basename)
@@ -99,7 +103,7 @@ def test_sann_chains_match_reference_fixture(ctx, path):
     st = ch.sync()
     res = ch.chains()
     ch.close()
-    tol = tol_of(cfg.dtype)
+    tol = tol_of(cfg.dtype, cfg.objective)
     assert rel_close(res["f_best"], z["f_best"], tol) and rel_close(res["x_best"], z["x_best"], tol)
     assert st["best_index"] == z["best_index"].item() and st["function_calls"] == z["function_calls_total"].item()
     # draws the reference consumed = 2d per candidate + one per Metropolis test, and a Metropolis test happens exactly
@@ -124,7 +128,7 @@ def test_sann_lane_group_width_never_changes_a_decision(ctx, oracle_lib, monkeyp
     res = ch.chains()
     ch.close()
     so, ao = oracle_chains(oracle_lib, dtype, obj, True, n, d, it, 10, 10.0, seed, x0)
-    assert_chains_match(res, ao, tol_of(dtype))
+    assert_chains_match(res, ao, tol_of(dtype, obj))
     monkeypatch.setenv("NLS_SANN_LANES", "32")
     ch = gpu_chains(ctx, dtype, obj, True, n, d, it, 10, 10.0, seed, x0)
     ch.run()

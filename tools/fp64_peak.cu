@@ -1,5 +1,5 @@
 // fp64_peak.cu — measures the FP64 FMA throughput of the GPU (the denominator for the FP64-bound kernels; it is not
-// in MEASURED_PEAKS.json).  nvcc -gencode arch=compute_100a,code=sm_100a -O3 tools/fp64_peak.cu -o tools/fp64_peak
+// in MEASURED_PEAKS.json).  nvcc -cudart shared -gencode arch=compute_100a,code=sm_100a -O3 tools/fp64_peak.cu -o tools/fp64_peak
 #include <cstdio>
 #include <cuda_runtime.h>
 
