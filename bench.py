@@ -247,7 +247,7 @@ class Bench:
 
 
 def short_clocks(c):
-    return {"sm_mhz": c["sm_mhz"], "reasons": c["reasons"]}
+    return {"sm_mhz": c["sm_mhz"], "reasons": c["reasons"], "power_w_max": c["power_w_max"]}
 
 
 def bench_cold_call(b, pop, dim, K):

@@ -221,6 +221,50 @@ NLS_API int nls_xchg_destroy(nls_xchg *x);
 NLS_API int nls_pso_attach_exchange(nls_pso *pso, nls_xchg *x);
 NLS_API int nls_pso_step_fused(nls_pso *pso, uint64_t n_generations);
 
+/* ---- several GPUs from ONE process: device groups ----
+ * The reference is single-threaded C++ with no notion of devices; a C++ caller that wants the whole box gets it here
+ * without a process group: a group opens one context per device and enables peer access between them.
+ *   sharded swarm : contiguous slices of the GLOBAL particle ids per device, draw streams keyed by the global id, the
+ *                   per-generation min-loc exchange done by the fused kernels over peer memory (no host collective):
+ *                   results are identical to the same swarm on one GPU.  The stop statistic std_err is evaluated
+ *                   exactly as the reference does (sequential sums over all shards) whenever it lands near eps.
+ *   islands       : one reference-exact DE population per device (global agent ids rank * pop_size + i); every
+ *                   migrate_every generations the `migrants` best rows move around the ring rank -> rank + 1 over
+ *                   NVLink and replace the receiver's worst rows.  The status is the best island's.
+ * Devices of a group must be distinct (the exchange kernels of different shards wait on one another). */
+typedef struct nls_group nls_group;
+typedef struct nls_pso_sharded nls_pso_sharded;
+typedef struct nls_de_islands nls_de_islands;
+/* devices: n_devices ordinals, or NULL for 0 .. n_devices - 1 */
+NLS_API int nls_group_create(int n_devices, const int *devices, nls_group **out);
+NLS_API int nls_group_destroy(nls_group *g);
+NLS_API int nls_group_size(const nls_group *g);
+/* cfg describes the GLOBAL swarm (n_particles = all particles; particle_offset / n_particles_global are ignored) */
+NLS_API int nls_pso_sharded_create(nls_group *g, const nls_pso_cfg *cfg, const void *lower_host, const void *upper_host,
+                                   nls_pso_sharded **out);
+NLS_API int nls_pso_sharded_step(nls_pso_sharded *h, uint64_t n_generations);
+NLS_API int nls_pso_sharded_sync(nls_pso_sharded *h, nls_status *status);
+NLS_API int nls_pso_sharded_read_best(nls_pso_sharded *h, void *x_host);
+/* the shard of device `rank` (read-back of positions etc. through the nls_pso_read_* calls); owned by `h` */
+NLS_API int nls_pso_sharded_shard(nls_pso_sharded *h, int rank, nls_pso **shard);
+NLS_API int nls_pso_sharded_destroy(nls_pso_sharded *h);
+/* PSO::minimize / maximize over all devices of the group: same arguments and results as nls_pso_solve */
+NLS_API int nls_pso_solve_sharded(nls_group *g, const nls_pso_cfg *cfg, const void *lower_host, const void *upper_host,
+                                  void *x_best_host, nls_status *status);
+/* cfg describes ONE island (pop_size agents per device; agent_offset of island r is cfg->agent_offset + r * pop_size) */
+NLS_API int nls_de_islands_create(nls_group *g, const nls_de_cfg *cfg, const void *x0_host, uint64_t migrate_every,
+                                  uint64_t migrants, nls_de_islands **out);
+NLS_API int nls_de_islands_step(nls_de_islands *h, uint64_t n_generations);
+/* status: f_value / best_index (global agent id) of the best island (lowest rank on ties), iterations of island 0,
+ * function_calls summed over the islands, stopped = every island has stopped */
+NLS_API int nls_de_islands_sync(nls_de_islands *h, nls_status *status);
+NLS_API int nls_de_islands_read_best(nls_de_islands *h, void *x_host);
+NLS_API int nls_de_islands_island(nls_de_islands *h, int rank, nls_de **island);
+NLS_API int nls_de_islands_destroy(nls_de_islands *h);
+/* DE::minimize / maximize as islands over all devices of the group; runs until every island's stop rule has fired */
+NLS_API int nls_de_solve_islands(nls_group *g, const nls_de_cfg *cfg, const void *x0_host, uint64_t migrate_every,
+                                 uint64_t migrants, void *x_best_host, nls_status *status);
+
 /* ---- simulated annealing as a batch of independent chains ----
  * nlsolver::SANN (nlsolver.h:2744-2815) is one sequential chain; chains never interact, so many of them — multi-start
  * from one point, or one start point per chain — run side by side with the reference's loop unchanged inside each.

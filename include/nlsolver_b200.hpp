@@ -356,6 +356,41 @@ inline nls_ctx *default_context() {
   static Holder h;
   return h.ctx;
 }
+// ---- several GPUs from one process -------------------------------------------------------------------------------
+// nlsolver::b200::devices(n) makes every solve that follows use n GPUs (devices 0 .. n - 1) of the box:
+//   PSO  — ONE swarm of n_particles sharded over the devices; the result is identical to the single-GPU solve;
+//   DE   — n islands of pop_size agents each (a DE population does not shard: every agent gathers three random rows),
+//          the `migrants` best rows moving around the ring every `migrate_every` generations; x receives the best
+//          island's best agent.  With n = 1 (the default) a solve is exactly the reference's single population.
+struct group_options {
+  int n_devices = 1;
+  uint64_t migrate_every = 10, migrants = 64;
+};
+inline group_options &options() {
+  static group_options o;
+  return o;
+}
+inline void devices(int n, uint64_t migrate_every = 10, uint64_t migrants = 64) {
+  options().n_devices = n < 1 ? 1 : n;
+  options().migrate_every = migrate_every;
+  options().migrants = migrants;
+}
+inline nls_group *default_group() {
+  struct Holder {
+    nls_group *g = nullptr;
+    int n = 0;
+    ~Holder() { nls_group_destroy(g); }
+  };
+  static Holder h;
+  if (h.n != options().n_devices) {
+    nls_group_destroy(h.g);
+    h.g = nullptr;
+    h.n = 0;
+    check(nls_group_create(options().n_devices, nullptr, &h.g));
+    h.n = options().n_devices;
+  }
+  return h.g;
+}
 // two draws of the user's generator -> 64-bit tape seed (hi word first)
 template <typename RNG>
 uint64_t seed_from(RNG &generator) {
@@ -439,7 +474,11 @@ class DE {
     cfg.seed = b200::seed_from(generator);
     std::vector<scalar_t> best_row(x.size());
     nls_status st{};
-    b200::check(nls_de_solve(b200::default_context(), &cfg, x.data(), best_row.data(), &st));
+    if (b200::options().n_devices > 1)
+      b200::check(nls_de_solve_islands(b200::default_group(), &cfg, x.data(), b200::options().migrate_every,
+                                       b200::options().migrants, best_row.data(), &st));
+    else
+      b200::check(nls_de_solve(b200::default_context(), &cfg, x.data(), best_row.data(), &st));
     x = best_row;                                              // nlsolver.h:2444
     return solver_status<scalar_t>(static_cast<scalar_t>(st.f_value), st.iterations, st.function_calls);
   }
@@ -501,7 +540,10 @@ class PSO {
     cfg.seed = b200::seed_from(generator);
     std::vector<scalar_t> best_row(lower.size());
     nls_status st{};
-    b200::check(nls_pso_solve(b200::default_context(), &cfg, lower.data(), upper.data(), best_row.data(), &st));
+    if (b200::options().n_devices > 1 && n_particles >= size_t(b200::options().n_devices))
+      b200::check(nls_pso_solve_sharded(b200::default_group(), &cfg, lower.data(), upper.data(), best_row.data(), &st));
+    else
+      b200::check(nls_pso_solve(b200::default_context(), &cfg, lower.data(), upper.data(), best_row.data(), &st));
     if (st.best_valid) x = best_row;
     else x.clear();   // the reference assigns a never-filled swarm_best_position (nlsolver.h:2601)
     return solver_status<scalar_t>(static_cast<scalar_t>(st.f_value), st.iterations, st.function_calls);

@@ -13,3 +13,4 @@ from .solvers import (DE, PSO, Ackley, Context, DEPopulation, DESolver, Exchange
                       Rastrigin, RecombinationStrategy, Rosenbrock, RosenbrockExample, SolverStatus, Sphere, de_cfg,
                       default_context, pso_cfg)
 from .solvers import SANN, SANNChains, sann_cfg  # noqa: F401
+from .solvers import DEIslands, DeviceGroup, ShardedSwarm  # noqa: F401

@@ -109,6 +109,23 @@ SYMBOLS = {
     "nls_xchg_destroy": (C.c_int, [P]),
     "nls_pso_attach_exchange": (C.c_int, [P, P]),
     "nls_pso_step_fused": (C.c_int, [P, u64]),
+    "nls_group_create": (C.c_int, [C.c_int, C.POINTER(C.c_int), C.POINTER(P)]),
+    "nls_group_destroy": (C.c_int, [P]),
+    "nls_group_size": (C.c_int, [P]),
+    "nls_pso_sharded_create": (C.c_int, [P, C.POINTER(PSOCfg), P, P, C.POINTER(P)]),
+    "nls_pso_sharded_step": (C.c_int, [P, u64]),
+    "nls_pso_sharded_sync": (C.c_int, [P, C.POINTER(Status)]),
+    "nls_pso_sharded_read_best": (C.c_int, [P, P]),
+    "nls_pso_sharded_shard": (C.c_int, [P, C.c_int, C.POINTER(P)]),
+    "nls_pso_sharded_destroy": (C.c_int, [P]),
+    "nls_pso_solve_sharded": (C.c_int, [P, C.POINTER(PSOCfg), P, P, P, C.POINTER(Status)]),
+    "nls_de_islands_create": (C.c_int, [P, C.POINTER(DECfg), P, u64, u64, C.POINTER(P)]),
+    "nls_de_islands_step": (C.c_int, [P, u64]),
+    "nls_de_islands_sync": (C.c_int, [P, C.POINTER(Status)]),
+    "nls_de_islands_read_best": (C.c_int, [P, P]),
+    "nls_de_islands_island": (C.c_int, [P, C.c_int, C.POINTER(P)]),
+    "nls_de_islands_destroy": (C.c_int, [P]),
+    "nls_de_solve_islands": (C.c_int, [P, C.POINTER(DECfg), P, u64, u64, P, C.POINTER(Status)]),
     "nls_sann_create": (C.c_int, [P, C.POINTER(SANNCfg), P, u64, C.POINTER(P)]),
     "nls_sann_step": (C.c_int, [P, u64]),
     "nls_sann_sync": (C.c_int, [P, C.POINTER(Status)]),

@@ -264,6 +264,7 @@ struct nls_de {
   double timed_ms[3];
   u64 timed_generations;
   GraphCache graph;
+  bool persistent_failed = false;
 };
 
 struct nls_xchg {
@@ -290,6 +291,7 @@ struct nls_pso {
   nls_xchg *xchg;        // fused peer exchange, or NULL
   GraphCache graph;
   size_t elem;
+  bool persistent_failed = false;
 };
 
 extern "C" {
@@ -425,9 +427,11 @@ static int de_build(nls_ctx *ctx, const nls_de_cfg *cfg, const void *x0_host, nl
   NLS_ALLOC(s.rej, P * sizeof(uint32_t));
   NLS_ALLOC(s.list, P * sizeof(uint32_t));
   NLS_ALLOC(s.ctrl, sizeof(DECtrl));
-  NLS_ALLOC(s.part_min, de->g.reduce_blocks * sizeof(double));
-  NLS_ALLOC(s.part_idx, de->g.reduce_blocks * sizeof(unsigned long long));
-  NLS_ALLOC(s.part_mom, de->g.reduce_blocks * sizeof(Moments));
+  // (the one-launch path reduces with up to 16 blocks whatever the population)
+  const size_t n_part = std::max(de->g.reduce_blocks, 16);
+  NLS_ALLOC(s.part_min, n_part * sizeof(double));
+  NLS_ALLOC(s.part_idx, n_part * sizeof(unsigned long long));
+  NLS_ALLOC(s.part_mom, n_part * sizeof(Moments));
   if (cfg->flags & NLS_FLAG_RECORD_MASKS) NLS_ALLOC(s.masks, P * d);
   NLS_ALLOC(de->record, nls_record_bytes(cfg->dtype, d));
   // read-back staging: up to 256 MB, but never less than one row (rows are gathered whole)
@@ -460,10 +464,24 @@ int nls_de_create(nls_ctx *ctx, const nls_de_cfg *cfg, const void *x0_host, nls_
   return NLS_OK;
 }
 
+// Populations of up to kPersistMaxElems elements take the one-launch path: all the generations of a step in one kernel
+// on one thread-block cluster (de_persistent_kernel); NLS_DE_ONE_LAUNCH=0 in the environment keeps the graph path.
+constexpr unsigned long long kPersistMaxElems = 1ull << 16;
+static bool de_one_launch_enabled() {
+  const char *e = std::getenv("NLS_DE_ONE_LAUNCH");
+  return !(e && e[0] == '0');
+}
+
 int nls_de_step(nls_de *de, uint64_t n_generations) {
   if (!de) return fail(NLS_ERR_INVALID, "nls_de_step: NULL handle");
   NLS_CUDA(cudaSetDevice(de->ctx->device));
   uint64_t left = n_generations;
+  if (!de->timing && left > 0 && de->s.P * de->s.d <= kPersistMaxElems && de->ops->persistent && !de->persistent_failed &&
+      de_one_launch_enabled()) {
+    if (de->ops->persistent(de->s, left, de->ctx->stream) == cudaSuccess) return NLS_OK;
+    cudaGetLastError();
+    de->persistent_failed = true;                 // e.g. no cluster launch on this device: the graph path still works
+  }
   if (!de->timing && de->s.P * de->s.d <= kGraphMaxElems) {
     while (left >= kGraphGens) {
       const bool ok = graph_replay(de->graph, de->ctx->stream, [&] {
@@ -664,8 +682,9 @@ int nls_de_solve(nls_ctx *ctx, const nls_de_cfg *cfg, const void *x0_host, void 
   if (rc != NLS_OK) return rc;
   nls_status st;
   rc = nls_de_sync(de, &st);
-  // generations past the stop rule are no-ops on the device, so batches only bound the host's polling interval
-  uint64_t batch = 4;
+  // generations past the stop rule are no-ops on the device, so batches only bound the host's polling interval; the
+  // one-launch path (small populations) leaves its generation loop when a stop rule fires, so it gets the whole budget
+  uint64_t batch = (de && de->s.P * de->s.d <= kPersistMaxElems) ? (1ull << 16) : 4;
   while (rc == NLS_OK && !st.stopped) {
     const uint64_t left = cfg->max_iter > st.iterations ? cfg->max_iter - st.iterations : 1;
     rc = nls_de_step(de, std::min<uint64_t>(batch, left));
@@ -751,9 +770,10 @@ static int pso_build(nls_ctx *ctx, const nls_pso_cfg *cfg, const void *lower, co
   NLS_ALLOC(s.lower, s.stride * p->elem);   // padded like a row: the move kernel reads bounds with 128-bit loads
   NLS_ALLOC(s.upper, s.stride * p->elem);
   NLS_ALLOC(s.ctrl, sizeof(PSOCtrl));
-  NLS_ALLOC(s.part_min, p->g.reduce_blocks * sizeof(double));
-  NLS_ALLOC(s.part_idx, p->g.reduce_blocks * sizeof(unsigned long long));
-  NLS_ALLOC(s.part_mom, p->g.reduce_blocks * sizeof(Moments));
+  const size_t n_part = std::max(p->g.reduce_blocks, 16);   // (the one-launch path reduces with up to 16 blocks)
+  NLS_ALLOC(s.part_min, n_part * sizeof(double));
+  NLS_ALLOC(s.part_idx, n_part * sizeof(unsigned long long));
+  NLS_ALLOC(s.part_mom, n_part * sizeof(Moments));
   NLS_ALLOC(p->record, p->record_bytes);
   std::vector<double> inertia_table;
   if (cfg->pso_type == NLS_PSO_ACCELERATED) {
@@ -837,6 +857,16 @@ int nls_pso_step(nls_pso *p, uint64_t n_generations) {
   if (!p) return fail(NLS_ERR_INVALID, "nls_pso_step: NULL handle");
   if (p->s.P_global != p->s.P) return fail(NLS_ERR_STATE, "nls_pso_step is for a single-GPU swarm; a shard uses step_local / apply_candidates");
   uint64_t left = n_generations;
+  if (left > 0 && p->s.P * p->s.d <= kPersistMaxElems && !p->first_apply_pending && p->ops->persistent &&
+      !p->persistent_failed && de_one_launch_enabled()) {
+    NLS_CUDA(cudaSetDevice(p->ctx->device));
+    if (p->ops->persistent(p->s, p->record, p->record_bytes, left, p->ctx->stream) == cudaSuccess) {
+      p->enqueued += left;
+      return NLS_OK;
+    }
+    cudaGetLastError();
+    p->persistent_failed = true;
+  }
   if (p->s.P * p->s.d <= kGraphMaxElems && !p->first_apply_pending) {
     NLS_CUDA(cudaSetDevice(p->ctx->device));
     cudaStream_t st = p->ctx->stream;
@@ -915,7 +945,7 @@ int nls_pso_solve(nls_ctx *ctx, const nls_pso_cfg *cfg, const void *lower_host, 
   if (rc != NLS_OK) return rc;
   nls_status st;
   rc = nls_pso_sync(p, &st);
-  uint64_t batch = 4;
+  uint64_t batch = (p && p->s.P * p->s.d <= kPersistMaxElems) ? (1ull << 16) : 4;   // one launch runs to the stop rule
   while (rc == NLS_OK && !st.stopped) {
     const uint64_t left = cfg->max_iter > st.iterations ? cfg->max_iter - st.iterations : 1;
     rc = nls_pso_step(p, std::min<uint64_t>(batch, left));
@@ -1180,7 +1210,10 @@ int nls_xchg_create(nls_ctx *ctx, uint64_t record_bytes, int world, int rank, nl
   x->attached = false;
   x->flags_offset = round_up(2 * size_t(world) * record_bytes, 256);
   x->bytes = x->flags_offset + 2 * size_t(world) * sizeof(unsigned long long);
-  for (int r = 0; r < kMaxPeers; r++) { x->peer_base[r] = nullptr; x->w.records[r] = nullptr; x->w.flags[r] = nullptr; }
+  for (int r = 0; r < kMaxPeers; r++) {
+    x->peer_base[r] = nullptr; x->w.records[r] = nullptr; x->w.flags[r] = nullptr;
+    x->w.values[r] = nullptr; x->w.counts[r] = 0;
+  }
   x->w.world = world; x->w.rank = rank; x->w.record_bytes = record_bytes;
   cudaError_t e = cudaMalloc(&x->base, x->bytes);     // plain cudaMalloc: the allocation must be IPC-exportable
   if (e != cudaSuccess) { delete x; return fail(NLS_ERR_NOMEM, "nls_xchg_create: %s", cudaGetErrorString(e)); }
@@ -1258,6 +1291,378 @@ int nls_pso_step_fused(nls_pso *p, uint64_t n_generations) {
     p->enqueued++;
   }
   return NLS_OK;
+}
+
+
+/* ================================================================ device groups =============================== */
+
+struct nls_group {
+  std::vector<nls_ctx *> ctx;
+};
+struct nls_pso_sharded {
+  nls_group *g;
+  std::vector<nls_pso *> shard;
+  std::vector<nls_xchg *> win;
+  std::vector<GraphCache> graph;     // kGraphGens fused generations per device
+  bool small;                        // launch-bound shards: replay graphs
+};
+struct nls_de_islands {
+  nls_group *g;
+  std::vector<nls_de *> isl;
+  uint64_t migrate_every, k, generation;
+  std::vector<void *> out_rows, out_scores, in_rows, in_scores;
+  std::vector<cudaEvent_t> exported, imported;   // per island: emigrants ready / immigrants consumed
+  size_t elem;
+};
+
+int nls_group_create(int n_devices, const int *devices, nls_group **out) {
+  if (!out) return fail(NLS_ERR_INVALID, "nls_group_create: out is NULL");
+  *out = nullptr;
+  if (n_devices < 1 || n_devices > kMaxPeers) return fail(NLS_ERR_INVALID, "nls_group_create: 1 .. %d devices", kMaxPeers);
+  for (int a = 0; a < n_devices; a++)
+    for (int b = a + 1; b < n_devices; b++)
+      if (devices && devices[a] == devices[b])
+        return fail(NLS_ERR_INVALID, "nls_group_create: device %d listed twice (shards of one group wait on one another "
+                                     "and must run on distinct devices)", devices[a]);
+  nls_group *g = new nls_group();
+  for (int r = 0; r < n_devices; r++) {
+    nls_ctx *c = nullptr;
+    int rc = nls_ctx_create(devices ? devices[r] : r, nullptr, &c);
+    if (rc != NLS_OK) { nls_group_destroy(g); return rc; }
+    g->ctx.push_back(c);
+  }
+  for (int a = 0; a < n_devices; a++)
+    for (int b = 0; b < n_devices; b++) {
+      if (a == b) continue;
+      int can = 0;
+      cudaSetDevice(g->ctx[a]->device);
+      cudaDeviceCanAccessPeer(&can, g->ctx[a]->device, g->ctx[b]->device);
+      if (!can) { nls_group_destroy(g); return fail(NLS_ERR_CUDA, "device %d cannot map the memory of device %d", g->ctx[a]->device, g->ctx[b]->device); }
+      cudaError_t e = cudaDeviceEnablePeerAccess(g->ctx[b]->device, 0);
+      if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) {
+        nls_group_destroy(g);
+        return fail(NLS_ERR_CUDA, "cudaDeviceEnablePeerAccess(%d -> %d): %s", g->ctx[a]->device, g->ctx[b]->device, cudaGetErrorString(e));
+      }
+      cudaGetLastError();
+    }
+  *out = g;
+  return NLS_OK;
+}
+int nls_group_destroy(nls_group *g) {
+  if (!g) return NLS_OK;
+  for (nls_ctx *c : g->ctx) nls_ctx_destroy(c);
+  delete g;
+  return NLS_OK;
+}
+int nls_group_size(const nls_group *g) { return g ? int(g->ctx.size()) : -1; }
+
+/* ---- sharded swarm ---- */
+static void slice_of(u64 n_global, int world, int rank, u64 *begin, u64 *end) {
+  // contiguous slices; the first n_global % world ranks hold one extra element (nlsolver_b200/distributed.py: slice_bounds)
+  const u64 base = n_global / world, extra = n_global % world;
+  *begin = rank * base + std::min<u64>(rank, extra);
+  *end = *begin + base + (u64(rank) < extra ? 1 : 0);
+}
+
+int nls_pso_sharded_destroy(nls_pso_sharded *h) {
+  if (!h) return NLS_OK;
+  for (nls_pso *p : h->shard)
+    if (p) { cudaSetDevice(p->ctx->device); cudaStreamSynchronize(p->ctx->stream); }
+  for (size_t r = 0; r < h->graph.size(); r++) {
+    if (r < h->shard.size() && h->shard[r]) cudaSetDevice(h->shard[r]->ctx->device);
+    h->graph[r].reset();
+  }
+  for (nls_pso *p : h->shard) nls_pso_destroy(p);
+  for (nls_xchg *x : h->win) nls_xchg_destroy(x);
+  delete h;
+  return NLS_OK;
+}
+
+int nls_pso_sharded_create(nls_group *g, const nls_pso_cfg *cfg, const void *lower_host, const void *upper_host,
+                           nls_pso_sharded **out) {
+  if (!g || !cfg || !lower_host || !upper_host || !out) return fail(NLS_ERR_INVALID, "nls_pso_sharded_create: NULL argument");
+  *out = nullptr;
+  const int world = int(g->ctx.size());
+  if (cfg->n_particles < u64(world)) return fail(NLS_ERR_INVALID, "nls_pso_sharded_create: fewer particles than devices");
+  nls_pso_sharded *h = new nls_pso_sharded();
+  h->g = g;
+  h->graph.resize(world);
+  int rc = NLS_OK;
+  for (int r = 0; r < world && rc == NLS_OK; r++) {
+    nls_pso_cfg local = *cfg;
+    u64 b, e;
+    slice_of(cfg->n_particles, world, r, &b, &e);
+    local.n_particles = e - b;
+    local.particle_offset = b;
+    local.n_particles_global = cfg->n_particles;
+    nls_pso *p = nullptr;
+    rc = nls_pso_create(g->ctx[r], &local, lower_host, upper_host, &p);
+    h->shard.push_back(p);
+    nls_xchg *x = nullptr;
+    if (rc == NLS_OK) rc = nls_xchg_create(g->ctx[r], nls_record_bytes(cfg->dtype, cfg->dim), world, r, &x);
+    h->win.push_back(x);
+  }
+  if (rc != NLS_OK) { nls_pso_sharded_destroy(h); return rc; }
+  // every window is addressable from every device of the group (peer access): link them directly, no IPC handles
+  for (int r = 0; r < world; r++) {
+    for (int q = 0; q < world; q++) {
+      h->win[r]->w.records[q] = h->win[q]->w.records[q];
+      h->win[r]->w.flags[q] = h->win[q]->w.flags[q];
+      h->win[r]->w.values[q] = h->shard[q]->s.pbest;
+      h->win[r]->w.counts[q] = h->shard[q]->s.P;
+    }
+    h->win[r]->opened = true;
+  }
+  h->small = h->shard[0]->s.P * h->shard[0]->s.d <= kGraphMaxElems;
+  // the first update_best_positions across the shards (nlsolver.h:2595): enqueue every shard's publish + gather
+  for (int r = 0; r < world && rc == NLS_OK; r++) rc = nls_pso_attach_exchange(h->shard[r], h->win[r]);
+  if (rc != NLS_OK) { nls_pso_sharded_destroy(h); return rc; }
+  *out = h;
+  return NLS_OK;
+}
+
+int nls_pso_sharded_step(nls_pso_sharded *h, uint64_t n_generations) {
+  if (!h) return fail(NLS_ERR_INVALID, "nls_pso_sharded_step: NULL handle");
+  const int world = int(h->shard.size());
+  uint64_t left = n_generations;
+  // Every device gets the same work in the same order; a shard's apply kernel waits (on the device) for the records of
+  // all shards, so the host must enqueue generation g on every device before it may block on anything.
+  if (h->small) {
+    while (left >= kGraphGens) {
+      bool ok = true;
+      for (int r = 0; r < world && ok; r++) {
+        nls_pso *p = h->shard[r];
+        cudaSetDevice(p->ctx->device);
+        cudaStream_t st = p->ctx->stream;
+        ok = graph_replay(h->graph[r], st, [&] {
+          for (int g = 0; g < kGraphGens; g++) {
+            if (p->ops->move(p->s, p->g, st) != cudaSuccess) return false;
+            if (p->ops->candidate_publish(p->s, p->xchg->w, 0, p->g, st) != cudaSuccess) return false;
+            if (p->ops->gather_apply(p->s, p->xchg->w, 0, st) != cudaSuccess) return false;
+          }
+          return true;
+        });
+        if (ok) p->enqueued += kGraphGens;
+        else if (r > 0) return fail(NLS_ERR_CUDA, "nls_pso_sharded_step: graph launch failed on device %d after other shards were enqueued", p->ctx->device);
+      }
+      if (!ok) { h->small = false; break; }
+      left -= kGraphGens;
+    }
+  }
+  for (uint64_t g = 0; g < left; g++)
+    for (int r = 0; r < world; r++) {
+      int rc = nls_pso_step_fused(h->shard[r], 1);
+      if (rc != NLS_OK) return rc;
+    }
+  return NLS_OK;
+}
+
+int nls_pso_sharded_sync(nls_pso_sharded *h, nls_status *status) {
+  if (!h) return fail(NLS_ERR_INVALID, "nls_pso_sharded_sync: NULL handle");
+  int rc = NLS_OK;
+  nls_status st0;
+  for (size_t r = 0; r < h->shard.size() && rc == NLS_OK; r++) {
+    nls_status st;
+    rc = nls_pso_sync(h->shard[r], &st);
+    if (r == 0) st0 = st;      // every shard holds the same swarm-level state
+  }
+  if (rc == NLS_OK && status) *status = st0;
+  return rc;
+}
+int nls_pso_sharded_read_best(nls_pso_sharded *h, void *x_host) {
+  if (!h || !x_host) return fail(NLS_ERR_INVALID, "nls_pso_sharded_read_best: NULL argument");
+  return nls_pso_read_best(h->shard[0], x_host);
+}
+int nls_pso_sharded_shard(nls_pso_sharded *h, int rank, nls_pso **shard) {
+  if (!h || !shard || rank < 0 || rank >= int(h->shard.size())) return fail(NLS_ERR_INVALID, "nls_pso_sharded_shard: bad argument");
+  *shard = h->shard[rank];
+  return NLS_OK;
+}
+
+int nls_pso_solve_sharded(nls_group *g, const nls_pso_cfg *cfg, const void *lower_host, const void *upper_host,
+                          void *x_best_host, nls_status *status) {
+  if (!x_best_host) return fail(NLS_ERR_INVALID, "nls_pso_solve_sharded: x_best_host is NULL");
+  nls_pso_sharded *h = nullptr;
+  int rc = nls_pso_sharded_create(g, cfg, lower_host, upper_host, &h);
+  if (rc != NLS_OK) return rc;
+  nls_status st;
+  rc = nls_pso_sharded_sync(h, &st);
+  uint64_t batch = 8;
+  while (rc == NLS_OK && !st.stopped) {
+    const uint64_t left = cfg->max_iter > st.iterations ? cfg->max_iter - st.iterations : 1;
+    rc = nls_pso_sharded_step(h, std::min<uint64_t>(batch, left));
+    if (rc == NLS_OK) rc = nls_pso_sharded_sync(h, &st);
+    if (batch < 256) batch *= 2;
+  }
+  if (rc == NLS_OK && st.best_valid) rc = nls_pso_sharded_read_best(h, x_best_host);
+  if (rc == NLS_OK && status) *status = st;
+  nls_pso_sharded_destroy(h);
+  return rc;
+}
+
+/* ---- DE islands ---- */
+int nls_de_islands_destroy(nls_de_islands *h) {
+  if (!h) return NLS_OK;
+  for (size_t r = 0; r < h->isl.size(); r++) {
+    if (!h->isl[r]) continue;
+    cudaSetDevice(h->isl[r]->ctx->device);
+    cudaStreamSynchronize(h->isl[r]->ctx->stream);
+  }
+  for (size_t r = 0; r < h->isl.size(); r++) {
+    if (h->isl[r]) cudaSetDevice(h->isl[r]->ctx->device);
+    if (r < h->exported.size() && h->exported[r]) cudaEventDestroy(h->exported[r]);
+    if (r < h->imported.size() && h->imported[r]) cudaEventDestroy(h->imported[r]);
+    for (std::vector<void *> *v : {&h->out_rows, &h->out_scores, &h->in_rows, &h->in_scores})
+      if (r < v->size() && (*v)[r]) cudaFree((*v)[r]);
+    nls_de_destroy(h->isl[r]);
+  }
+  delete h;
+  return NLS_OK;
+}
+
+int nls_de_islands_create(nls_group *g, const nls_de_cfg *cfg, const void *x0_host, uint64_t migrate_every,
+                          uint64_t migrants, nls_de_islands **out) {
+  if (!g || !cfg || !x0_host || !out) return fail(NLS_ERR_INVALID, "nls_de_islands_create: NULL argument");
+  *out = nullptr;
+  const int world = int(g->ctx.size());
+  nls_de_islands *h = new nls_de_islands();
+  h->g = g;
+  h->migrate_every = migrate_every;
+  h->k = std::min<uint64_t>(migrants, cfg->pop_size);
+  h->generation = 0;
+  h->elem = elem_size(cfg->dtype);
+  int rc = NLS_OK;
+  for (int r = 0; r < world && rc == NLS_OK; r++) {
+    nls_de_cfg local = *cfg;
+    local.agent_offset = cfg->agent_offset + u64(r) * cfg->pop_size;   // islands draw from disjoint streams
+    nls_de *de = nullptr;
+    rc = nls_de_create(g->ctx[r], &local, x0_host, &de);
+    h->isl.push_back(de);
+    h->exported.push_back(nullptr); h->imported.push_back(nullptr);
+    h->out_rows.push_back(nullptr); h->out_scores.push_back(nullptr);
+    h->in_rows.push_back(nullptr); h->in_scores.push_back(nullptr);
+    if (rc != NLS_OK || h->k == 0 || world == 1) continue;
+    const size_t rows = size_t(h->k) * cfg->dim * h->elem, scores = size_t(h->k) * h->elem;
+    cudaError_t e = cudaSetDevice(g->ctx[r]->device);
+    if (e == cudaSuccess) e = cudaMalloc(&h->out_rows[r], rows);
+    if (e == cudaSuccess) e = cudaMalloc(&h->out_scores[r], scores);
+    if (e == cudaSuccess) e = cudaMalloc(&h->in_rows[r], rows);
+    if (e == cudaSuccess) e = cudaMalloc(&h->in_scores[r], scores);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->exported[r], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->imported[r], cudaEventDisableTiming);
+    if (e != cudaSuccess) rc = fail(NLS_ERR_CUDA, "nls_de_islands_create: %s", cudaGetErrorString(e));
+  }
+  if (rc != NLS_OK) { nls_de_islands_destroy(h); return rc; }
+  *out = h;
+  return NLS_OK;
+}
+
+// ring migration after a generation that is a multiple of migrate_every: island r sends its k best rows to island
+// r + 1, which overwrites its k worst with them (same selection orders as nls_de_export_top / nls_de_import_migrants)
+static int islands_migrate(nls_de_islands *h) {
+  const int world = int(h->isl.size());
+  const size_t rows = size_t(h->k) * h->isl[0]->s.d * h->elem, scores = size_t(h->k) * h->elem;
+  for (int r = 0; r < world; r++) {          // emigrants: wait until the previous batch was consumed by the receiver
+    nls_de *de = h->isl[r];
+    NLS_CUDA(cudaSetDevice(de->ctx->device));
+    NLS_CUDA(cudaStreamWaitEvent(de->ctx->stream, h->imported[(r + 1) % world], 0));
+    int rc = nls_de_export_top(de, h->k, h->out_rows[r], h->out_scores[r]);
+    if (rc != NLS_OK) return rc;
+    NLS_CUDA(cudaEventRecord(h->exported[r], de->ctx->stream));
+  }
+  for (int r = 0; r < world; r++) {          // immigrants: pull from the left neighbour over NVLink, then import
+    nls_de *de = h->isl[r];
+    const int src = (r + world - 1) % world;
+    NLS_CUDA(cudaSetDevice(de->ctx->device));
+    NLS_CUDA(cudaStreamWaitEvent(de->ctx->stream, h->exported[src], 0));
+    NLS_CUDA(cudaMemcpyPeerAsync(h->in_rows[r], de->ctx->device, h->out_rows[src], h->isl[src]->ctx->device, rows, de->ctx->stream));
+    NLS_CUDA(cudaMemcpyPeerAsync(h->in_scores[r], de->ctx->device, h->out_scores[src], h->isl[src]->ctx->device, scores, de->ctx->stream));
+    NLS_CUDA(cudaEventRecord(h->imported[r], de->ctx->stream));
+    int rc = nls_de_import_migrants(de, h->k, h->in_rows[r], h->in_scores[r]);
+    if (rc != NLS_OK) return rc;
+  }
+  return NLS_OK;
+}
+
+int nls_de_islands_step(nls_de_islands *h, uint64_t n_generations) {
+  if (!h) return fail(NLS_ERR_INVALID, "nls_de_islands_step: NULL handle");
+  const int world = int(h->isl.size());
+  const bool migrating = world > 1 && h->migrate_every > 0 && h->k > 0;
+  uint64_t left = n_generations;
+  while (left > 0) {
+    // run up to the next migration point in one call per island (small islands: one launch each)
+    uint64_t chunk = left;
+    if (migrating) chunk = std::min<uint64_t>(chunk, h->migrate_every - h->generation % h->migrate_every);
+    for (int r = 0; r < world; r++) {
+      int rc = nls_de_step(h->isl[r], chunk);
+      if (rc != NLS_OK) return rc;
+    }
+    h->generation += chunk;
+    left -= chunk;
+    if (migrating && h->generation % h->migrate_every == 0) {
+      int rc = islands_migrate(h);
+      if (rc != NLS_OK) return rc;
+    }
+  }
+  return NLS_OK;
+}
+
+int nls_de_islands_sync(nls_de_islands *h, nls_status *status) {
+  if (!h) return fail(NLS_ERR_INVALID, "nls_de_islands_sync: NULL handle");
+  nls_status best;
+  std::memset(&best, 0, sizeof(best));
+  uint64_t calls = 0, reruns = 0, rounds = 0, accepted = 0;
+  int all_stopped = 1;
+  for (size_t r = 0; r < h->isl.size(); r++) {
+    nls_status st;
+    int rc = nls_de_sync(h->isl[r], &st);
+    if (rc != NLS_OK) return rc;
+    calls += st.function_calls; reruns += st.repair_reruns; rounds += st.repair_rounds; accepted += st.accepted_total;
+    all_stopped &= st.stopped;
+    const uint64_t iter0 = r == 0 ? st.iterations : best.iterations;
+    if (r == 0 || st.f_value < best.f_value) {        // strict <: the lowest rank wins ties
+      best = st;
+      best.best_index = h->isl[r]->s.offset + st.best_index;
+      best._reserved = int32_t(r);                    // rank of the best island
+    }
+    best.iterations = iter0;
+  }
+  best.function_calls = calls; best.repair_reruns = reruns; best.repair_rounds = rounds; best.accepted_total = accepted;
+  best.stopped = all_stopped;
+  if (status) *status = best;
+  return NLS_OK;
+}
+int nls_de_islands_read_best(nls_de_islands *h, void *x_host) {
+  if (!h || !x_host) return fail(NLS_ERR_INVALID, "nls_de_islands_read_best: NULL argument");
+  nls_status st;
+  int rc = nls_de_islands_sync(h, &st);
+  if (rc != NLS_OK) return rc;
+  return nls_de_read_best(h->isl[st._reserved], x_host);
+}
+int nls_de_islands_island(nls_de_islands *h, int rank, nls_de **island) {
+  if (!h || !island || rank < 0 || rank >= int(h->isl.size())) return fail(NLS_ERR_INVALID, "nls_de_islands_island: bad argument");
+  *island = h->isl[rank];
+  return NLS_OK;
+}
+int nls_de_solve_islands(nls_group *g, const nls_de_cfg *cfg, const void *x0_host, uint64_t migrate_every,
+                         uint64_t migrants, void *x_best_host, nls_status *status) {
+  if (!x_best_host) return fail(NLS_ERR_INVALID, "nls_de_solve_islands: x_best_host is NULL");
+  nls_de_islands *h = nullptr;
+  int rc = nls_de_islands_create(g, cfg, x0_host, migrate_every, migrants, &h);
+  if (rc != NLS_OK) return rc;
+  nls_status st;
+  rc = nls_de_islands_sync(h, &st);
+  uint64_t batch = migrate_every ? migrate_every : 8;
+  while (rc == NLS_OK && !st.stopped) {
+    const uint64_t left = cfg->max_iter > st.iterations ? cfg->max_iter - st.iterations : 1;
+    rc = nls_de_islands_step(h, std::min<uint64_t>(batch, left));
+    if (rc == NLS_OK) rc = nls_de_islands_sync(h, &st);
+    if (batch < 256) batch *= 2;
+  }
+  if (rc == NLS_OK) rc = nls_de_islands_read_best(h, x_best_host);
+  if (rc == NLS_OK && status) *status = st;
+  nls_de_islands_destroy(h);
+  return rc;
 }
 
 }  /* extern "C" */

@@ -21,6 +21,7 @@
 //                              (nlsolver.h:2037-2052) and the stop test (nlsolver.h:2439-2447), last block finalises.
 #pragma once
 #include <cooperative_groups.h>
+#include <algorithm>
 #include <cstdlib>
 #include <math_constants.h>
 
@@ -96,11 +97,13 @@ __device__ __forceinline__ T de_sweep(const DEState &s, const T *p0, const T *p1
       }
       if (SKIP_BASE) {
         const u32 jl = jj < d ? jj : 0u;
-        ld_row(p1 + jl, x1[u]); ld_row(p2 + jl, x2[u]); ld_row(p3 + jl, x3[u]);
+        // (the predicated base-row load goes FIRST: issued after the donor loads, ptxas has been seen to sink it below
+        //  the first use of the donors' data to save a register pair, which exposes a second DRAM latency per step)
         if (!all_mut) {                                // the base row is only touched where a coordinate keeps it
           if (SHARED_BASE) ld_row_shared(p0 + jl, x0[u]);
           else ld_row(p0 + jl, x0[u]);
         }
+        ld_row(p1 + jl, x1[u]); ld_row(p2 + jl, x2[u]); ld_row(p3 + jl, x3[u]);
       }
     }
 #pragma unroll
@@ -296,19 +299,29 @@ __device__ __forceinline__ void de_tile_body(const DEState &s, const DETileEntry
 // twice the loads in flight per lane and the per-agent overhead spread over twice the coordinates; W = 32, U = 1 with
 // the base-row skip for long rows.
 #ifndef NLS_DE_BULK_STAGES
-#define NLS_DE_BULK_STAGES 3
+#define NLS_DE_BULK_STAGES 2
 #endif
 #ifndef NLS_DE_BULK_STEPS
 #define NLS_DE_BULK_STEPS 2
 #endif
+#ifndef NLS_DE_BULK_BLOCKS
+#define NLS_DE_BULK_BLOCKS 2
+#endif
 template <int U> struct DEBlocksPerSM { static constexpr int value = U >= 2 ? 3 : 4; };
+// barriers of the multi-phase passes: the whole grid (cooperative launch) or one thread-block cluster (the one-launch
+// path for small populations, where a generation is a handful of microseconds and the barrier latency is what counts)
+struct GridSync {
+  cg::grid_group g;
+  __device__ __forceinline__ void operator()() { g.sync(); }
+};
+struct ClusterSync {
+  __device__ __forceinline__ void operator()() { cg::this_cluster().sync(); }
+};
+
 template <class T, int OBJ, int W, int U, int S, bool SKIP_BASE>
-__global__ void __launch_bounds__(kBlock, DEBlocksPerSM<U>::value) de_generation_kernel(DEState s, int tile_shift) {
-  __shared__ DETileEntry tile_mem[kWarpsPerBlock][32];
+__device__ __forceinline__ void de_generation_pass(const DEState &s, DETileEntry *tile_entries, int tile_shift) {
   DECtrl *ctrl = s.ctrl;
-  if (ctrl->stop) return;
   const int lane = threadIdx.x & 31;
-  DETileEntry *tile_entries = tile_mem[threadIdx.x >> 5];
   const u64 warp = (u64(blockIdx.x) * kBlock + threadIdx.x) >> 5, n_warps = (u64(gridDim.x) * kBlock) >> 5;
   const u64 gen_key = tape_gen_key(s.seed, ctrl->iter + 1), best_id = ctrl->best_id;
   const bool random_mode = s.strategy != 0;             // NLS_DE_RANDOM = 1: ids[0] = i; best: ids[0] = best_id
@@ -328,6 +341,12 @@ __global__ void __launch_bounds__(kBlock, DEBlocksPerSM<U>::value) de_generation
   n_ok = __reduce_add_sync(kFull, n_ok);
   if (lane == 0 && n_ok) atomicAdd(&ctrl->spec_accepted, n_ok);
 }
+template <class T, int OBJ, int W, int U, int S, bool SKIP_BASE>
+__global__ void __launch_bounds__(kBlock, DEBlocksPerSM<U>::value) de_generation_kernel(DEState s, int tile_shift) {
+  __shared__ DETileEntry tile_mem[kWarpsPerBlock][32];
+  if (s.ctrl->stop) return;
+  de_generation_pass<T, OBJ, W, U, S, SKIP_BASE>(s, tile_mem[threadIdx.x >> 5], tile_shift);
+}
 
 // ------------------------------------------------------------------------------------------------ K2, TMA-staged
 // The same generation pass for long rows, the four rows of every agent staged through shared memory by bulk copies
@@ -336,7 +355,7 @@ __global__ void __launch_bounds__(kBlock, DEBlocksPerSM<U>::value) de_generation
 // comes out of L2; in random mode that costs the ~3 % of traffic the LDG version saves by skipping fully mutated
 // 128-byte lines).  An accepted trial is materialised by the ordinary second sweep.
 template <class T, int OBJ, int kStages, int kSteps>
-__global__ void __launch_bounds__(kBlock, 2) de_generation_bulk_kernel(DEState s, int tile_shift) {
+__global__ void __launch_bounds__(kBlock, NLS_DE_BULK_BLOCKS) de_generation_bulk_kernel(DEState s, int tile_shift) {
   constexpr int V = Vec<T>::V;
   constexpr u32 kStride = 32 * V;                        // coordinates per sweep step
   constexpr u32 kChunkBytes = 512u * kSteps;             // per row and stage
@@ -467,17 +486,13 @@ __global__ void __launch_bounds__(kBlock, 2) de_generation_bulk_kernel(DEState s
 // donor stamped in the previous iteration?  hits go to a list through warp-aggregated atomics) and RE-EVALUATE (the
 // listed agents spread evenly over all lane groups of the grid — a tile-local loop left most warps idle behind the few
 // that drew several hits: 9.6 % issue utilisation at a 5 % hit rate).
-template <class T, int OBJ, int W, int U, int S, bool SKIP_BASE>
-__global__ void __launch_bounds__(kBlock, DEBlocksPerSM<U>::value) de_repair_kernel(DEState s) {
-  __shared__ DETileEntry tile_mem[kWarpsPerBlock][32];
-  cg::grid_group grid = cg::this_grid();
+template <class T, int OBJ, int W, int U, int S, bool SKIP_BASE, class Sync>
+__device__ __forceinline__ void de_repair_pass(const DEState &s, DETileEntry *tile_entries, Sync &sync) {
   DECtrl *ctrl = s.ctrl;
-  if (ctrl->stop) return;                                // uniform over the grid: only K3 changes it
   // If the speculative pass accepted nothing, no row changed and every speculative result already equals the
   // sequential one (induction over the agent index) — nothing to repair.
   if (*reinterpret_cast<volatile unsigned int *>(&ctrl->spec_accepted) == 0) return;
   const int lane = threadIdx.x & 31;
-  DETileEntry *tile_entries = tile_mem[threadIdx.x >> 5];
   const u64 tid = u64(blockIdx.x) * kBlock + threadIdx.x, n_threads = u64(gridDim.x) * kBlock;
   const u64 warp = tid >> 5, n_warps = n_threads >> 5;
   const u64 gen_key = tape_gen_key(s.seed, ctrl->iter + 1), best_id = ctrl->best_id;
@@ -509,7 +524,7 @@ __global__ void __launch_bounds__(kBlock, DEBlocksPerSM<U>::value) de_repair_ker
         if (hit) s.list[slot + __popc(vote & ((1u << lane) - 1u))] = u32(mine);
       }
     }
-    grid.sync();
+    sync();
     const u32 n_list = *reinterpret_cast<volatile unsigned int *>(&ctrl->list_count[cur]);
     // recycle the counter slots iteration k + 2 will use: their last readers passed an earlier barrier, their next
     // writers start after the barrier that ends this iteration
@@ -533,26 +548,37 @@ __global__ void __launch_bounds__(kBlock, DEBlocksPerSM<U>::value) de_repair_ker
     n_changed = __reduce_add_sync(kFull, n_changed);
     if (lane == 0 && n_changed) atomicAdd(&ctrl->changed[cur], n_changed);
     if (tid == 0) ctrl->reruns += n_list;
-    grid.sync();
+    sync();
     if (*reinterpret_cast<volatile unsigned int *>(&ctrl->changed[cur]) == 0) break;
     if (k >= 65000u) { if (tid == 0) ctrl->error = 1; break; }
   }
   if (tid == 0) ctrl->rounds += k;
 }
 
+template <class T, int OBJ, int W, int U, int S, bool SKIP_BASE>
+__global__ void __launch_bounds__(kBlock, DEBlocksPerSM<U>::value) de_repair_kernel(DEState s) {
+  __shared__ DETileEntry tile_mem[kWarpsPerBlock][32];
+  if (s.ctrl->stop) return;                              // uniform over the grid: only K3 changes it
+  GridSync sync{cg::this_grid()};
+  de_repair_pass<T, OBJ, W, U, S, SKIP_BASE>(s, tile_mem[threadIdx.x >> 5], sync);
+}
+
 // ------------------------------------------------------------------------------------------------ K3 commit + reduce
-template <class T>
 // mode 0: commit the generation in flight; 1: first scan after init; 2: re-scan after island migration (best only)
-__global__ void __launch_bounds__(kBlock) de_commit_kernel(DEState s, int mode) {
+template <class T>
+__device__ __forceinline__ void de_commit_pass(const DEState &s, int mode) {
   const bool initial = mode != 0;
   DECtrl *ctrl = s.ctrl;
-  if (ctrl->stop) return;
   T *score = static_cast<T *>(s.score);
   const T *tscore = static_cast<const T *>(s.tscore);
   u32 n_acc = 0;
+  // an accepted trial commits as: score = trial score, row location flipped (the row itself is already in place)
   auto item = [&](u64 i, double &for_min, double &for_moments) {
+    const bool a = !initial && s.acc[i];
+    for_min = for_moments = static_cast<double>(a ? tscore[i] : score[i]);
+  };
+  auto store = [&](u64 i) {
     if (!initial && s.acc[i]) { score[i] = tscore[i]; s.where[i] ^= 1u; n_acc++; }
-    for_min = for_moments = static_cast<double>(score[i]);
   };
   auto fin = [&](MinLoc ml, Moments mo) {
     if (!initial) ctrl->iter += 1;                        // nlsolver.h:2474
@@ -587,9 +613,14 @@ __global__ void __launch_bounds__(kBlock) de_commit_kernel(DEState s, int mode) 
   };
   MinLoc ml;
   Moments mo;
-  if (population_reduce(s.P, s.part_min, s.part_idx, s.part_mom, &ctrl->ticket, item, post, ml, mo) &&
+  if (population_reduce(s.P, s.part_min, s.part_idx, s.part_mom, &ctrl->ticket, item, store, post, ml, mo) &&
       threadIdx.x == 0)
     fin(ml, mo);
+}
+template <class T>
+__global__ void __launch_bounds__(kBlock) de_commit_kernel(DEState s, int mode) {
+  if (s.ctrl->stop) return;
+  de_commit_pass<T>(s, mode);
 }
 
 // ------------------------------------------------------------------------------------------------ island hooks
@@ -718,6 +749,7 @@ __global__ void __launch_bounds__(kBlock) de_gather_kernel(DEState s, u32 k, T *
 // ... or overwrite the k selected agents (immigrants): row in place, score, and nothing else
 template <class T>
 __global__ void __launch_bounds__(kBlock) de_scatter_kernel(DEState s, u32 k, const T *rows, const T *scores) {
+  if (s.ctrl->stop) return;                              // an island whose stop rule has fired stays as it is
   for (u32 e = blockIdx.x; e < k; e += gridDim.x) {
     const u32 a = s.list[e];
     if (a == 0xffffffffu) continue;
@@ -831,11 +863,11 @@ void de_launch_k2_w(const DEState &s, const LaunchGeom &g, cudaStream_t st) {
   while (shift > 0 && ((s.P + (1ull << shift) - 1) >> shift) < 8ull * grid * kWarpsPerBlock) shift--;
   kernel<<<grid, kBlock, 0, st>>>(s, shift);
 }
-// NLS_DE_BULK in the environment overrides the staging policy: 0 never, 1 best recombination only (the default),
-// 2 both recombination modes, 3 both and for every row length (tests)
+// NLS_DE_BULK in the environment overrides the staging policy: 0 never, 1 best recombination only, 2 both
+// recombination modes (the default), 3 both and for every row length (tests)
 inline int de_bulk_mode() {
   const char *e = std::getenv("NLS_DE_BULK");
-  return e ? std::atoi(e) : 1;
+  return e ? std::atoi(e) : 2;
 }
 template <class T, int O, int kStages, int kSteps>
 void de_launch_k2_bulk(const DEState &s, const LaunchGeom &g, cudaStream_t st) {
@@ -885,16 +917,14 @@ cudaError_t de_launch_repair_w(const DEState &s, const LaunchGeom &g, cudaStream
   const unsigned int grid = clamp_grid((s.P + kBlock - 1) / kBlock, u64(g.sm_count) * blocks_per_sm(kernel));
   return cudaLaunchCooperativeKernel(reinterpret_cast<void *>(kernel), dim3(grid), dim3(kBlock), args, 0, st);
 }
-// same lane-group shapes as the speculative pass (de_launch_k2); long rows always take the LDG sweep
+// one sweep step per agent where it covers the row (W = 4 / 8 / 16 lanes), else a full warp looping over the row
 template <class T, int O>
 cudaError_t de_launch_repair(const DEState &s, const LaunchGeom &g, cudaStream_t st) {
   const u64 vecs = (s.d + Vec<T>::V - 1) / Vec<T>::V;
   if constexpr (closed_form_dim(O) > 0) return de_launch_repair_w<T, O, 4, 1, 1, false>(s, g, st);
   if (vecs <= 4) return de_launch_repair_w<T, O, 4, 1, 1, false>(s, g, st);
   if (vecs <= 8) return de_launch_repair_w<T, O, 8, 1, 1, false>(s, g, st);
-  if (vecs <= 16) return de_launch_repair_w<T, O, 8, 2, 4, false>(s, g, st);
-  if (vecs <= 32) return de_launch_repair_w<T, O, 16, 2, 2, false>(s, g, st);
-  if (vecs <= 64) return de_launch_repair_w<T, O, 32, 2, 1, false>(s, g, st);
+  if (vecs <= 16) return de_launch_repair_w<T, O, 16, 1, 1, false>(s, g, st);
   return de_launch_repair_w<T, O, 32, 1, 1, true>(s, g, st);
 }
 
@@ -919,6 +949,10 @@ cudaError_t de_launch_generation(const DEState &s, const LaunchGeom &g, cudaStre
 }
 
 
+// the one-launch path (de_persist.cuh, compiled in its own translation units)
+template <class T>
+cudaError_t de_launch_persistent(const DEState &s, unsigned long long n_generations, cudaStream_t st);
+
 template <class T>
 cudaError_t de_launch_gather_rows(const DEState &s, unsigned long long first, unsigned long long count, void *out,
                                   cudaStream_t st) {
@@ -926,10 +960,17 @@ cudaError_t de_launch_gather_rows(const DEState &s, unsigned long long first, un
   return cudaGetLastError();
 }
 
+// (objective plugins are one translation unit compiled at run time: they leave the one-launch kernels out and small
+//  populations take the graph-replay path there)
+#ifdef NLS_PLUGIN_BUILD
+#define NLS_PERSISTENT_OR_NULL(f) nullptr
+#else
+#define NLS_PERSISTENT_OR_NULL(f) f
+#endif
 #define NLS_DEFINE_DE_OPS(T, NAME)                                                                        \
   const DEOps *NAME() {                                                                                   \
     static const DEOps ops = {de_launch_init<T>, de_launch_generation<T>, de_launch_export_best<T>,       \
-                              de_launch_migrate<T>, de_launch_gather_rows<T>};                            \
+                              de_launch_migrate<T>, de_launch_gather_rows<T>, NLS_PERSISTENT_OR_NULL(de_launch_persistent<T>)}; \
     return &ops;                                                                                          \
   }
 

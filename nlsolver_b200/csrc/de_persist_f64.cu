@@ -1,0 +1,4 @@
+#include "de_persist.cuh"
+namespace nls {
+NLS_DEFINE_DE_PERSISTENT(double)
+}

@@ -13,6 +13,8 @@ struct DEOps {
                          const LaunchGeom &g, cudaStream_t st);
   cudaError_t (*gather_rows)(const DEState &s, unsigned long long first, unsigned long long count, void *out,
                              cudaStream_t st);
+  // small populations: n generations (K2 + repair + K3 each) in ONE launch on one thread-block cluster
+  cudaError_t (*persistent)(const DEState &s, unsigned long long n_generations, cudaStream_t st);
 };
 struct PSOOps {
   cudaError_t (*init)(const PSOState &s, const LaunchGeom &g, cudaStream_t st);
@@ -24,6 +26,9 @@ struct PSOOps {
   cudaError_t (*candidate_publish)(const PSOState &s, const XchgWindow &w, int initial, const LaunchGeom &g,
                                    cudaStream_t st);
   cudaError_t (*gather_apply)(const PSOState &s, const XchgWindow &w, int initial, cudaStream_t st);
+  // small single-GPU swarms: n generations (move + candidate + apply each) in ONE launch on one thread-block cluster
+  cudaError_t (*persistent)(const PSOState &s, void *record, unsigned long long record_bytes,
+                            unsigned long long n_generations, cudaStream_t st);
 };
 struct SANNOps {
   // x0: device, x0_count rows of d elements (1 = shared start)

@@ -1,0 +1,4 @@
+#include "pso_persist.cuh"
+namespace nls {
+NLS_DEFINE_PSO_PERSISTENT(double)
+}

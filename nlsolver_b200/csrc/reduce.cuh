@@ -47,25 +47,42 @@ __device__ __forceinline__ void block_reduce(MinLoc &ml, Moments &mo, MinLoc *sm
   __syncthreads();
 }
 
-// item(i, for_min, for_moments) yields the two values of element i; post() runs once per thread after its sweep.
+// item(i, for_min, for_moments) yields the two values of element i and must only LOAD; store(i) runs after the loads
+// of a batch of kReduceBatch elements were issued (side effects of committing element i); post() runs once per thread
+// after its sweep.  Batching keeps kReduceBatch independent loads in flight per thread: the sweep is a chain of dependent
+// Welford updates, and with one element per iteration each of them waited for its own load.
 // Returns true in every thread of the last block to finish, with the grid-wide result in (ml, mo).
-template <class PerItem, class PostSweep>
+constexpr int kReduceBatch = 4;
+template <class PerItem, class Store, class PostSweep>
 __device__ __forceinline__ bool population_reduce(u64 n, double *part_min, unsigned long long *part_idx,
-                                                  Moments *part_mom, unsigned int *ticket, PerItem item,
+                                                  Moments *part_mom, unsigned int *ticket, PerItem item, Store store,
                                                   PostSweep post, MinLoc &ml, Moments &mo) {
   __shared__ MinLoc sm_ml[kWarpsPerBlock];
   __shared__ Moments sm_mo[kWarpsPerBlock];
   __shared__ bool is_last;
   ml.v = CUDART_INF; ml.i = ~0ull;
   mo.n = 0.0; mo.mean = 0.0; mo.m2 = 0.0;
-  for (u64 i = u64(blockIdx.x) * kBlock + threadIdx.x; i < n; i += u64(gridDim.x) * kBlock) {
-    double v, w;
-    item(i, v, w);
-    if (v < ml.v) { ml.v = v; ml.i = i; }
-    mo.n += 1.0;
-    const double delta = w - mo.mean;
-    mo.mean += delta / mo.n;
-    mo.m2 += delta * (w - mo.mean);
+  const u64 stride = u64(gridDim.x) * kBlock;
+  for (u64 i0 = u64(blockIdx.x) * kBlock + threadIdx.x; i0 < n; i0 += stride * kReduceBatch) {
+    double v[kReduceBatch], w[kReduceBatch];
+#pragma unroll
+    for (int u = 0; u < kReduceBatch; u++) {
+      const u64 i = i0 + u * stride;
+      v[u] = CUDART_INF; w[u] = 0.0;
+      if (i < n) item(i, v[u], w[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < kReduceBatch; u++) {
+      const u64 i = i0 + u * stride;
+      if (i < n) {
+        store(i);
+        if (v[u] < ml.v) { ml.v = v[u]; ml.i = i; }
+        mo.n += 1.0;
+        const double delta = w[u] - mo.mean;
+        mo.mean += delta / mo.n;
+        mo.m2 += delta * (w[u] - mo.mean);
+      }
+    }
   }
   post();   // per-thread side results (ordered before the election by the barrier inside block_reduce)
   block_reduce(ml, mo, sm_ml, sm_mo);
@@ -106,11 +123,52 @@ __device__ T sequential_std_err(const T *x, u64 n) {
   result = result / static_cast<T>(n - 1);
   return static_cast<T>(sqrt(static_cast<double>(result)));
 }
+// the same over a population stored as consecutive segments (the shards of a swarm, in rank order)
+template <class T>
+__device__ T sequential_std_err_segments(const void *const *seg, const unsigned long long *count, int n_seg) {
+  T mean_val = T(0), result = T(0);
+  u64 n = 0;
+  for (int k = 0; k < n_seg; k++) {
+    const T *x = static_cast<const T *>(seg[k]);
+    for (u64 i = 0; i < count[k]; i++) mean_val = Ar<T>::add(mean_val, __ldcg(x + i));
+    n += count[k];
+  }
+  mean_val = mean_val / static_cast<T>(n);
+  for (int k = 0; k < n_seg; k++) {
+    const T *x = static_cast<const T *>(seg[k]);
+    for (u64 i = 0; i < count[k]; i++) {
+      const double dlt = static_cast<double>(Ar<T>::sub(__ldcg(x + i), mean_val));
+      result = static_cast<T>(__dadd_rn(static_cast<double>(result), __dmul_rn(dlt, dlt)));
+    }
+  }
+  result = result / static_cast<T>(n - 1);
+  return static_cast<T>(sqrt(static_cast<double>(result)));
+}
+// The pairwise value decides the stop test except where the last bits matter: within `window` (relative) of eps the
+// reference's own sequential evaluation is used.  The window covers the gap between the two summation orders: a few
+// ulp of T per addition level for the pairwise tree against up to n ulp for the reference's running sums — generous
+// multiples of both, so a wrong decision would need the two evaluations to disagree by more than their error bounds.
+template <class T>
+__device__ __forceinline__ double std_err_window(double n) {
+  const double ulp = sizeof(T) == 8 ? 2.220446049250313e-16 : 1.1920928955078125e-07;
+  const double w = 8.0 * n * ulp;
+  return w < 1e-9 ? 1e-9 : (w > 0.25 ? 0.25 : w);
+}
 template <class T>
 __device__ __forceinline__ T stop_std_err(const Moments &mo, const T *values, u64 n, double eps) {
   T se = static_cast<T>(sqrt(mo.m2 / (mo.n - 1.0)));
   const double e = static_cast<double>(static_cast<T>(eps));
-  if (values != nullptr && e > 0.0 && fabs(static_cast<double>(se) - e) <= 1e-9 * e) se = sequential_std_err<T>(values, n);
+  if (values != nullptr && e > 0.0 && fabs(static_cast<double>(se) - e) <= std_err_window<T>(mo.n) * e)
+    se = sequential_std_err<T>(values, n);
+  return se;
+}
+template <class T>
+__device__ __forceinline__ T stop_std_err_segments(const Moments &mo, const void *const *seg,
+                                                   const unsigned long long *count, int n_seg, double eps) {
+  T se = static_cast<T>(sqrt(mo.m2 / (mo.n - 1.0)));
+  const double e = static_cast<double>(static_cast<T>(eps));
+  if (seg[0] != nullptr && e > 0.0 && fabs(static_cast<double>(se) - e) <= std_err_window<T>(mo.n) * e)
+    se = sequential_std_err_segments<T>(seg, count, n_seg);
   return se;
 }
 

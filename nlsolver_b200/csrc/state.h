@@ -85,6 +85,10 @@ struct XchgWindow {
   unsigned long long *flags[kMaxPeers];     // base of rank r's flag area    [2][world]
   int world, rank;
   unsigned long long record_bytes;
+  // device groups (one process, every shard addressable): the shards' stop-statistic arrays in rank order, so that
+  // std_err can be re-evaluated exactly as the reference does when it lands near eps; NULL otherwise
+  const void *values[kMaxPeers];
+  unsigned long long counts[kMaxPeers];
 };
 
 // A batch of independent simulated-annealing chains (SANN::solve, nlsolver.h:2778-2815, once per chain).  Each chain

@@ -367,6 +367,148 @@ class ExchangeWindow:
             self._h = C.c_void_p()
 
 
+class DeviceGroup:
+    """Several GPUs driven from ONE process (nls_group_*): one context per device, peer access enabled between them."""
+
+    def __init__(self, devices):
+        devices = list(range(devices)) if isinstance(devices, int) else list(devices)
+        arr = (C.c_int * len(devices))(*devices)
+        self._h = C.c_void_p()
+        self.devices = devices
+        L.check(L.lib().nls_group_create(len(devices), arr, C.byref(self._h)))
+        self._children = weakref.WeakSet()
+
+    @property
+    def handle(self):
+        return self._h
+
+    def __len__(self):
+        return len(self.devices)
+
+    def close(self):
+        if self._h:
+            for child in list(self._children):
+                child.close()
+            L.lib().nls_group_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class _ShardView(PSOSwarm):
+    """A shard of a ShardedSwarm (owned by it): only the read-back calls are meaningful."""
+
+    def __init__(self, handle, cfg):
+        self._h, self.cfg, self.dt = handle, cfg, np_dtype(cfg.dtype)
+
+    def close(self):
+        self._h = C.c_void_p()
+
+
+class ShardedSwarm:
+    """One swarm over the devices of a group (nls_pso_sharded_*): identical to the same swarm on one GPU."""
+
+    def __init__(self, group, cfg, lower, upper):
+        self.group, self.cfg = group, cfg
+        self.dt = np_dtype(cfg.dtype)
+        lower = np.ascontiguousarray(lower, dtype=self.dt)
+        upper = np.ascontiguousarray(upper, dtype=self.dt)
+        self._h = C.c_void_p()
+        L.check(L.lib().nls_pso_sharded_create(group.handle, C.byref(cfg), lower.ctypes.data, upper.ctypes.data,
+                                               C.byref(self._h)))
+        group._children.add(self)
+
+    def step(self, n=1):
+        L.check(L.lib().nls_pso_sharded_step(self._h, n))
+
+    def sync(self):
+        st = L.Status()
+        L.check(L.lib().nls_pso_sharded_sync(self._h, C.byref(st)))
+        return st.as_dict()
+
+    def best(self):
+        x = np.zeros(self.cfg.dim, self.dt)
+        L.check(L.lib().nls_pso_sharded_read_best(self._h, x.ctypes.data))
+        return x
+
+    def positions(self):
+        """particle_positions of the whole swarm, shard after shard (global particle order)."""
+        parts, world, n = [], len(self.group), self.cfg.n_particles
+        for r in range(world):
+            h = C.c_void_p()
+            L.check(L.lib().nls_pso_sharded_shard(self._h, r, C.byref(h)))
+            base, extra = divmod(n, world)
+            local = pso_cfg(self.cfg.dtype, self.cfg.objective, self.cfg.pso_type, True, base + (1 if r < extra else 0),
+                            self.cfg.dim)
+            parts.append(_ShardView(h, local).positions())
+        return np.concatenate(parts)
+
+    def close(self):
+        if self._h:
+            L.lib().nls_pso_sharded_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class _IslandView(DEPopulation):
+    def __init__(self, handle, cfg):
+        self._h, self.cfg, self.dt = handle, cfg, np_dtype(cfg.dtype)
+
+    def close(self):
+        self._h = C.c_void_p()
+
+
+class DEIslands:
+    """One DE island per device of a group with ring migration over NVLink (nls_de_islands_*)."""
+
+    def __init__(self, group, cfg, x0, migrate_every=10, migrants=64):
+        self.group, self.cfg = group, cfg
+        self.dt = np_dtype(cfg.dtype)
+        x0 = np.ascontiguousarray(x0, dtype=self.dt)
+        self._h = C.c_void_p()
+        L.check(L.lib().nls_de_islands_create(group.handle, C.byref(cfg), x0.ctypes.data, migrate_every, migrants,
+                                              C.byref(self._h)))
+        group._children.add(self)
+
+    def step(self, n=1):
+        L.check(L.lib().nls_de_islands_step(self._h, n))
+
+    def sync(self):
+        st = L.Status()
+        L.check(L.lib().nls_de_islands_sync(self._h, C.byref(st)))
+        return st.as_dict()
+
+    def best(self):
+        x = np.zeros(self.cfg.dim, self.dt)
+        L.check(L.lib().nls_de_islands_read_best(self._h, x.ctypes.data))
+        return x
+
+    def island(self, rank):
+        h = C.c_void_p()
+        L.check(L.lib().nls_de_islands_island(self._h, rank, C.byref(h)))
+        return _IslandView(h, self.cfg)
+
+    def close(self):
+        if self._h:
+            L.lib().nls_de_islands_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def de_cfg(dtype=L.F64, objective=L.SPHERE, strategy=L.DE_RANDOM, minimize=True, pop_size=50, dim=2,
            crossover_prob=0.9, differential_weight=0.8, eps=10e-4, max_iter=1000, best_val_no_change=50, seed=0,
            agent_offset=0, flags=0):

@@ -231,3 +231,32 @@ def test_de_tma_staged_generation_matches_oracle(ctx, oracle_lib, monkeypatch, d
         so, ao = oracle_de(oracle_lib, dtype, obj, strategy, True, P, d, g, seed, x0, f=F)
         compare_generation(pop, st, so, ao, tol, g, check_decisions=True)
     pop.close()
+
+
+@pytest.mark.parametrize("dtype,obj,strategy,P,d,scale,F", [
+    (B.F64, B.SPHERE, B.DE_RANDOM, 1024, 64, 10.24, 0.5),        # 16 CTAs in the cluster
+    (B.F64, B.ROSENBROCK, B.DE_BEST, 50, 2, 4.096, 0.8),         # the reference's default shape: one CTA
+    (B.F32, B.RASTRIGIN, B.DE_RANDOM, 300, 40, 10.24, 0.3),
+    (B.F64, B.ACKLEY, B.DE_BEST, 16, 1000, 32.768, 0.8),         # few agents, long rows
+])
+def test_de_one_launch_path_equals_separate_kernels(ctx, monkeypatch, dtype, obj, strategy, P, d, scale, F):
+    """Populations of up to 2^16 elements run all the generations of a step in ONE launch on one thread-block cluster
+    (de_persistent_kernel); with NLS_DE_ONE_LAUNCH=0 the same step goes through the separate kernels (CUDA graph).  Both
+    must give the same bits: rows, scores, decisions of the last generation, counters — over several step sizes."""
+    seed, x0 = 77 + P, np.full(d, scale)
+    out = []
+    for env in ("1", "0"):
+        monkeypatch.setenv("NLS_DE_ONE_LAUNCH", env)
+        pop = gpu_de(ctx, dtype, obj, strategy, True, P, d, seed, x0, f=F, masks=False)
+        for n in (1, 9, 30):
+            pop.step(n)
+        st = pop.sync()
+        out.append((st, pop.population(), pop.scores(), pop.decisions()))
+        pop.close()
+    (sa, ra, ca, da), (sb, rb, cb, db) = out
+    assert sa["iterations"] == sb["iterations"] == 40
+    for k in ("f_value", "function_calls", "best_index", "val_no_change", "std_err", "accepted_total"):
+        assert sa[k] == sb[k], k
+    assert np.array_equal(bits(ra), bits(rb)) and np.array_equal(bits(ca), bits(cb))
+    for k in ("donors", "dim_idx", "rejects", "accepted", "trial_scores"):
+        assert np.array_equal(bits(da[k]), bits(db[k])), k

@@ -1,0 +1,150 @@
+"""Device groups (nls_group_*, nls_pso_sharded_*, nls_de_islands_*): several GPUs driven from ONE process over peer
+memory.  A swarm sharded over the group must equal the same swarm on one GPU bit for bit; islands must
+equal the harness-level restatement (each island a reference-exact DE, ring migration of the k best rows).
+With one visible GPU the group has one device (the exchange kernels of different shards wait on one another and must not
+share a device); the multi-device cases run where several GPUs are visible."""
+import numpy as np
+import pytest
+
+import nlsolver_b200 as nb
+from nlsolver_b200 import distributed as D
+from oracle import binding as B
+from tests.cpu_engines import oracle_de_cfg
+from tests.gpu_util import bits
+
+pytestmark = pytest.mark.gpu
+
+
+def group_sizes():
+    import torch
+    n = torch.cuda.device_count()
+    return [1] + ([2] if n >= 2 else []) + ([n] if n > 2 else [])
+
+
+def test_group_rejects_duplicate_devices():
+    with pytest.raises(nb.NlsError):
+        nb.DeviceGroup([0, 0])
+
+
+@pytest.mark.parametrize("ptype,obj,P,d", [(nb.PSO_ACCELERATED, nb.ACKLEY, 4096 + 3, 64), (nb.PSO_VANILLA, nb.SPHERE, 700, 33),
+                                           (nb.PSO_ACCELERATED, nb.RASTRIGIN, 40000, 256)])
+def test_sharded_swarm_over_group_equals_single_gpu_swarm(ptype, obj, P, d):
+    up = np.full(d, 5.12)
+    kw = dict(objective=obj, pso_type=ptype, n_particles=P, dim=d, eps=0.0, max_iter=1 << 40, best_val_no_change=1 << 40,
+              seed=123, flags=nb.FLAG_SOCIAL_INDEX_J if ptype == nb.PSO_VANILLA else 0)
+    ctx = nb.Context(0)
+    whole = nb.PSOSwarm(ctx, nb.pso_cfg(**kw), -up, up)
+    for n in (1, 8, 11):
+        whole.step(n)
+    ws, wpos, wbest = whole.sync(), whole.positions(), whole.best()
+    whole.close()
+    ctx.close()
+    for world in group_sizes():
+        group = nb.DeviceGroup(world)
+        sw = nb.ShardedSwarm(group, nb.pso_cfg(**kw), -up, up)
+        for n in (1, 8, 11):        # 8 goes through the per-device CUDA graphs for small shards
+            sw.step(n)
+        st = sw.sync()
+        for k in ("f_value", "iterations", "function_calls", "best_index", "val_no_change"):
+            assert st[k] == ws[k], (world, k)
+        assert np.array_equal(bits(sw.best()), bits(wbest)), world
+        assert np.array_equal(bits(sw.positions()), bits(wpos)), world
+        sw.close()
+        group.close()
+
+
+def test_sharded_swarm_stop_rule_uses_the_exact_std_err_over_all_shards():
+    """eps set to the std_err the single-GPU swarm reports at some generation: the sharded swarm must stop in the same
+    generation (the exact sequential re-evaluation reads every shard's particle_best_values over peer memory)."""
+    P, d = 999, 12
+    up = np.full(d, 5.12)
+    kw = dict(objective=nb.SPHERE, pso_type=nb.PSO_ACCELERATED, n_particles=P, dim=d, max_iter=400,
+              best_val_no_change=1 << 40, seed=7)
+    ctx = nb.Context(0)
+    probe = nb.PSOSwarm(ctx, nb.pso_cfg(eps=0.0, **kw), -up, up)
+    probe.step(25)
+    eps = probe.sync()["std_err"]          # a value the statistic actually takes: the stop test sits exactly on it
+    probe.close()
+    whole = nb.PSOSwarm(ctx, nb.pso_cfg(eps=eps, **kw), -up, up)
+    whole.step(400)
+    ws = whole.sync()
+    whole.close()
+    ctx.close()
+    assert ws["stopped"] and ws["stop_reason"] == 3
+    so, _ = B.pso_run(B.oracle(), B.pso_cfg(objective=B.SPHERE, pso_type=B.PSO_ACCELERATED, n_particles=P, dim=d, eps=eps,
+                                            max_iter=400, best_val_no_change=1 << 40, seed=7), -up, up)
+    assert ws["iterations"] == so["iterations"] and so["stop_reason"] == 3
+    for world in group_sizes():
+        group = nb.DeviceGroup(world)
+        sw = nb.ShardedSwarm(group, nb.pso_cfg(eps=eps, **kw), -up, up)
+        sw.step(400)
+        st = sw.sync()
+        assert st["stopped"] and st["stop_reason"] == 3 and st["iterations"] == ws["iterations"], world
+        sw.close()
+        group.close()
+
+
+@pytest.mark.parametrize("obj,strategy,P,d", [(nb.ROSENBROCK, nb.DE_BEST, 300, 12), (nb.SPHERE, nb.DE_RANDOM, 2000, 64)])
+def test_islands_over_group_match_restatement(obj, strategy, P, d):
+    every, k, gens = 3, 5, 11
+    kw = dict(objective=obj, strategy=strategy, pop_size=P, dim=d, eps=0.0, max_iter=1 << 40, best_val_no_change=1 << 40,
+              seed=21)
+    x0 = np.full(d, 4.096)
+    for world in group_sizes():
+        group = nb.DeviceGroup(world)
+        isl = nb.DEIslands(group, nb.de_cfg(**kw), x0, migrate_every=every, migrants=k)
+        isl.step(4)
+        isl.step(gens - 4)
+        st = isl.sync()
+        cpu = [B.DEStepper(oracle_de_cfg(nb.de_cfg(**dict(kw, agent_offset=r * P))), x0) for r in range(world)]
+        for g in range(1, gens + 1):
+            for s in cpu:
+                s.advance(1)
+            if D.migration_due(g, every) and world > 1:
+                out = [s.export_top(k) for s in cpu]
+                for r, s in enumerate(cpu):
+                    s.import_migrants(*out[D.ring_neighbors(r, world)[1]])
+        want = [s.report() for s in cpu]
+        for r in range(world):
+            view = isl.island(r)
+            assert np.array_equal(bits(view.population()), bits(want[r][1]["rows"])), (world, r)
+            assert np.array_equal(bits(view.scores()), bits(want[r][1]["scores"])), (world, r)
+        best_rank = min(range(world), key=lambda r: (want[r][0]["f_value"], r))
+        assert st["f_value"] == want[best_rank][0]["f_value"]
+        assert st["best_index"] == best_rank * P + want[best_rank][0]["best_index"]
+        assert st["iterations"] == gens and st["function_calls"] == world * P * (gens + 1)
+        assert np.array_equal(bits(isl.best()), bits(want[best_rank][1]["x_best"]))
+        isl.close()
+        group.close()
+
+
+def test_one_shot_group_solves_match_single_gpu():
+    """nls_pso_solve_sharded == nls_pso_solve (any group size); nls_de_solve_islands with one device == nls_de_solve."""
+    import ctypes as C
+    from nlsolver_b200 import _lib as L
+    d = 6
+    up = np.full(d, 5.12)
+    pcfg = nb.pso_cfg(objective=nb.SPHERE, pso_type=nb.PSO_ACCELERATED, n_particles=500, dim=d, seed=3)
+    ctx = nb.Context(0)
+    x1, s1 = np.zeros(d), L.Status()
+    L.check(L.lib().nls_pso_solve(ctx.handle, C.byref(pcfg), (-up).ctypes.data, up.ctypes.data, x1.ctypes.data, C.byref(s1)))
+    dcfg = nb.de_cfg(objective=nb.ROSENBROCK_EX, pop_size=50, dim=2, seed=11)
+    x0 = np.array([5.0, 7.0])
+    y1, t1 = np.zeros(2), L.Status()
+    L.check(L.lib().nls_de_solve(ctx.handle, C.byref(dcfg), x0.ctypes.data, y1.ctypes.data, C.byref(t1)))
+    ctx.close()
+    for world in group_sizes():
+        group = nb.DeviceGroup(world)
+        x2, s2 = np.zeros(d), L.Status()
+        L.check(L.lib().nls_pso_solve_sharded(group.handle, C.byref(pcfg), (-up).ctypes.data, up.ctypes.data,
+                                              x2.ctypes.data, C.byref(s2)))
+        assert (s2.f_value, s2.iterations, s2.function_calls, s2.stop_reason) == (s1.f_value, s1.iterations,
+                                                                                  s1.function_calls, s1.stop_reason)
+        assert np.array_equal(bits(x2), bits(x1))
+        if world == 1:
+            y2, t2 = np.zeros(2), L.Status()
+            L.check(L.lib().nls_de_solve_islands(group.handle, C.byref(dcfg), x0.ctypes.data, 10, 8, y2.ctypes.data,
+                                                 C.byref(t2)))
+            assert (t2.f_value, t2.iterations, t2.function_calls) == (t1.f_value, t1.iterations, t1.function_calls)
+            assert np.array_equal(bits(y2), bits(y1))
+        group.close()

@@ -183,3 +183,28 @@ def test_fused_peer_exchange_single_rank_equals_plain_step(ctx):
     fused.close()
     win.close()
     plain.close()
+
+
+@pytest.mark.parametrize("dtype,obj,ptype,P,d", [(B.F64, B.ACKLEY, B.PSO_ACCELERATED, 1024, 64),
+                                                (B.F64, B.SPHERE, B.PSO_VANILLA, 10, 16),
+                                                (B.F32, B.SPHERE, B.PSO_ACCELERATED, 300, 40),
+                                                (B.F64, B.ROSENBROCK, B.PSO_VANILLA, 64, 200)])
+def test_pso_one_launch_path_equals_separate_kernels(ctx, monkeypatch, dtype, obj, ptype, P, d):
+    """Swarms of up to 2^16 elements run a whole step in ONE launch on one thread-block cluster (pso_persistent_kernel);
+    NLS_DE_ONE_LAUNCH=0 keeps the separate kernels.  Same bits either way."""
+    up = np.full(d, 5.12)
+    out = []
+    for env in ("1", "0"):
+        monkeypatch.setenv("NLS_DE_ONE_LAUNCH", env)
+        sw = nb.PSOSwarm(ctx, nb.pso_cfg(dtype=dtype, objective=obj, pso_type=ptype, n_particles=P, dim=d, eps=0.0,
+                                         max_iter=1 << 40, best_val_no_change=1 << 40, seed=5), -up, up)
+        for n in (1, 9, 30):
+            sw.step(n)
+        st = sw.sync()
+        out.append((st, sw.positions(), sw.pbest_values(), sw.best()))
+        sw.close()
+    (sa, pa, ba, xa), (sb, pb, bb, xb) = out
+    assert sa["iterations"] == sb["iterations"] == 40
+    for k in ("f_value", "function_calls", "best_index", "val_no_change", "std_err"):
+        assert sa[k] == sb[k], k
+    assert np.array_equal(bits(pa), bits(pb)) and np.array_equal(bits(ba), bits(bb)) and np.array_equal(bits(xa), bits(xb))
