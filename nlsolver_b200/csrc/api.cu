@@ -19,6 +19,7 @@
 
 #include "../../include/nls_b200.h"
 #include "common.cuh"
+#include "de_tiny.cuh"
 #include "launch.h"
 #include "reduce.cuh"
 #include "state.h"
@@ -114,6 +115,8 @@ struct nls_ctx {
   // pin every population it ever used.
   std::vector<std::pair<void *, size_t>> pool;   // oldest first
   size_t pool_bytes = 0;
+  void *tiny_host = nullptr;    // mapped host memory the one-block tiny solver writes its result to (de_tiny.cuh)
+  void *tiny_dev = nullptr;
   size_t pool_limit = 0;        // 0: automatic (the largest single handle released so far)
   size_t largest_handle = 0;
   void evict_to(size_t cap) {
@@ -329,6 +332,7 @@ int nls_ctx_destroy(nls_ctx *ctx) {
   if (!ctx) return NLS_OK;
   cudaSetDevice(ctx->device);
   for (auto &b : ctx->pool) cudaFree(b.first);
+  if (ctx->tiny_host) cudaFreeHost(ctx->tiny_host);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
   return NLS_OK;
@@ -464,12 +468,19 @@ int nls_de_create(nls_ctx *ctx, const nls_de_cfg *cfg, const void *x0_host, nls_
   return NLS_OK;
 }
 
-// Populations of up to kPersistMaxElems elements take the one-launch path: all the generations of a step in one kernel
-// on one thread-block cluster (de_persistent_kernel); NLS_DE_ONE_LAUNCH=0 in the environment keeps the graph path.
+// Small populations can take the one-launch path: all the generations of a step in one kernel on one thread-block
+// cluster (de_persistent_kernel / pso_persistent_kernel).  Measured on B200 (tools/bench_small.py): 27 against 36 us per
+// generation at pop 50 x 2, but no gain over the graph replay at 1024 x 64 and beyond (16 us either way: the latency
+// chain of the three passes is the same, only the launches go), and slower for the accelerated move.  So by default
+// only populations of up to kPersistDefaultAgents agents take it; NLS_DE_ONE_LAUNCH=1 in the environment sends every
+// population of up to kPersistMaxElems elements there, NLS_DE_ONE_LAUNCH=0 none.
 constexpr unsigned long long kPersistMaxElems = 1ull << 16;
-static bool de_one_launch_enabled() {
+constexpr unsigned long long kPersistDefaultAgents = 256;
+static bool de_one_launch_enabled(unsigned long long agents) {
   const char *e = std::getenv("NLS_DE_ONE_LAUNCH");
-  return !(e && e[0] == '0');
+  if (e && e[0] == '0') return false;
+  if (e && e[0] == '1') return true;
+  return agents <= kPersistDefaultAgents;
 }
 
 int nls_de_step(nls_de *de, uint64_t n_generations) {
@@ -477,7 +488,7 @@ int nls_de_step(nls_de *de, uint64_t n_generations) {
   NLS_CUDA(cudaSetDevice(de->ctx->device));
   uint64_t left = n_generations;
   if (!de->timing && left > 0 && de->s.P * de->s.d <= kPersistMaxElems && de->ops->persistent && !de->persistent_failed &&
-      de_one_launch_enabled()) {
+      de_one_launch_enabled(de->s.P)) {
     if (de->ops->persistent(de->s, left, de->ctx->stream) == cudaSuccess) return NLS_OK;
     cudaGetLastError();
     de->persistent_failed = true;                 // e.g. no cluster launch on this device: the graph path still works
@@ -675,8 +686,69 @@ int nls_de_import_migrants(nls_de *de, uint64_t k, const void *rows_dev, const v
   return NLS_OK;
 }
 
+// Tiny problems (the reference's own shapes: pop_size 50, 2-D): the whole solve in one launch of one block with the
+// population in shared memory and the result written to mapped host memory (de_tiny.cuh).  NLS_DE_TINY=0 in the
+// environment sends them through the general kernels instead (same results).
+static bool de_tiny_eligible(const nls_de_cfg *c) {
+  const char *e = std::getenv("NLS_DE_TINY");
+  if (e && e[0] == '0') return false;
+  return c->pop_size <= kTinyMaxPop && c->dim <= kTinyMaxDim && c->objective >= 0 && c->objective < NLS_OBJECTIVE_COUNT &&
+         c->flags == 0 && !guard_mode();
+}
+static int de_solve_tiny(nls_ctx *ctx, const nls_de_cfg *cfg, const void *x0_host, void *x_best_host, nls_status *status) {
+  NLS_CUDA(cudaSetDevice(ctx->device));
+  if (!ctx->tiny_host) {
+    NLS_CUDA(cudaHostAlloc(&ctx->tiny_host, sizeof(DETinyResult), cudaHostAllocMapped));
+    NLS_CUDA(cudaHostGetDevicePointer(&ctx->tiny_dev, ctx->tiny_host, 0));
+  }
+  DETinyArgs a;
+  std::memset(&a, 0, sizeof(a));
+  a.P = unsigned(cfg->pop_size); a.d = unsigned(cfg->dim);
+  a.seed = cfg->seed; a.offset = cfg->agent_offset;
+  a.max_iter = cfg->max_iter; a.vnc_limit = cfg->best_val_no_change;
+  a.strategy = cfg->strategy;
+  a.F = cfg->differential_weight; a.fm = cfg->minimize ? 1.0 : -1.0; a.eps = cfg->eps;
+  u64 cr_le; int cr_none;
+  if (cfg->dtype == NLS_F64) crossover_threshold<double>(cfg->crossover_prob, &cr_le, &cr_none);
+  else crossover_threshold<float>(cfg->crossover_prob, &cr_le, &cr_none);
+  a.cr_le = cr_le; a.cr_none = cr_none;
+  for (u64 j = 0; j < cfg->dim; j++)
+    a.x0[j] = cfg->dtype == NLS_F64 ? static_cast<const double *>(x0_host)[j]
+                                    : static_cast<double>(static_cast<const float *>(x0_host)[j]);
+  a.result = ctx->tiny_dev;
+  NLS_CUDA(cfg->dtype == NLS_F64 ? de_tiny_launch_f64(cfg->objective, a, ctx->stream)
+                                 : de_tiny_launch_f32(cfg->objective, a, ctx->stream));
+  NLS_CUDA(cudaStreamSynchronize(ctx->stream));
+  const DETinyResult *r = static_cast<const DETinyResult *>(ctx->tiny_host);
+  for (u64 j = 0; j < cfg->dim; j++) {
+    if (cfg->dtype == NLS_F64) static_cast<double *>(x_best_host)[j] = r->x[j];
+    else static_cast<float *>(x_best_host)[j] = static_cast<float>(r->x[j]);
+  }
+  if (status) {
+    std::memset(status, 0, sizeof(*status));
+    status->f_value = r->f_value;
+    status->iterations = r->iterations;
+    status->function_calls = cfg->pop_size * (r->iterations + 1);
+    status->best_index = r->best_id;
+    status->val_no_change = r->vnc;
+    status->stopped = 1;
+    status->stop_reason = r->stop_reason;
+    status->best_valid = 1;
+    status->std_err = r->std_err;
+    status->repair_reruns = r->reruns;
+    status->repair_rounds = r->rounds;
+    status->accepted_total = r->accepted;
+  }
+  return NLS_OK;
+}
+
 int nls_de_solve(nls_ctx *ctx, const nls_de_cfg *cfg, const void *x0_host, void *x_best_host, nls_status *status) {
   if (!x_best_host) return fail(NLS_ERR_INVALID, "nls_de_solve: x_best_host is NULL");
+  if (ctx && cfg && x0_host && de_tiny_eligible(cfg)) {
+    int rc = de_validate(cfg);
+    if (rc != NLS_OK) return rc;
+    return de_solve_tiny(ctx, cfg, x0_host, x_best_host, status);
+  }
   nls_de *de = nullptr;
   int rc = nls_de_create(ctx, cfg, x0_host, &de);
   if (rc != NLS_OK) return rc;
@@ -858,7 +930,7 @@ int nls_pso_step(nls_pso *p, uint64_t n_generations) {
   if (p->s.P_global != p->s.P) return fail(NLS_ERR_STATE, "nls_pso_step is for a single-GPU swarm; a shard uses step_local / apply_candidates");
   uint64_t left = n_generations;
   if (left > 0 && p->s.P * p->s.d <= kPersistMaxElems && !p->first_apply_pending && p->ops->persistent &&
-      !p->persistent_failed && de_one_launch_enabled()) {
+      !p->persistent_failed && de_one_launch_enabled(p->s.P)) {
     NLS_CUDA(cudaSetDevice(p->ctx->device));
     if (p->ops->persistent(p->s, p->record, p->record_bytes, left, p->ctx->stream) == cudaSuccess) {
       p->enqueued += left;

@@ -60,6 +60,16 @@ template <> __device__ __forceinline__ u64 index_from<float>(u64 raw, u64 max_) 
   return v >= max_ ? max_ - 1 : v;
 }
 
+// generate_indices (nlsolver.h:2331-2355): draw until three proposals differ from `fixed` and from each other.
+template <class T>
+__device__ __forceinline__ void de_select_donors(u64 key, u64 P, u64 fixed, u64 &r1, u64 &r2, u64 &r3, u32 &rej) {
+  u64 k = 0;
+  rej = 0;
+  for (;;) { r1 = index_from<T>(tape_draw(key, k++), P); if (r1 != fixed) break; rej++; }
+  for (;;) { r2 = index_from<T>(tape_draw(key, k++), P); if (r2 != fixed && r2 != r1) break; rej++; }
+  for (;;) { r3 = index_from<T>(tape_draw(key, k++), P); if (r3 != fixed && r3 != r1 && r3 != r2) break; rej++; }
+}
+
 // 16-byte vectors: V coordinates per lane per step
 template <class T> struct Vec;
 template <> struct Vec<double> { typedef double2 type; static constexpr int V = 2; };

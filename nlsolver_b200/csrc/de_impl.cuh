@@ -169,16 +169,6 @@ __global__ void __launch_bounds__(kBlock) de_init_kernel(DEState s, const T *__r
 }
 
 // ------------------------------------------------------------------------------------------------ K2 generation
-// generate_indices (nlsolver.h:2331-2355): draw until three proposals differ from `fixed` and from each other.
-template <class T>
-__device__ __forceinline__ void de_select_donors(u64 key, u64 P, u64 fixed, u64 &r1, u64 &r2, u64 &r3, u32 &rej) {
-  u64 k = 0;
-  rej = 0;
-  for (;;) { r1 = index_from<T>(tape_draw(key, k++), P); if (r1 != fixed) break; rej++; }
-  for (;;) { r2 = index_from<T>(tape_draw(key, k++), P); if (r2 != fixed && r2 != r1) break; rej++; }
-  for (;;) { r3 = index_from<T>(tape_draw(key, k++), P); if (r3 != fixed && r3 != r1 && r3 != r2) break; rej++; }
-}
-
 // What the lane-parallel prologue hands to the cooperative part, one entry per agent of the tile (shared memory).
 struct __align__(16) DETileEntry {
   unsigned long long key;      // draw stream of (generation, agent)
@@ -770,6 +760,7 @@ __global__ void __launch_bounds__(kBlock) de_gather_rows_kernel(DEState s, u64 f
 }
 
 // ------------------------------------------------------------------------------------------------ host launchers
+constexpr int kMaxDevices = 64;
 template <class K>
 inline int blocks_per_sm(K kernel) {
   int n = 0;
@@ -873,12 +864,17 @@ template <class T, int O, int kStages, int kSteps>
 void de_launch_k2_bulk(const DEState &s, const LaunchGeom &g, cudaStream_t st) {
   auto kernel = de_generation_bulk_kernel<T, O, kStages, kSteps>;
   constexpr size_t smem = size_t(kWarpsPerBlock) * kStages * 4 * 512 * kSteps;
-  static const int per_sm = [&] {
+  // function attributes are per DEVICE: a device group launches the same kernel on several of them
+  static int per_sm_of[kMaxDevices] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  int &per_sm = per_sm_of[dev % kMaxDevices];
+  if (per_sm == 0) {
     cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     int n = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, kBlock, smem);
-    return n < 1 ? 1 : n;
-  }();
+    per_sm = n < 1 ? 1 : n;
+  }
   const u64 want = (s.P + kWarpsPerBlock - 1) / kWarpsPerBlock;
   const unsigned int grid = clamp_grid(want, u64(g.sm_count) * per_sm);
   int shift = 5;                                       // largest tile that still gives >= 8 tiles per warp

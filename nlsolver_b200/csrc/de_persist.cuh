@@ -36,7 +36,12 @@ constexpr int kMaxClusterBlocks = 16;                      // > 8 needs the non-
 template <class T, int O, int W, int U, int S, bool SKIP_BASE>
 cudaError_t de_launch_persistent_w(const DEState &s, unsigned long long n_generations, cudaStream_t st) {
   auto kernel = de_persistent_kernel<T, O, W, U, S, SKIP_BASE>;
-  static const bool wide_ok = cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess;
+  static signed char wide_of[kMaxDevices] = {};           // per DEVICE: 0 unknown, 1 allowed, -1 refused
+  int dev = 0;
+  cudaGetDevice(&dev);
+  signed char &wide = wide_of[dev % kMaxDevices];
+  if (wide == 0) wide = cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess ? 1 : -1;
+  const bool wide_ok = wide > 0;
   // one warp streams 32 / W agents at a time; aim at two such sweeps per warp and generation
   const u64 per_block = u64(kWarpsPerBlock) * (32 / W) * 2;
   int blocks = int(std::min<u64>((s.P + per_block - 1) / per_block, wide_ok ? kMaxClusterBlocks : 8));

@@ -41,6 +41,10 @@ struct SANNOps {
   cudaError_t (*gather)(const SANNState &s, int which, void *out, const LaunchGeom &g, cudaStream_t st);
   cudaError_t (*best)(const SANNState &s, cudaStream_t st);
 };
+// tiny DE problems (pop_size <= 1024, dim <= 8, built-in objectives): the whole solve in one launch of one block
+struct DETinyArgs;
+cudaError_t de_tiny_launch_f64(int objective, const DETinyArgs &a, cudaStream_t st);
+cudaError_t de_tiny_launch_f32(int objective, const DETinyArgs &a, cudaStream_t st);
 const SANNOps *sann_ops_f64();
 const SANNOps *sann_ops_f32();
 const DEOps *de_ops_f64();

@@ -27,7 +27,12 @@ __global__ void __launch_bounds__(kBlock, 1) pso_persistent_kernel(PSOState s, v
 template <class T, int O, int TYPE, int W, int U, int S>
 cudaError_t pso_launch_persistent_w(const PSOState &s, void *record, u64 record_bytes, unsigned long long n, cudaStream_t st) {
   auto kernel = pso_persistent_kernel<T, O, TYPE, W, U, S>;
-  static const bool wide_ok = cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess;
+  static signed char wide_of[64] = {};           // per DEVICE: 0 unknown, 1 allowed, -1 refused
+  int dev = 0;
+  cudaGetDevice(&dev);
+  signed char &wide = wide_of[dev % 64];
+  if (wide == 0) wide = cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess ? 1 : -1;
+  const bool wide_ok = wide > 0;
   const u64 per_block = u64(kWarpsPerBlock) * (32 / W) * 2;   // two sweeps per warp and generation
   int blocks = int(std::min<u64>((s.P + per_block - 1) / per_block, wide_ok ? 16 : 8));
   if (blocks < 1) blocks = 1;

@@ -106,6 +106,34 @@ typedef struct {
   uint64_t *iterations, *function_calls; /* [n_chains] as solver_status reports them */
 } orc_sann_out;
 
+/* ---- NelderMeadPSO as a batch of independent solvers (nlsolver.h:3546-3920 is one solver) ----
+ * Tape: solver s draws from stream (tag, global solver id); tag 0 serves init_solver_state (nlsolver.h:3712-3721: for
+ * every PSO particle p = 0 .. 2n-1 and coordinate j the position draw k = 2 (p n + j), then the velocity draw k + 1),
+ * tag it + 1 serves apply_pso of loop iteration it (nlsolver.h:3843-3847: for the q-th PSO particle in sorted order
+ * and coordinate j, r_p = draw 2 (q n + j), r_g = the next one).  Both consume exactly 4 n^2 draws, so the unmodified
+ * reference is fed the same tape by counting.  Only the unbounded overloads exist here: the bounded ones clamp with
+ * lower[i] / upper[i] indexed by the PARTICLE loop counter (nlsolver.h:3859), which is out of bounds for every particle.
+ * The reference's initial simplex writes particle_positions[n][n] and reads x[n] (nlsolver.h:3697-3700, one element past
+ * the end); the restatement ignores that store.  With glibc it lands in allocator slack for some n (fp64: even n; fp32:
+ * 2, 4, 8, 12, ...) and corrupts the heap for the others, which the reference harness therefore refuses (returns -1). */
+typedef struct {
+  int32_t dtype, objective, minimize, rng_mode;
+  uint64_t n_solvers, dim;
+  double alpha, gamma, rho, sigma, inertia, cognitive_coef, social_coef, eps; /* defaults 1, 2, .5, .5, .8, 1.8, 1.8, 1e-6 */
+  uint64_t max_iter, no_change_best_iter;                                     /* defaults 1000, 20 */
+  uint64_t seed, solver_offset;
+  uint64_t xs_state[2];
+  uint64_t x0_count; /* 1: every solver starts from the same x0[d]; n_solvers: x0[n_solvers*d] */
+} orc_nmpso_cfg;
+
+typedef struct {
+  void *x_best;  /* [n_solvers*d] */
+  void *f_best;  /* [n_solvers] */
+  uint64_t *iterations, *function_calls, *draws; /* [n_solvers] */
+  uint8_t *ties; /* [n_solvers] 1 if a sort ever compared two equal values (std::sort is unstable: the reference's
+                    order is then whatever libstdc++ produces; parity cases must be tie-free) */
+} orc_nmpso_out;
+
 #ifdef __cplusplus
 }
 #endif

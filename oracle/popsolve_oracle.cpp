@@ -597,6 +597,182 @@ int sann_dispatch(const orc_sann_cfg *c, const void *x0v, const orc_sann_out *ou
   return 0;
 }
 
+/* ---------------------------------------------------------------- NelderMeadPSO -------------------------- */
+/* One NelderMeadPSO::solve<minimize, false> (nlsolver.h:3615-3920) with the accidents of the reference kept:
+ *   - init_solver_state (:3679-3729): the nested loops share `i`, so the body runs once; simplex vertex v (1 <= v < n)
+ *     is x with coordinate v raised by `scale` (coordinate 0 is never raised on its own), vertex n is x itself (the
+ *     store to [n][n] is out of bounds and ignored here), vertex 0 is x + (1 - sqrt(n + 1)) / n * scale in every
+ *     coordinate; PSO particles draw position and velocity interleaved;
+ *   - best_val is set once from particle 0 and never updated (:3650), so best_val_no_change only counts iterations
+ *     whose best value EQUALS that initial value;
+ *   - apply_pso (:3824-3868): `velocity` and `pairwise_best` are by-value copies (only the first declarator of that
+ *     line is a reference), so velocities never change; the pair's reference particle is current_order[i + 1] from
+ *     the second pair on (the worse of the pair);
+ *   - std::sort is unstable: `ties` reports whether two compared values were ever equal. */
+template <class T, class Src>
+void nmpso_solve(const orc_nmpso_cfg &c, u64 solver, const T *x0, Src &src, T *x_out, T *f_out, u64 *iters_out,
+                 u64 *evals_out, uint8_t *ties_out) {
+  const size_t n = c.dim, ns = n + 1, np = 2 * n, N = ns + np;
+  const T fm = c.minimize ? static_cast<T>(1.0) : static_cast<T>(-1.0);
+  const T alpha = static_cast<T>(c.alpha), gamma = static_cast<T>(c.gamma), rho = static_cast<T>(c.rho),
+          sigma = static_cast<T>(c.sigma), inertia = static_cast<T>(c.inertia), cog = static_cast<T>(c.cognitive_coef),
+          soc = static_cast<T>(c.social_coef), eps = static_cast<T>(c.eps);
+  std::vector<T> x(x0, x0 + n), lower(n), upper(n);
+  for (size_t i = 0; i < n; i++) {                                     /* minimize(x), :3583-3593 */
+    const T temp = std::abs(2.5 * x[i]);
+    lower[i] = -temp; upper[i] = temp;
+  }
+  std::vector<std::vector<T>> pos(N, std::vector<T>(n)), vel(N, std::vector<T>(n, 0.0));
+  std::vector<T> val(N);
+  u64 evals = 0;
+  uint8_t ties = 0;
+  pos[0] = x;                                                          /* :3691 */
+  if (ns > 1) {                                                        /* :3692-3708, executed once */
+    T x_inf_norm = std::abs(x[0]);                                     /* max_abs_vec, :1894-1904 */
+    for (size_t i = 1; i < n; i++) { const T t = std::abs(x[i]); if (x_inf_norm < t) x_inf_norm = t; }
+    const T a = x_inf_norm < 1.0 ? 1.0 : x_inf_norm;
+    const T scale = a < 10 ? a : 10;
+    for (size_t i = 1; i < ns; i++) {
+      pos[i] = x;
+      if (i < n) pos[i][i] = x[i] + scale;                             /* i == n: out of bounds in the reference */
+    }
+    const T nn = static_cast<T>(n);
+    for (size_t i = 0; i < n; i++) pos[0][i] = x[i] + ((1.0 - sqrt(nn + 1.0)) / nn * scale);
+  }
+  src.begin(0, solver);
+  for (size_t i = ns; i < N; i++)                                      /* :3710-3721 */
+    for (size_t j = 0; j < n; j++) {
+      const T temp = std::abs(upper[j] - lower[j]);
+      pos[i][j] = lower[j] + ((upper[j] - lower[j]) * unit<T>(src.next()));
+      vel[i][j] = -temp + (unit<T>(src.next()) * temp);
+    }
+  for (size_t i = 0; i < N; i++) { val[i] = fm * objective<T>(c.objective, pos[i].data(), n); evals++; }   /* :3723-3727 */
+  std::vector<T> centroid(n), t_ref(n), t_exp(n), t_con(n);
+  std::vector<size_t> order(N);
+  for (size_t i = 0; i < N; i++) order[i] = i;
+  auto sort_order = [&]() {
+    std::sort(order.begin(), order.end(), [&](size_t l, size_t r) { if (l != r && val[l] == val[r]) ties = 1; return val[l] < val[r]; });
+  };
+  auto transform = [&](const std::vector<T> &point, std::vector<T> &result, T coef, bool reflect) {   /* :1988-2010 */
+    for (size_t i = 0; i < n; i++)
+      result[i] = reflect ? centroid[i] + coef * (centroid[i] - point[i]) : centroid[i] + coef * (point[i] - centroid[i]);
+  };
+  u64 iter = 0, no_change = 0;
+  const T best_val = val[0];                                           /* :3650, never updated */
+  while (true) {
+    sort_order();                                                      /* :3654-3658 */
+    const bool same = best_val == val[order[0]];
+    no_change += same; no_change *= same;                              /* :3663-3664 */
+    bool stop = iter >= c.max_iter || no_change >= c.no_change_best_iter;
+    if (!stop) {                                                       /* simplex_std_err, :3901-3918 */
+      T mean_val = 0, result = 0;
+      for (size_t i = 0; i < ns; i++) mean_val += val[order[i]];
+      mean_val /= static_cast<T>(ns);
+      for (size_t i = 0; i < ns; i++) result += pow(val[order[i]] - mean_val, 2);
+      result /= (T)(ns - 1);
+      stop = static_cast<T>(sqrt(result)) < eps;
+    }
+    if (stop) break;
+    /* ---- apply_simplex, :3731-3822 */
+    {
+      const T best_score = val[order[0]];
+      const size_t worst = order[ns - 1], second = order[ns - 2];
+      std::fill(centroid.begin(), centroid.end(), 0.0);                /* update_centroid, :3869-3885 */
+      for (size_t i = 0; i < ns - 1; i++)
+        for (size_t j = 0; j < n; j++) centroid[j] += pos[order[i]][j];
+      for (auto &v : centroid) v /= static_cast<T>(ns - 1);
+      transform(pos[worst], t_ref, alpha, true);
+      const T ref_score = fm * objective<T>(c.objective, t_ref.data(), n); evals++;
+      if (ref_score >= best_score && ref_score < val[second]) {
+        pos[worst] = t_ref; val[worst] = ref_score;
+      } else if (ref_score < best_score) {
+        transform(t_ref, t_exp, gamma, false);
+        const T exp_score = fm * objective<T>(c.objective, t_exp.data(), n); evals++;
+        pos[worst] = exp_score < ref_score ? t_exp : t_ref;
+        val[worst] = exp_score < ref_score ? exp_score : ref_score;
+      } else {
+        const T worst_score = val[worst];
+        transform(ref_score < worst_score ? t_ref : pos[worst], t_con, rho, false);
+        const T cont_score = fm * objective<T>(c.objective, t_con.data(), n); evals++;
+        if (cont_score < std::min(ref_score, worst_score)) {
+          pos[worst] = t_con; val[worst] = cont_score;
+        } else {
+          const std::vector<T> &best = pos[order[0]];                  /* shrink, :3886-3900 */
+          for (size_t i = 1; i < ns; i++) {
+            std::vector<T> &cur = pos[order[i]];
+            for (size_t j = 0; j < n; j++) cur[j] = best[j] + sigma * (cur[j] - best[j]);
+          }
+          for (size_t i = 1; i < ns; i++) val[order[i]] = fm * objective<T>(c.objective, pos[order[i]].data(), n);
+          evals += ns - 1;
+          sort_order();
+        }
+      }
+    }
+    /* ---- apply_pso, :3824-3868 */
+    {
+      src.begin(iter + 1, solver);
+      bool order_flip = false;
+      size_t best_in_pair = order[ns];
+      const std::vector<T> &best = pos[order[0]];
+      for (size_t i = ns; i < N; i++) {
+        const size_t id = order[i];
+        if (order_flip) best_in_pair = order[i + 1];
+        order_flip = static_cast<bool>((i - ns) % 2);
+        std::vector<T> &particle = pos[id];
+        const std::vector<T> velocity = vel[id], pairwise_best = pos[best_in_pair];   /* copies */
+        for (size_t j = 0; j < n; j++) {
+          const T r_p = unit<T>(src.next()), r_g = unit<T>(src.next());
+          const T temp = (inertia * velocity[j]) + cog * r_p * (pairwise_best[j] - particle[j]) +
+                         soc * r_g * (best[j] - particle[j]);
+          particle[j] += temp;
+        }
+        val[id] = fm * objective<T>(c.objective, particle.data(), n); evals++;
+      }
+    }
+    iter++;
+  }
+  std::memcpy(x_out, pos[order[0]].data(), n * sizeof(T));
+  *f_out = val[order[0]]; *iters_out = iter; *evals_out = evals; *ties_out = ties;
+}
+
+template <class T>
+int nmpso_dispatch(const orc_nmpso_cfg *c, const void *x0v, const orc_nmpso_out *out, orc_status *st) {
+  if (c->n_solvers < 1 || c->dim < 2 || (c->x0_count != 1 && c->x0_count != c->n_solvers)) return -1;
+  const T *x0 = static_cast<const T *>(x0v);
+  const size_t d = c->dim;
+  SeqSource seq(c->xs_state);
+  T best_f = 0; u64 best_solver = 0, iters = 0, evals_total = 0, draws_total = 0;
+  std::vector<T> xb(d);
+  for (u64 s = 0; s < c->n_solvers; s++) {
+    const T *start = x0 + (c->x0_count == 1 ? 0 : s * d);
+    T f; u64 it, ev, draws; uint8_t ties;
+    if (c->rng_mode == ORC_RNG_TAPE) {
+      TapeSource src(c->seed, c->solver_offset);
+      nmpso_solve<T>(*c, s, start, src, xb.data(), &f, &it, &ev, &ties);
+      draws = src.total;
+    } else {
+      const u64 before = seq.total;
+      nmpso_solve<T>(*c, s, start, seq, xb.data(), &f, &it, &ev, &ties);
+      draws = seq.total - before;
+    }
+    if (s == 0 || f < best_f) { best_f = f; best_solver = s; }
+    iters = it; evals_total += ev; draws_total += draws;
+    if (!out) continue;
+    if (out->x_best) std::memcpy(static_cast<T *>(out->x_best) + s * d, xb.data(), d * sizeof(T));
+    if (out->f_best) static_cast<T *>(out->f_best)[s] = f;
+    if (out->iterations) out->iterations[s] = it;
+    if (out->function_calls) out->function_calls[s] = ev;
+    if (out->draws) out->draws[s] = draws;
+    if (out->ties) out->ties[s] = ties;
+  }
+  if (st) {
+    std::memset(st, 0, sizeof(*st));
+    st->f_value = best_f; st->iterations = iters; st->function_calls = evals_total; st->best_index = best_solver;
+    st->draws_consumed = draws_total; st->best_valid = 1;
+  }
+  return 0;
+}
+
 template <class T>
 int de_dispatch(const orc_de_cfg *c, const void *x0, const orc_de_out *out, orc_status *st) {
   if (c->pop_size < 4 || c->dim < 1) return -1;     /* the reference loops forever for pop < 4 (:2344-2354) */
@@ -626,6 +802,9 @@ int oracle_pso_run(const orc_pso_cfg *c, const void *lower, const void *upper, c
                              : pso_dispatch<float>(c, lower, upper, out, st);
 }
 /* a batch of SANN chains; the batch status reports the best chain (lowest value, lowest chain index on ties) */
+int oracle_nmpso_run(const orc_nmpso_cfg *c, const void *x0, const orc_nmpso_out *out, orc_status *st) {
+  return c->dtype == ORC_F64 ? nmpso_dispatch<double>(c, x0, out, st) : nmpso_dispatch<float>(c, x0, out, st);
+}
 int oracle_sann_run(const orc_sann_cfg *c, const void *x0, const orc_sann_out *out, orc_status *st) {
   return c->dtype == ORC_F64 ? sann_dispatch<double>(c, x0, out, st) : sann_dispatch<float>(c, x0, out, st);
 }

@@ -409,6 +409,73 @@ int pso_time(const orc_pso_cfg *c, const void *upper, double *seconds, orc_statu
   return 0;
 }
 
+/* ------------------------------------------------------------------ NelderMeadPSO ------------------------ */
+/* nlsolver::NelderMeadPSO (nlsolver.h:3546-3920), one solver per start point.  Both draw phases consume exactly
+ * 4 n^2 draws (init_solver_state, then every apply_pso), so the tape position follows from the draw count. */
+template <class T>
+struct NMPSOTapeRNG {
+  const orc_nmpso_cfg &c;
+  u64 solver, count = 0;
+  T operator()() {
+    const u64 per = 4 * c.dim * c.dim, tag = count / per, k = count % per;
+    count++;
+    return to_unit<T>(oracle_tape_draw(oracle_tape_key(c.seed, tag, c.solver_offset + solver), k));
+  }
+};
+template <class T>
+int nmpso_run(const orc_nmpso_cfg *c, const void *x0v, const orc_nmpso_out *out, orc_status *st) {
+  /* The reference stores one element past the end of a vector<T>(n) (nlsolver.h:3697-3700).  glibc hands out chunks of
+   * max(32, (bytes + 8 + 15) & ~15) bytes of which all but 8 are usable: the stray store is harmless iff it still fits
+   * (fp64: even n; fp32: n = 2, 4, 8, 12, 16, ...), otherwise it overwrites the next chunk's size field and the process
+   * aborts in free().  The harness refuses the shapes that would corrupt its own heap. */
+  {
+    const size_t bytes = c->dim * sizeof(T);
+    size_t chunk = (bytes + 8 + 15) & ~size_t(15);
+    if (chunk < 32) chunk = 32;
+    if (c->n_solvers < 1 || c->dim < 2 || chunk - 8 < bytes + sizeof(T)) return -1;
+  }
+  const T *x0 = static_cast<const T *>(x0v);
+  const size_t d = c->dim;
+  PlainObjective<T> f{c->objective};
+  nlsolver::rng::xorshift<T> seq;
+  if (c->xs_state[0] | c->xs_state[1]) seq.set_state(c->xs_state[0], c->xs_state[1]);
+  T best_f = 0; u64 best_solver = 0, iters = 0, evals_total = 0, draws_total = 0;
+  for (u64 s = 0; s < c->n_solvers; s++) {
+    std::vector<T> x(x0 + (c->x0_count == 1 ? 0 : s * d), x0 + (c->x0_count == 1 ? 0 : s * d) + d);
+    u64 draws = 0;
+    auto run = [&](auto &gen) {
+      nlsolver::NelderMeadPSO<PlainObjective<T>, std::remove_reference_t<decltype(gen)>, T> solver(
+          f, gen, c->alpha, c->gamma, c->rho, c->sigma, c->inertia, c->cognitive_coef, c->social_coef, c->eps,
+          c->max_iter, c->no_change_best_iter);
+      return c->minimize ? solver.minimize(x) : solver.maximize(x);
+    };
+    T fv; u64 it, ev;
+    if (c->rng_mode == ORC_RNG_TAPE) {
+      NMPSOTapeRNG<T> g{*c, s};
+      const auto sum = run(g).get_summary();
+      fv = std::get<2>(sum); it = std::get<1>(sum); ev = std::get<0>(sum); draws = g.count;
+    } else {
+      const auto sum = run(seq).get_summary();
+      fv = std::get<2>(sum); it = std::get<1>(sum); ev = std::get<0>(sum);
+    }
+    if (s == 0 || fv < best_f) { best_f = fv; best_solver = s; }
+    iters = it; evals_total += ev; draws_total += draws;
+    if (!out) continue;
+    if (out->x_best) std::memcpy(static_cast<T *>(out->x_best) + s * d, x.data(), d * sizeof(T));
+    if (out->f_best) static_cast<T *>(out->f_best)[s] = fv;
+    if (out->iterations) out->iterations[s] = it;
+    if (out->function_calls) out->function_calls[s] = ev;
+    if (out->draws) out->draws[s] = draws;
+    if (out->ties) out->ties[s] = 0;
+  }
+  if (st) {
+    std::memset(st, 0, sizeof(*st));
+    st->f_value = best_f; st->iterations = iters; st->function_calls = evals_total; st->best_index = best_solver;
+    st->draws_consumed = draws_total; st->best_valid = 1;
+  }
+  return 0;
+}
+
 }  // namespace
 
 extern "C" {
@@ -421,6 +488,9 @@ int ref_pso_run(const orc_pso_cfg *c, const void *lower, const void *upper, cons
 }
 int ref_sann_run(const orc_sann_cfg *c, const void *x0, const orc_sann_out *out, orc_status *st) {
   return c->dtype == ORC_F64 ? sann_run<double>(c, x0, out, st) : sann_run<float>(c, x0, out, st);
+}
+int ref_nmpso_run(const orc_nmpso_cfg *c, const void *x0, const orc_nmpso_out *out, orc_status *st) {
+  return c->dtype == ORC_F64 ? nmpso_run<double>(c, x0, out, st) : nmpso_run<float>(c, x0, out, st);
 }
 int ref_sann_time(const orc_sann_cfg *c, const void *x0, double *seconds, orc_status *st) {
   return c->dtype == ORC_F64 ? sann_time<double>(c, x0, seconds, st) : sann_time<float>(c, x0, seconds, st);

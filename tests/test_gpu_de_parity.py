@@ -260,3 +260,50 @@ def test_de_one_launch_path_equals_separate_kernels(ctx, monkeypatch, dtype, obj
     assert np.array_equal(bits(ra), bits(rb)) and np.array_equal(bits(ca), bits(cb))
     for k in ("donors", "dim_idx", "rejects", "accepted", "trial_scores"):
         assert np.array_equal(bits(da[k]), bits(db[k])), k
+
+
+TINY_CASES = [
+    # dtype, objective, strategy, minimize, P, d, scale, max_iter
+    (B.F64, B.ROSENBROCK_EX, B.DE_RANDOM, True, 50, 2, 5.0, 1000),       # BASELINE configs[0]: the README snippet's shape
+    (B.F64, B.ROSENBROCK_EX, B.DE_BEST, True, 50, 2, 2.0, 1000),         # example.cpp:186-188
+    (B.F64, B.RASTRIGIN, B.DE_RANDOM, True, 1024, 8, 10.24, 60),         # the largest shape of the one-block solver
+    (B.F64, B.ACKLEY, B.DE_BEST, False, 333, 5, 32.768, 40),             # maximize
+    (B.F64, B.SHEKEL, B.DE_RANDOM, True, 50, 4, -0.5, 300),
+    (B.F64, B.BEALE, B.DE_BEST, True, 50, 2, -0.5, 300),
+    (B.F64, B.STYBLINSKI_TANG, B.DE_RANDOM, True, 64, 7, 5.0, 80),
+    (B.F64, B.SPHERE, B.DE_RANDOM, True, 4, 1, 10.24, 30),               # smallest legal population, d = 1
+    (B.F32, B.ROSENBROCK, B.DE_BEST, True, 100, 8, 4.096, 50),
+    (B.F32, B.SPHERE, B.DE_RANDOM, True, 50, 2, 5.0, 1000),
+]
+
+
+@pytest.mark.parametrize("dtype,obj,strategy,minimize,P,d,scale,max_iter", TINY_CASES)
+def test_de_one_block_solver_equals_general_path_and_oracle(ctx, oracle_lib, monkeypatch, dtype, obj, strategy, minimize, P,
+                                                            d, scale, max_iter):
+    """nls_de_solve for pop_size <= 1024 and dim <= 8 runs the whole solve in ONE launch of ONE block with the population
+    in shared memory (de_tiny_solve_kernel).  It must return what the general kernels return (NLS_DE_TINY=0) bit for bit
+    — default stop rules active — and agree with the oracle like them."""
+    import ctypes as C
+    from nlsolver_b200 import _lib as L
+    dt = np.float64 if dtype == B.F64 else np.float32
+    x0 = np.full(d, scale, dt)
+    cfg = nb.de_cfg(dtype=dtype, objective=obj, strategy=strategy, minimize=minimize, pop_size=P, dim=d, max_iter=max_iter,
+                    seed=4242 + P)
+    res = []
+    for env in ("1", "0"):
+        monkeypatch.setenv("NLS_DE_TINY", env)
+        out, st = np.zeros(d, dt), L.Status()
+        L.check(L.lib().nls_de_solve(ctx.handle, C.byref(cfg), x0.ctypes.data, out.ctypes.data, C.byref(st)))
+        res.append((st.as_dict(), out))
+    (sa, xa), (sb, xb) = res
+    for k in ("f_value", "iterations", "function_calls", "best_index", "val_no_change", "stop_reason", "accepted_total"):
+        assert sa[k] == sb[k], (k, sa[k], sb[k])
+    assert sa["stopped"] == 1 and np.array_equal(bits(xa), bits(xb))
+    so, ao = B.de_run(oracle_lib, B.de_cfg(dtype=dtype, objective=obj, strategy=strategy, minimize=minimize, pop_size=P, dim=d,
+                                           max_iter=max_iter, seed=4242 + P), x0)
+    tol = tolerance(dtype, obj)
+    if tol == 0.0 or obj in (B.SHEKEL, B.BEALE):
+        assert (sa["iterations"], sa["function_calls"], sa["stop_reason"]) == (so["iterations"], so["function_calls"],
+                                                                             so["stop_reason"])
+    if tol == 0.0:
+        assert sa["f_value"] == so["f_value"] and np.array_equal(bits(xa), bits(ao["x_best"]))

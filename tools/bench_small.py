@@ -78,7 +78,7 @@ def config1():
             return ((t + s) & 0xFFFFFFFFFFFFFFFF) / 18446744073709551615.0
     ctx = nb.Context(0)
     times, last = [], None
-    for k in range(60):
+    for k in range(int(os.environ.get("NLS_BENCH_SMALL_CALLS", "60"))):
         x = [5.0, 7.0]
         solver = nb.DE(nb.RosenbrockExample, XorShift(), ctx=ctx)
         t0 = time.perf_counter()
@@ -112,6 +112,11 @@ def config1():
 
 def main():
     res = {"config1_readme_de": config1(), "sweep_d64_small": []}
+    os.environ["NLS_DE_TINY"] = "0"          # the same call through the general kernels (one-launch cluster path)
+    res["config1_readme_de_general_kernels"] = {k: v for k, v in config1().items() if k.startswith("gpu_") or k == "iterations"}
+    os.environ.pop("NLS_DE_TINY")
+    for P, d in ((50, 2),):
+        res["sweep_d64_small"].append(sweep_point("DE-random", nb.F64, P, d=d, gens=256))
     for solver in ("DE-random", "PSO-vanilla", "PSO-accelerated"):
         for P in (1 << 10, 1 << 12):
             res["sweep_d64_small"].append(sweep_point(solver, nb.F64, P))
