@@ -221,6 +221,29 @@ NLS_API int nls_xchg_destroy(nls_xchg *x);
 NLS_API int nls_pso_attach_exchange(nls_pso *pso, nls_xchg *x);
 NLS_API int nls_pso_step_fused(nls_pso *pso, uint64_t n_generations);
 
+/* ---- NelderMeadPSO as a batch of independent solvers ----
+ * nlsolver::NelderMeadPSO (nlsolver.h:3546-3920) is a sequential hybrid over 3 dim + 1 particles: per iteration a sort,
+ * one Nelder-Mead step on the best dim + 1 and a PSO move of the other 2 dim.  Solvers never interact, so a batch — one
+ * solver per start point, or n_solvers from one point on different draw streams — runs one warp per solver with the
+ * reference's loop (and its accidents: DESIGN.md §10) unchanged inside each.  Only the unbounded minimize / maximize
+ * exist: the reference's bounded overloads index the bounds with the particle counter (nlsolver.h:3859) and read out
+ * of bounds for every particle.  2 <= dim <= 256.  With n_solvers = 1 this is NelderMeadPSO::minimize / maximize. */
+typedef struct {
+  int32_t dtype, objective, minimize;
+  uint32_t flags;
+  uint64_t n_solvers, dim;
+  double alpha, gamma, rho, sigma, inertia, cognitive_coef, social_coef, eps; /* 1, 2, 0.5, 0.5, 0.8, 1.8, 1.8, 1e-6 */
+  uint64_t max_iter, no_change_best_iter;                                     /* 1000, 20 */
+  uint64_t seed;
+  uint64_t solver_offset; /* global id of local solver 0 in the tape key */
+} nls_nmpso_cfg;
+/* x0_host: x0_count rows of dim elements (1: every solver starts there, or n_solvers).  Per solver: x_best_host
+ * n_solvers * dim elements, f_best_host n_solvers elements, iterations / function_calls n_solvers counters (any may be
+ * NULL).  status: the best solver (lowest value, lowest id on ties); function_calls summed over the batch. */
+NLS_API int nls_nmpso_solve(nls_ctx *ctx, const nls_nmpso_cfg *cfg, const void *x0_host, uint64_t x0_count,
+                            void *x_best_host, void *f_best_host, uint64_t *iterations_host,
+                            uint64_t *function_calls_host, nls_status *status);
+
 /* ---- several GPUs from ONE process: device groups ----
  * The reference is single-threaded C++ with no notion of devices; a C++ caller that wants the whole box gets it here
  * without a process group: a group opens one context per device and enables peer access between them.

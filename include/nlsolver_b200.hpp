@@ -635,6 +635,91 @@ class SANN {
   const scalar_t temperature_max;
 };
 
+// ------------------------------------------------------------------------------------------------ NelderMeadPSO
+// nlsolver.h:3546-3920.  minimize(x) / maximize(x) run ONE solver from x, as the reference does; the batch calls are
+// what this engine adds (one independent solver per start point, all resident on the GPU, one warp each).  The
+// reference's bounded overloads clamp with lower[i] / upper[i] indexed by the particle loop counter (nlsolver.h:3859),
+// which is out of bounds for every particle; they are declared here and throw.
+template <typename Callable, typename RNG, typename scalar_t = double>
+class NelderMeadPSO {
+  static_assert(b200::is_objective<Callable>(),
+                "nlsolver_b200: Callable must be a device objective tag (see nlsolver::test_functions)");
+
+ public:
+  NelderMeadPSO(Callable &f, RNG &generator, const scalar_t alpha = 1, const scalar_t gamma = 2,
+                const scalar_t rho = 0.5, const scalar_t sigma = 0.5, const scalar_t inertia = 0.8,
+                const scalar_t cognitive_coef = 1.8, const scalar_t social_coef = 1.8, const scalar_t eps = 1e-6,
+                const size_t max_iter = 1000, const size_t no_change_best_iter = 20)
+      : generator(generator), f(f), alpha(alpha), gamma(gamma), rho(rho), sigma(sigma), inertia(inertia),
+        cognitive_coef(cognitive_coef), social_coef(social_coef), eps(eps), max_iter(max_iter),
+        no_change_best_iter(no_change_best_iter) {}
+  solver_status<scalar_t> minimize(std::vector<scalar_t> &x) { return solve(x, true); }
+  solver_status<scalar_t> maximize(std::vector<scalar_t> &x) { return solve(x, false); }
+  solver_status<scalar_t> minimize(std::vector<scalar_t> &, const std::vector<scalar_t> &, const std::vector<scalar_t> &) {
+    throw std::invalid_argument("nlsolver_b200: the bounded NelderMeadPSO overloads read lower[i] / upper[i] out of "
+                                "bounds in the reference (nlsolver.h:3859) and have no defined result");
+  }
+  solver_status<scalar_t> maximize(std::vector<scalar_t> &x, const std::vector<scalar_t> &l, const std::vector<scalar_t> &u) {
+    return minimize(x, l, u);
+  }
+  // one solver per row of xs; every row is overwritten with its solver's best point
+  std::vector<solver_status<scalar_t>> minimize_batch(std::vector<std::vector<scalar_t>> &xs) { return batch(xs, true); }
+  std::vector<solver_status<scalar_t>> maximize_batch(std::vector<std::vector<scalar_t>> &xs) { return batch(xs, false); }
+
+ private:
+  nls_nmpso_cfg config(size_t n_solvers, size_t dim, bool minimize) {
+    nls_nmpso_cfg cfg{};
+    cfg.dtype = b200::dtype_of<scalar_t>();
+    cfg.objective = b200::objective_id(f);
+    cfg.minimize = minimize ? 1 : 0;
+    cfg.n_solvers = n_solvers;
+    cfg.dim = dim;
+    cfg.alpha = alpha; cfg.gamma = gamma; cfg.rho = rho; cfg.sigma = sigma; cfg.inertia = inertia;
+    cfg.cognitive_coef = cognitive_coef; cfg.social_coef = social_coef; cfg.eps = eps;
+    cfg.max_iter = max_iter; cfg.no_change_best_iter = no_change_best_iter;
+    cfg.seed = b200::seed_from(generator);
+    return cfg;
+  }
+  solver_status<scalar_t> solve(std::vector<scalar_t> &x, bool minimize) {
+    if (x.size() < 2) {   // nlsolver.h:3619-3629
+      std::cout << "You are trying to optimize a one dimensional function "
+                << "you should probably be using vanilla NelderMead (or vanilla PSO)"
+                << " - our implementation does not support this in the "
+                   "NelderMead-PSO hybrid."
+                << std::endl;
+      return solver_status<scalar_t>(999999, 0, 0);
+    }
+    std::vector<std::vector<scalar_t>> one{x};
+    auto res = batch(one, minimize);
+    x = one[0];
+    return res[0];
+  }
+  std::vector<solver_status<scalar_t>> batch(std::vector<std::vector<scalar_t>> &xs, bool minimize) {
+    std::vector<solver_status<scalar_t>> out;
+    if (xs.empty()) return out;
+    const size_t n = xs.size(), d = xs[0].size();
+    std::vector<scalar_t> flat(n * d), fbest(n);
+    std::vector<uint64_t> iters(n), calls(n);
+    for (size_t c = 0; c < n; c++) {
+      if (xs[c].size() != d) throw std::invalid_argument("nlsolver_b200: start points of different sizes");
+      for (size_t j = 0; j < d; j++) flat[c * d + j] = xs[c][j];
+    }
+    const nls_nmpso_cfg cfg = config(n, d, minimize);
+    nls_status st{};
+    b200::check(nls_nmpso_solve(b200::default_context(), &cfg, flat.data(), n, flat.data(), fbest.data(), iters.data(),
+                                calls.data(), &st));
+    for (size_t c = 0; c < n; c++) {
+      for (size_t j = 0; j < d; j++) xs[c][j] = flat[c * d + j];
+      out.emplace_back(fbest[c], iters[c], calls[c]);
+    }
+    return out;
+  }
+  RNG &generator;
+  Callable &f;
+  const scalar_t alpha, gamma, rho, sigma, inertia, cognitive_coef, social_coef, eps;
+  const size_t max_iter, no_change_best_iter;
+};
+
 // the names README.md:80,99 uses
 template <typename Callable, typename RNG, typename scalar_t = double,
           RecombinationStrategy RecombinationType = random>

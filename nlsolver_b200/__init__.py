@@ -14,3 +14,4 @@ from .solvers import (DE, PSO, Ackley, Context, DEPopulation, DESolver, Exchange
                       default_context, pso_cfg)
 from .solvers import SANN, SANNChains, sann_cfg  # noqa: F401
 from .solvers import DEIslands, DeviceGroup, ShardedSwarm  # noqa: F401
+from .solvers import NelderMeadPSO, nmpso_cfg, nmpso_solve  # noqa: F401

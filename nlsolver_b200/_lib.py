@@ -44,6 +44,14 @@ class SANNCfg(C.Structure):
                 ("temperature_max", f64), ("seed", u64), ("chain_offset", u64)]
 
 
+class NMPSOCfg(C.Structure):
+    _fields_ = [("dtype", i32), ("objective", i32), ("minimize", i32), ("flags", u32),
+                ("n_solvers", u64), ("dim", u64),
+                ("alpha", f64), ("gamma", f64), ("rho", f64), ("sigma", f64), ("inertia", f64), ("cognitive_coef", f64),
+                ("social_coef", f64), ("eps", f64), ("max_iter", u64), ("no_change_best_iter", u64),
+                ("seed", u64), ("solver_offset", u64)]
+
+
 class Status(C.Structure):
     _fields_ = [("f_value", f64), ("iterations", u64), ("function_calls", u64), ("best_index", u64),
                 ("val_no_change", u64), ("stopped", i32), ("stop_reason", i32), ("best_valid", i32),
@@ -109,6 +117,7 @@ SYMBOLS = {
     "nls_xchg_destroy": (C.c_int, [P]),
     "nls_pso_attach_exchange": (C.c_int, [P, P]),
     "nls_pso_step_fused": (C.c_int, [P, u64]),
+    "nls_nmpso_solve": (C.c_int, [P, C.POINTER(NMPSOCfg), P, u64, P, P, P, P, C.POINTER(Status)]),
     "nls_group_create": (C.c_int, [C.c_int, C.POINTER(C.c_int), C.POINTER(P)]),
     "nls_group_destroy": (C.c_int, [P]),
     "nls_group_size": (C.c_int, [P]),

@@ -21,6 +21,7 @@
 #include "common.cuh"
 #include "de_tiny.cuh"
 #include "launch.h"
+#include "nmpso_impl.cuh"
 #include "reduce.cuh"
 #include "state.h"
 
@@ -1239,6 +1240,81 @@ int nls_sann_solve(nls_ctx *ctx, const nls_sann_cfg *cfg, const void *x0_host, u
   if (rc == NLS_OK && status) *status = st;
   nls_sann_destroy(sa);
   return rc;
+}
+
+/* ================================================================ NelderMeadPSO batches ======================= */
+
+int nls_nmpso_solve(nls_ctx *ctx, const nls_nmpso_cfg *cfg, const void *x0_host, uint64_t x0_count, void *x_best_host,
+                    void *f_best_host, uint64_t *iterations_host, uint64_t *function_calls_host, nls_status *status) {
+  if (!ctx || !cfg || !x0_host) return fail(NLS_ERR_INVALID, "nls_nmpso_solve: NULL argument");
+  if (cfg->dtype != NLS_F32 && cfg->dtype != NLS_F64) return fail(NLS_ERR_INVALID, "NelderMeadPSO: unknown dtype %d", cfg->dtype);
+  if (cfg->objective < 0 || cfg->objective >= NLS_OBJECTIVE_COUNT)
+    return fail(NLS_ERR_INVALID, "NelderMeadPSO: objective %d is not a built-in objective", cfg->objective);
+  if (const unsigned fd = objective_fixed_dim(cfg->objective))
+    if (fd != cfg->dim) return fail(NLS_ERR_INVALID, "NelderMeadPSO: objective %d is a closed form of dimension %u", cfg->objective, fd);
+  // dim < 2: the reference prints a notice and returns solver_status(999999, 0, 0) (nlsolver.h:3619-3629)
+  if (cfg->dim < 2 || cfg->dim > kNMPSOMaxDim) return fail(NLS_ERR_INVALID, "NelderMeadPSO: 2 <= dim <= %u", kNMPSOMaxDim);
+  if (cfg->n_solvers < 1 || cfg->n_solvers >= 0xffffffffull) return fail(NLS_ERR_INVALID, "NelderMeadPSO: n_solvers out of range");
+  if (x0_count != 1 && x0_count != cfg->n_solvers) return fail(NLS_ERR_INVALID, "NelderMeadPSO: x0_count must be 1 or n_solvers");
+  NLS_CUDA(cudaSetDevice(ctx->device));
+  const size_t elem = elem_size(cfg->dtype);
+  const u64 C = cfg->n_solvers, d = cfg->dim, N = 3 * d + 1;
+  DeviceBuffers mem;
+  mem.ctx = ctx;
+  NMPSOState s;
+  std::memset(&s, 0, sizeof(s));
+  s.C = C; s.d = d; s.stride = round_up(d, 32 / elem); s.x0_count = x0_count;
+  s.seed = cfg->seed; s.offset = cfg->solver_offset; s.max_iter = cfg->max_iter; s.no_change_limit = cfg->no_change_best_iter;
+  s.alpha = cfg->alpha; s.gamma = cfg->gamma; s.rho = cfg->rho; s.sigma = cfg->sigma; s.inertia = cfg->inertia;
+  s.cog = cfg->cognitive_coef; s.soc = cfg->social_coef; s.eps = cfg->eps; s.fm = cfg->minimize ? 1.0 : -1.0;
+  s.objective = cfg->objective;
+  int rc = NLS_OK;
+  auto alloc = [&](void **p, size_t bytes) { if (rc == NLS_OK) rc = mem.alloc(p, bytes); };
+  alloc(&s.pos, size_t(C) * N * s.stride * elem);
+  alloc(&s.vel, size_t(C) * N * s.stride * elem);
+  alloc(&s.tmp, size_t(C) * 4 * s.stride * elem);
+  alloc(&s.x0, size_t(x0_count) * d * elem);
+  alloc(&s.x_best, size_t(C) * d * elem);
+  alloc(&s.f_best, size_t(C) * elem);
+  alloc(reinterpret_cast<void **>(&s.iters), size_t(C) * sizeof(unsigned long long));
+  alloc(reinterpret_cast<void **>(&s.evals), size_t(C) * sizeof(unsigned long long));
+  cudaStream_t st = ctx->stream;
+  std::vector<unsigned long long> iters(C), evals(C);
+  std::vector<char> fbest(C * elem);
+  auto run = [&]() -> int {
+    if (rc != NLS_OK) return rc;
+    NLS_CUDA(cudaMemcpyAsync(s.x0, x0_host, size_t(x0_count) * d * elem, cudaMemcpyHostToDevice, st));
+    NLS_CUDA(cfg->dtype == NLS_F64 ? nmpso_launch_f64(s, st) : nmpso_launch_f32(s, st));
+    if (x_best_host) NLS_CUDA(cudaMemcpyAsync(x_best_host, s.x_best, size_t(C) * d * elem, cudaMemcpyDeviceToHost, st));
+    NLS_CUDA(cudaMemcpyAsync(fbest.data(), s.f_best, C * elem, cudaMemcpyDeviceToHost, st));
+    NLS_CUDA(cudaMemcpyAsync(iters.data(), s.iters, C * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    NLS_CUDA(cudaMemcpyAsync(evals.data(), s.evals, C * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    NLS_CUDA(cudaStreamSynchronize(st));
+    return NLS_OK;
+  };
+  rc = run();
+  mem.release();
+  if (rc != NLS_OK) return rc;
+  u64 best = 0, total = 0;
+  auto value = [&](u64 k) { return cfg->dtype == NLS_F64 ? reinterpret_cast<const double *>(fbest.data())[k]
+                                                         : static_cast<double>(reinterpret_cast<const float *>(fbest.data())[k]); };
+  for (u64 k = 0; k < C; k++) {
+    if (value(k) < value(best)) best = k;
+    total += evals[k];
+  }
+  if (f_best_host) std::memcpy(f_best_host, fbest.data(), C * elem);
+  if (iterations_host) for (u64 k = 0; k < C; k++) iterations_host[k] = iters[k];
+  if (function_calls_host) for (u64 k = 0; k < C; k++) function_calls_host[k] = evals[k];
+  if (status) {
+    std::memset(status, 0, sizeof(*status));
+    status->f_value = value(best);
+    status->iterations = iters[best];
+    status->function_calls = total;
+    status->best_index = cfg->solver_offset + best;
+    status->stopped = 1;
+    status->best_valid = 1;
+  }
+  return NLS_OK;
 }
 
 /* ================================================================ objective plugins =========================== */

@@ -45,6 +45,9 @@ struct SANNOps {
 struct DETinyArgs;
 cudaError_t de_tiny_launch_f64(int objective, const DETinyArgs &a, cudaStream_t st);
 cudaError_t de_tiny_launch_f32(int objective, const DETinyArgs &a, cudaStream_t st);
+struct NMPSOState;
+cudaError_t nmpso_launch_f64(const NMPSOState &s, cudaStream_t st);
+cudaError_t nmpso_launch_f32(const NMPSOState &s, cudaStream_t st);
 const SANNOps *sann_ops_f64();
 const SANNOps *sann_ops_f32();
 const DEOps *de_ops_f64();

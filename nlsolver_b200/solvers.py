@@ -673,4 +673,70 @@ class SANN:
         return self._batch(xs, n_chains, False)
 
 
+def nmpso_cfg(dtype=L.F64, objective=L.SPHERE, minimize=True, n_solvers=1, dim=2, alpha=1.0, gamma=2.0, rho=0.5, sigma=0.5,
+              inertia=0.8, cognitive_coef=1.8, social_coef=1.8, eps=1e-6, max_iter=1000, no_change_best_iter=20, seed=0,
+              solver_offset=0, flags=0):
+    return L.NMPSOCfg(dtype, objective, int(minimize), flags, n_solvers, dim, alpha, gamma, rho, sigma, inertia,
+                      cognitive_coef, social_coef, eps, max_iter, no_change_best_iter, seed, solver_offset)
+
+
+def nmpso_solve(ctx, cfg, x0):
+    """nls_nmpso_solve: x0 is [dim] (every solver starts there) or [n_solvers, dim].
+    Returns (status dict, {"x_best" [n, dim], "f_best" [n], "iterations" [n], "function_calls" [n]})."""
+    dt = np_dtype(cfg.dtype)
+    x0 = np.ascontiguousarray(x0, dtype=dt)
+    count = 1 if x0.ndim == 1 else x0.shape[0]
+    n, d = cfg.n_solvers, cfg.dim
+    a = {"x_best": np.zeros((n, d), dt), "f_best": np.zeros(n, dt), "iterations": np.zeros(n, np.uint64),
+         "function_calls": np.zeros(n, np.uint64)}
+    st = L.Status()
+    L.check(L.lib().nls_nmpso_solve(ctx.handle, C.byref(cfg), x0.ctypes.data, count, a["x_best"].ctypes.data,
+                                    a["f_best"].ctypes.data, a["iterations"].ctypes.data,
+                                    a["function_calls"].ctypes.data, C.byref(st)))
+    return st.as_dict(), a
+
+
+class NelderMeadPSO:
+    """nlsolver::NelderMeadPSO<Callable, RNG, scalar_t> (nlsolver.h:3546-3614): `minimize(x)` / `maximize(x)` run one
+    solver from x.  `minimize_batch(xs)` is the batch form this engine adds: one independent solver per row of xs (or
+    n_solvers solvers from one point), each the reference's loop on its own draw stream.  The bounded overloads of the
+    reference read its bounds out of range (nlsolver.h:3859) and are not offered."""
+
+    def __init__(self, f, generator, alpha=1.0, gamma=2.0, rho=0.5, sigma=0.5, inertia=0.8, cognitive_coef=1.8,
+                 social_coef=1.8, eps=1e-6, max_iter=1000, no_change_best_iter=20, scalar_t=np.float64, ctx=None):
+        self.f, self.generator = f, generator
+        self.p = dict(alpha=alpha, gamma=gamma, rho=rho, sigma=sigma, inertia=inertia, cognitive_coef=cognitive_coef,
+                      social_coef=social_coef, eps=eps, max_iter=max_iter, no_change_best_iter=no_change_best_iter)
+        self.scalar_t, self.ctx = scalar_t, ctx
+
+    def _run(self, xs, n_solvers, minimize):
+        ctx = self.ctx or default_context()
+        dt = np.dtype(self.scalar_t)
+        xs = np.ascontiguousarray(xs, dtype=dt)
+        n = xs.shape[0] if xs.ndim == 2 else int(n_solvers)
+        cfg = nmpso_cfg(nls_dtype(dt), self.f, minimize, n, xs.shape[-1], seed=seed_from_generator(self.generator),
+                        **self.p)
+        return nmpso_solve(ctx, cfg, xs), dt
+
+    def _solve(self, x, minimize):
+        (st, a), dt = self._run(np.asarray(x, dtype=np.dtype(self.scalar_t)), 1, minimize)
+        x[:] = a["x_best"][0].tolist() if isinstance(x, list) else a["x_best"][0]
+        return SolverStatus(dt.type(a["f_best"][0]), int(a["iterations"][0]), int(a["function_calls"][0]))
+
+    def minimize(self, x):
+        return self._solve(x, True)
+
+    def maximize(self, x):
+        return self._solve(x, False)
+
+    def minimize_batch(self, xs, n_solvers=None, minimize=True):
+        """xs: [n_solvers, dim] start points, or [dim] with n_solvers.  Returns (best points, list of SolverStatus)."""
+        (st, a), dt = self._run(xs, n_solvers, minimize)
+        return a["x_best"], [SolverStatus(dt.type(f), int(i), int(c))
+                             for f, i, c in zip(a["f_best"], a["iterations"], a["function_calls"])]
+
+    def maximize_batch(self, xs, n_solvers=None):
+        return self.minimize_batch(xs, n_solvers, minimize=False)
+
+
 DESolver, PSOSolver = DE, PSO   # the names README.md:80,99 uses

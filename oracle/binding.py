@@ -76,6 +76,18 @@ class SANNOut(C.Structure):
                 ("x_best", "f_best", "p_cur", "n_accepted", "n_improved", "draws", "iterations", "function_calls")]
 
 
+class NMPSOCfg(C.Structure):
+    _fields_ = [("dtype", i32), ("objective", i32), ("minimize", i32), ("rng_mode", i32),
+                ("n_solvers", u64), ("dim", u64),
+                ("alpha", f64), ("gamma", f64), ("rho", f64), ("sigma", f64), ("inertia", f64), ("cognitive_coef", f64),
+                ("social_coef", f64), ("eps", f64), ("max_iter", u64), ("no_change_best_iter", u64),
+                ("seed", u64), ("solver_offset", u64), ("xs_state", u64 * 2), ("x0_count", u64)]
+
+
+class NMPSOOut(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("x_best", "f_best", "iterations", "function_calls", "draws", "ties")]
+
+
 def np_dtype(dtype):
     return np.float64 if dtype == F64 else np.float32
 
@@ -219,6 +231,35 @@ def sann_run(lib, cfg, x0, prefix=None):
     rc = getattr(lib, prefix + "sann_run")(C.byref(cfg), x0.ctypes.data, C.byref(out), C.byref(st))
     if rc != 0:
         raise RuntimeError(f"{prefix}sann_run failed: {rc}")
+    return st.as_dict(), a
+
+
+def nmpso_cfg(dtype=F64, objective=SPHERE, minimize=True, n_solvers=1, dim=2, alpha=1.0, gamma=2.0, rho=0.5, sigma=0.5,
+              inertia=0.8, cognitive_coef=1.8, social_coef=1.8, eps=1e-6, max_iter=1000, no_change_best_iter=20,
+              rng_mode=RNG_TAPE, seed=0, solver_offset=0, xs_state=(0, 0), x0_count=1):
+    return NMPSOCfg(dtype, objective, int(minimize), rng_mode, n_solvers, dim, alpha, gamma, rho, sigma, inertia,
+                    cognitive_coef, social_coef, eps, max_iter, no_change_best_iter, seed, solver_offset,
+                    (u64 * 2)(*xs_state), x0_count)
+
+
+def nmpso_run(lib, cfg, x0, prefix=None):
+    """A batch of NelderMeadPSO solvers; x0 is [dim] or [n_solvers, dim].  Returns (status, arrays); status is None when
+    the reference harness refuses the shape (the reference would corrupt the heap, oracle_abi.h)."""
+    prefix = prefix or ("ref_" if hasattr(lib, "ref_de_run") else "oracle_")
+    dt = np_dtype(cfg.dtype)
+    n, d = cfg.n_solvers, cfg.dim
+    x0 = np.ascontiguousarray(x0, dtype=dt)
+    cfg.x0_count = 1 if x0.ndim == 1 else n
+    a = {"x_best": np.zeros((n, d), dt), "f_best": np.zeros(n, dt), "iterations": np.zeros(n, np.uint64),
+         "function_calls": np.zeros(n, np.uint64), "draws": np.zeros(n, np.uint64), "ties": np.zeros(n, np.uint8)}
+    out = NMPSOOut(**{k: v.ctypes.data for k, v in a.items()})
+    st = Status()
+    fn = getattr(lib, prefix + "nmpso_run")
+    fn.argtypes = [C.POINTER(NMPSOCfg), C.c_void_p, C.POINTER(NMPSOOut), C.POINTER(Status)]
+    fn.restype = C.c_int
+    rc = fn(C.byref(cfg), x0.ctypes.data, C.byref(out), C.byref(st))
+    if rc != 0:
+        return None, a
     return st.as_dict(), a
 
 

@@ -36,6 +36,37 @@ SANN_GOLDEN = {
 }
 
 
+NMPSO_GOLDEN = {
+    # name: (dtype, objective, minimize, n_solvers, d, max_iter, spread, seed)   d: shapes the reference survives (oracle_abi.h)
+    "nmpso_rosenbrock_ex_f64": (B.F64, B.ROSENBROCK_EX, True, 24, 2, 1000, 3.0, 41),
+    "nmpso_rastrigin_f64": (B.F64, B.RASTRIGIN, True, 10, 6, 400, 3.0, 42),
+    "nmpso_sphere_max_f64": (B.F64, B.SPHERE, False, 8, 4, 60, 2.0, 43),
+    "nmpso_rosenbrock_f64": (B.F64, B.ROSENBROCK, True, 6, 16, 300, 1.5, 44),
+    "nmpso_sphere_f32": (B.F32, B.SPHERE, True, 12, 8, 300, 2.0, 45),
+}
+
+
+def nmpso_start(n, d, spread, seed, dtype):
+    return np.random.default_rng(seed).uniform(-spread, spread, size=(n, d)).astype(B.np_dtype(dtype))
+
+
+def write_nmpso(ref):
+    for name, (dtype, obj, mini, n, d, it, spread, seed) in NMPSO_GOLDEN.items():
+        cfg = B.nmpso_cfg(dtype=dtype, objective=obj, minimize=mini, n_solvers=n, dim=d, max_iter=it, seed=seed)
+        x0 = nmpso_start(n, d, spread, seed, dtype)
+        st, a = B.nmpso_run(ref, cfg, x0)
+        assert st is not None, name
+        # ties are detected by the restatement (the reference cannot report them): fixtures must be tie-free
+        so, ao = B.nmpso_run(B.oracle(), B.nmpso_cfg(dtype=dtype, objective=obj, minimize=mini, n_solvers=n, dim=d,
+                                                     max_iter=it, seed=seed), x0)
+        assert not ao["ties"].any(), (name, "a sort compared equal values: pick another seed")
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), kind="nmpso",
+                            cfg=np.array([dtype, obj, int(mini), n, d, it, seed], dtype=np.int64), x0=x0,
+                            f_value=st["f_value"], best_index=st["best_index"], x_best=a["x_best"], f_best=a["f_best"],
+                            draws=a["draws"], iterations=a["iterations"], function_calls=a["function_calls"])
+    print("wrote", len(NMPSO_GOLDEN), "NelderMeadPSO fixtures to", HERE)
+
+
 def sann_start(n_chains, d, start, dtype):
     # one start point per chain: start * (1 + chain / 8) on even coordinates, -start on odd ones
     x0 = np.empty((n_chains, d), dtype=B.np_dtype(dtype))
@@ -47,6 +78,9 @@ def sann_start(n_chains, d, start, dtype):
 def main():
     ref = B.reference()
     assert ref is not None, "build oracle/_ref first (make -C oracle ref)"
+    if "--only-nmpso" in sys.argv:      # leaves the other fixtures' files untouched
+        write_nmpso(ref)
+        return
     for name, (dtype, obj, strat, mini, P, d, G, scale, seed) in DE_GOLDEN.items():
         cfg = B.de_cfg(dtype=dtype, objective=obj, strategy=strat, minimize=mini, pop_size=P, dim=d, eps=0.0,
                        max_iter=G, best_val_no_change=1 << 40, seed=seed)
@@ -79,6 +113,7 @@ def main():
                             function_calls_total=st["function_calls"], x_best=a["x_best"], f_best=a["f_best"],
                             draws=a["draws"], iterations=a["iterations"], function_calls=a["function_calls"])
     print("wrote", len(DE_GOLDEN) + len(PSO_GOLDEN) + len(SANN_GOLDEN), "fixtures to", HERE)
+    write_nmpso(ref)
 
 
 if __name__ == "__main__":

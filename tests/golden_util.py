@@ -35,3 +35,10 @@ def load_sann(path):
     cfg = B.sann_cfg(dtype=dtype, objective=obj, minimize=bool(mini), n_chains=n, dim=d, max_iter=it,
                      temperature_iter=ti, temperature_max=float(z["tmax"]), seed=seed)
     return cfg, z["x0"], z
+
+
+def load_nmpso(path):
+    z = np.load(path)
+    dtype, obj, mini, n, d, it, seed = (int(v) for v in z["cfg"])
+    cfg = B.nmpso_cfg(dtype=dtype, objective=obj, minimize=bool(mini), n_solvers=n, dim=d, max_iter=it, seed=seed)
+    return cfg, z["x0"], z

@@ -41,3 +41,15 @@ def test_sann_oracle_reproduces_reference_fixture(oracle_lib, path):
     assert st["function_calls"] == z["function_calls_total"].item()
     for k in ("x_best", "f_best", "draws", "iterations", "function_calls"):
         assert np.array_equal(bits(a[k]), bits(z[k])), k
+
+
+@pytest.mark.parametrize("path", golden_files("nmpso_"), ids=os.path.basename)
+def test_nmpso_oracle_reproduces_reference_fixture(oracle_lib, path):
+    """NelderMeadPSO (nlsolver.h:3546-3920): the restatement against what the UNMODIFIED reference produced."""
+    from tests.golden_util import load_nmpso
+    cfg, x0, z = load_nmpso(path)
+    st, a = B.nmpso_run(oracle_lib, cfg, x0)
+    for k in ("x_best", "f_best", "iterations", "function_calls", "draws"):
+        assert np.array_equal(a[k].view(np.uint8), z[k].view(np.uint8)), k
+    assert st["best_index"] == z["best_index"].item() and st["f_value"] == z["f_value"].item()
+    assert not a["ties"].any()

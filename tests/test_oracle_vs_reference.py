@@ -254,3 +254,34 @@ def test_sann_restatement_cut_points_compose(oracle_lib):
     part, ap = B.sann_run(oracle_lib, B.sann_cfg(max_steps=100, **cfg), np.full(9, 2.0))
     assert (ap["function_calls"] == 101).all() and (ap["n_accepted"] <= af["n_accepted"]).all()
     assert (ap["f_best"] >= af["f_best"]).all()
+
+
+@pytest.mark.parametrize("dtype,obj,d,scale", [(B.F64, B.SPHERE, 2, 2.0), (B.F64, B.ROSENBROCK_EX, 2, 2.0),
+                                               (B.F64, B.RASTRIGIN, 4, 3.0), (B.F64, B.ACKLEY, 6, 5.0),
+                                               (B.F64, B.ROSENBROCK, 8, 1.5), (B.F64, B.STYBLINSKI_TANG, 10, 2.0),
+                                               (B.F32, B.SPHERE, 2, 2.0), (B.F32, B.ROSENBROCK, 4, 1.5),
+                                               (B.F32, B.RASTRIGIN, 8, 3.0)])
+def test_nmpso_restatement_equals_reference(oracle_lib, ref_lib, dtype, obj, d, scale):
+    """NelderMeadPSO::solve restated (oracle/popsolve_oracle.cpp: nmpso_solve) against the unmodified reference, on the
+    draw tape and on the reference's own sequential xorshift, minimise and maximise: best points, values, iteration and
+    call counters and the number of draws consumed, bit for bit."""
+    x0 = np.random.default_rng(d).uniform(-scale, scale, size=(7, d))
+    for mode in (B.RNG_TAPE, B.RNG_XORSHIFT):
+        for minimize in (True, False):
+            kw = dict(dtype=dtype, objective=obj, minimize=minimize, n_solvers=7, dim=d, rng_mode=mode, seed=5,
+                      max_iter=1000 if minimize else 25)
+            so, ao = B.nmpso_run(oracle_lib, B.nmpso_cfg(**kw), x0)
+            sr, ar = B.nmpso_run(ref_lib, B.nmpso_cfg(**kw), x0)
+            assert sr is not None, "the harness refused a shape this test believes the reference survives"
+            for k in ("x_best", "f_best", "iterations", "function_calls"):
+                assert np.array_equal(ao[k].view(np.uint8), ar[k].view(np.uint8)), (mode, minimize, k)
+            if mode == B.RNG_TAPE:
+                assert np.array_equal(ao["draws"], ar["draws"])
+            assert so["f_value"] == sr["f_value"] and so["best_index"] == sr["best_index"]
+
+
+def test_nmpso_harness_refuses_shapes_that_corrupt_the_reference_heap(ref_lib):
+    """The reference stores one element past the end of a row (nlsolver.h:3697-3700); for odd n in fp64 that overwrites
+    a heap chunk header.  The harness must refuse instead of aborting the test process."""
+    st, _ = B.nmpso_run(ref_lib, B.nmpso_cfg(objective=B.SPHERE, n_solvers=1, dim=3), np.ones(3))
+    assert st is None
