@@ -220,6 +220,14 @@ NLS_API int nls_xchg_open_peers(nls_xchg *x, const void *handles);
 NLS_API int nls_xchg_destroy(nls_xchg *x);
 NLS_API int nls_pso_attach_exchange(nls_pso *pso, nls_xchg *x);
 NLS_API int nls_pso_step_fused(nls_pso *pso, uint64_t n_generations);
+/* Islands: with a window attached, the commit kernel of every generation stores the island's record (best value,
+ * global agent id, score moments, best row) into every peer's window — the per-generation exchange of the island bests
+ * without a collective and without a wait.  nls_de_read_exchange copies the newest record of each of the `world`
+ * islands from its OWN window to the host (rank order, nls_record_bytes each; valid = 0 where nothing was published);
+ * the caller makes sure every rank has synchronised its stream first (a host barrier), and that no rank steps on before
+ * everybody has read.  Destroy the solver before its window. */
+NLS_API int nls_de_attach_exchange(nls_de *de, nls_xchg *x);
+NLS_API int nls_de_read_exchange(nls_de *de, void *records_host);
 
 /* ---- NelderMeadPSO as a batch of independent solvers ----
  * nlsolver::NelderMeadPSO (nlsolver.h:3546-3920) is a sequential hybrid over 3 dim + 1 particles: per iteration a sort,

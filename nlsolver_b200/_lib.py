@@ -117,6 +117,8 @@ SYMBOLS = {
     "nls_xchg_destroy": (C.c_int, [P]),
     "nls_pso_attach_exchange": (C.c_int, [P, P]),
     "nls_pso_step_fused": (C.c_int, [P, u64]),
+    "nls_de_attach_exchange": (C.c_int, [P, P]),
+    "nls_de_read_exchange": (C.c_int, [P, P]),
     "nls_nmpso_solve": (C.c_int, [P, C.POINTER(NMPSOCfg), P, u64, P, P, P, P, C.POINTER(Status)]),
     "nls_group_create": (C.c_int, [C.c_int, C.POINTER(C.c_int), C.POINTER(P)]),
     "nls_group_destroy": (C.c_int, [P]),

@@ -269,6 +269,7 @@ struct nls_de {
   u64 timed_generations;
   GraphCache graph;
   bool persistent_failed = false;
+  struct nls_xchg *xchg = nullptr;      // islands: window the commit kernel publishes into
 };
 
 struct nls_xchg {
@@ -572,6 +573,12 @@ static int de_status(nls_de *de, nls_status *status) {
     status->repair_rounds = c.rounds;
     status->accepted_total = c.accepted;
   }
+  return NLS_OK;
+}
+
+// re-scan the best and (with an exchange window attached) publish the island's record again
+static int nls_de_republish(nls_de *de) {
+  NLS_CUDA(de->ops->rescan(de->s, de->g, de->ctx->stream));
   return NLS_OK;
 }
 
@@ -1422,6 +1429,48 @@ int nls_pso_attach_exchange(nls_pso *p, nls_xchg *x) {
     NLS_CUDA(p->ops->candidate_publish(p->s, x->w, 1, p->g, p->ctx->stream));
     NLS_CUDA(p->ops->gather_apply(p->s, x->w, 1, p->ctx->stream));
     p->first_apply_pending = false;
+  }
+  return NLS_OK;
+}
+
+int nls_de_attach_exchange(nls_de *de, nls_xchg *x) {
+  if (!de || !x) return fail(NLS_ERR_INVALID, "nls_de_attach_exchange: NULL argument");
+  if (!x->opened) return fail(NLS_ERR_STATE, "nls_de_attach_exchange: open the peers' handles first");
+  if (x->w.record_bytes != nls_record_bytes(de->cfg.dtype, de->s.d)) return fail(NLS_ERR_INVALID, "exchange window record size mismatch");
+  if (x->attached) return fail(NLS_ERR_STATE, "nls_de_attach_exchange: an exchange window serves one solver; create a new one");
+  NLS_CUDA(cudaSetDevice(de->ctx->device));
+  void *dev = nullptr;
+  int rc = de->mem.alloc(&dev, sizeof(XchgWindow));
+  if (rc != NLS_OK) return rc;
+  NLS_CUDA(cudaMemcpyAsync(dev, &x->w, sizeof(XchgWindow), cudaMemcpyHostToDevice, de->ctx->stream));
+  NLS_CUDA(cudaStreamSynchronize(de->ctx->stream));
+  x->attached = true;
+  de->xchg = x;
+  de->s.xw = static_cast<const XchgWindow *>(dev);
+  de->graph.reset();                                     // captured launches carry the state by value
+  // publish the record of the population as it stands (a best re-scan changes nothing else)
+  return nls_de_republish(de);
+}
+
+int nls_de_read_exchange(nls_de *de, void *records_host) {
+  if (!de || !records_host) return fail(NLS_ERR_INVALID, "nls_de_read_exchange: NULL argument");
+  if (!de->xchg) return fail(NLS_ERR_STATE, "nls_de_read_exchange: no exchange window attached");
+  NLS_CUDA(cudaSetDevice(de->ctx->device));
+  const nls_xchg *x = de->xchg;
+  const size_t world = size_t(x->w.world), rb = x->w.record_bytes;
+  std::vector<char> win(x->bytes);
+  NLS_CUDA(cudaMemcpyAsync(win.data(), x->base, x->bytes, cudaMemcpyDeviceToHost, de->ctx->stream));
+  NLS_CUDA(cudaStreamSynchronize(de->ctx->stream));
+  // per source island the slot with the higher sequence number: islands that stopped early (or that are a generation
+  // apart) have their newest record in either parity slot
+  const unsigned long long *flags = reinterpret_cast<const unsigned long long *>(win.data() + x->flags_offset);
+  for (size_t r = 0; r < world; r++) {
+    const size_t parity = flags[world + r] > flags[r] ? 1 : 0;
+    if (flags[parity * world + r] == 0) {
+      std::memset(static_cast<char *>(records_host) + r * rb, 0, rb);      // nothing published yet: valid = 0
+      continue;
+    }
+    std::memcpy(static_cast<char *>(records_host) + r * rb, win.data() + (parity * world + r) * rb, rb);
   }
   return NLS_OK;
 }

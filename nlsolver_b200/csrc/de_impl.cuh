@@ -603,9 +603,35 @@ __device__ __forceinline__ void de_commit_pass(const DEState &s, int mode) {
   };
   MinLoc ml;
   Moments mo;
-  if (population_reduce(s.P, s.part_min, s.part_idx, s.part_mom, &ctrl->ticket, item, store, post, ml, mo) &&
-      threadIdx.x == 0)
-    fin(ml, mo);
+  if (!population_reduce(s.P, s.part_min, s.part_idx, s.part_mom, &ctrl->ticket, item, store, post, ml, mo)) return;
+  if (threadIdx.x == 0) fin(ml, mo);
+  // Islands: the last block stores the island's record (best value, global id, score moments, best row) straight into
+  // every peer's exchange window over NVLink and releases a sequence flag — the per-generation "all-gather of the
+  // island bests" without a collective, a launch or a wait: readers look at their own window when they need the
+  // global best (nls_de_read_exchange).  Sequence = iterations completed + 1, slot parity = sequence & 1.
+  if (s.xw != nullptr) {
+    __syncthreads();                                     // fin()'s updates of the control block
+    const XchgWindow &w = *s.xw;
+    const u64 seq = *reinterpret_cast<volatile unsigned long long *>(&ctrl->iter) + 1ull;
+    const u64 b = *reinterpret_cast<volatile unsigned long long *>(&ctrl->best_id);
+    const u64 slot = ((seq & 1ull) * u64(w.world) + u64(w.rank)) * w.record_bytes;
+    // (the location byte may have been flipped by another block of this launch: read it from L2, not from this SM's L1)
+    const T *src = static_cast<const T *>(s.buf[__ldcg(s.where + b)]) + b * s.stride;
+    for (int r = 0; r < w.world; r++) {
+      RecordHeader *h = reinterpret_cast<RecordHeader *>(w.records[r] + slot);
+      if (threadIdx.x == 0) {
+        h->value = *reinterpret_cast<volatile double *>(&ctrl->best_value); h->index = s.offset + b;
+        h->moments = ctrl->score_moments; h->valid = 1; h->_pad = 0;
+      }
+      T *row = reinterpret_cast<T *>(h + 1);
+      for (u64 j = threadIdx.x; j < s.d; j += kBlock) row[j] = __ldcg(src + j);
+    }
+    __syncthreads();
+    if (threadIdx.x < w.world) {
+      __threadfence_system();
+      asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(w.flags[threadIdx.x] + (seq & 1ull) * u64(w.world) + u64(w.rank)), "l"(seq) : "memory");
+    }
+  }
 }
 template <class T>
 __global__ void __launch_bounds__(kBlock) de_commit_kernel(DEState s, int mode) {
@@ -807,6 +833,10 @@ cudaError_t de_launch_commit(const DEState &s, int mode, const LaunchGeom &g, cu
   return cudaGetLastError();
 }
 template <class T>
+cudaError_t de_launch_rescan(const DEState &s, const LaunchGeom &g, cudaStream_t st) {
+  return de_launch_commit<T>(s, 2, g, st);
+}
+template <class T>
 cudaError_t de_launch_export_best(const DEState &s, void *record, cudaStream_t st) {
   de_export_best_kernel<T><<<1, kBlock, 0, st>>>(s, record);
   return cudaGetLastError();
@@ -966,7 +996,8 @@ cudaError_t de_launch_gather_rows(const DEState &s, unsigned long long first, un
 #define NLS_DEFINE_DE_OPS(T, NAME)                                                                        \
   const DEOps *NAME() {                                                                                   \
     static const DEOps ops = {de_launch_init<T>, de_launch_generation<T>, de_launch_export_best<T>,       \
-                              de_launch_migrate<T>, de_launch_gather_rows<T>, NLS_PERSISTENT_OR_NULL(de_launch_persistent<T>)}; \
+                              de_launch_migrate<T>, de_launch_gather_rows<T>, NLS_PERSISTENT_OR_NULL(de_launch_persistent<T>), \
+                              de_launch_rescan<T>};                                                      \
     return &ops;                                                                                          \
   }
 

@@ -15,6 +15,8 @@ struct DEOps {
                              cudaStream_t st);
   // small populations: n generations (K2 + repair + K3 each) in ONE launch on one thread-block cluster
   cudaError_t (*persistent)(const DEState &s, unsigned long long n_generations, cudaStream_t st);
+  // best re-scan without a generation (after migration / when an exchange window is attached)
+  cudaError_t (*rescan)(const DEState &s, const LaunchGeom &g, cudaStream_t st);
 };
 struct PSOOps {
   cudaError_t (*init)(const PSOState &s, const LaunchGeom &g, cudaStream_t st);

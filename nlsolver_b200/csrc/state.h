@@ -26,6 +26,7 @@ struct DECtrl {
   Moments score_moments;        // moments of the scores at the last scan (island exchange record)
 };
 
+struct XchgWindow;
 struct DEState {
   void *buf[2];          // two agent-major row buffers [P][stride]; where[i] says which one holds agent i's row
   uint8_t *where;        // [P]
@@ -48,6 +49,9 @@ struct DEState {
   int strategy, objective;
   double F, fm, eps;
   unsigned long long max_iter, vnc_limit;
+  // islands: exchange window (device copy of the descriptor) the commit kernel publishes the island's best record into,
+  // or NULL
+  const XchgWindow *xw;
 };
 
 struct PSOCtrl {

@@ -99,6 +99,10 @@ class _Comm:
         else:
             self.dist.all_gather_into_tensor(out, inp, group=self.group)
 
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier(group=self.group)
+
     def ring_exchange(self, send, recv):
         """send -> rank + 1, recv <- rank - 1."""
         if self.world == 1:
@@ -174,11 +178,28 @@ class CudaDEEngine:
         self.pop.import_migrants(k, rows.data_ptr(), scores.data_ptr())
         self.kernel_launches += 4
 
+    def open_peer_exchange(self, comm, record_bytes):
+        """Map every rank's exchange window into this process (CUDA IPC) and attach it to the island: from here on the
+        commit kernel of every generation stores the island's record into every peer's window over NVLink."""
+        from .solvers import ExchangeWindow
+        self.window = ExchangeWindow(self.ctx, record_bytes, comm.world, comm.rank)
+        if comm.world > 1:
+            handles = [None] * comm.world
+            comm.dist.all_gather_object(handles, self.window.ipc_handle(), group=comm.group)
+            self.window.open_peers(handles)
+        self.pop.attach_exchange(self.window)
+        self.kernel_launches += 1
+
+    def read_exchange(self, world):
+        return self.pop.read_exchange(world)
+
     def sync(self):
         return self.pop.sync()
 
     def close(self):
         self.pop.close()
+        if getattr(self, "window", None) is not None:
+            self.window.close()
         self.ctx.close()
 
 
@@ -344,10 +365,14 @@ class ShardedPSO:
 
 # ------------------------------------------------------------------ island DE -------------------------------------
 class IslandDE:
-    """One reference-exact DE island per rank; global best by all-gather, ring migration every `migrate_every`."""
+    """One reference-exact DE island per rank; ring migration every `migrate_every` generations.  The island bests are
+    exchanged every generation: exchange="peer" — the commit kernel itself stores the island's record into every
+    peer's window over NVLink (CUDA IPC), nothing is launched or waited for, and generations between two migrations
+    are one C call; exchange="nccl" — export kernel + all-gather through torch.distributed after every generation
+    (also the path of the gloo CPU tests).  Default: "peer" on GPUs."""
 
     def __init__(self, cfg, x0, device=0, group=None, migrate_every=10, migrants=64, stream=None,
-                 engine_factory=None):
+                 engine_factory=None, exchange=None):
         import torch
 
         from . import _lib as L
@@ -368,21 +393,29 @@ class IslandDE:
             self.stream = _NullStream()
             self._scope = lambda: self.stream
             self.engine = engine_factory(local, x0)
+        if exchange is None:
+            exchange = "peer" if engine_factory is None else "nccl"
+        self.fused = exchange == "peer"
         self.island = getattr(self.engine, "pop", None)
         self.generation = 0
         self.rb = record_bytes(8 if cfg.dtype == L.F64 else 4, cfg.dim)
+        self._records = None
         tdt = torch.float64 if cfg.dtype == L.F64 else torch.float32
         with self._scope():
-            self.mine = self.engine.tensor(self.rb, torch.uint8)
-            self.all = self.engine.tensor(self.rb * self.comm.world, torch.uint8)
             self.out_rows = self.engine.tensor(self.k * cfg.dim, tdt)
             self.out_scores = self.engine.tensor(self.k, tdt)
             self.in_rows = self.engine.tensor(self.k * cfg.dim, tdt)
             self.in_scores = self.engine.tensor(self.k, tdt)
+            if self.fused:
+                self.engine.open_peer_exchange(self.comm, self.rb)
+            else:
+                self.mine = self.engine.tensor(self.rb, torch.uint8)
+                self.all = self.engine.tensor(self.rb * self.comm.world, torch.uint8)
             if self.comm.world > 1:
                 # NCCL builds its collective and point-to-point channels lazily (seconds): do it here, not in the
                 # first generation / first migration
-                self.comm.all_gather(self.all, self.mine)
+                if not self.fused:
+                    self.comm.all_gather(self.all, self.mine)
                 self.comm.ring_exchange(self.out_rows, self.in_rows)
                 self.comm.ring_exchange(self.out_scores, self.in_scores)
 
@@ -390,25 +423,54 @@ class IslandDE:
     def launches(self):
         return getattr(self.engine, "kernel_launches", 0)
 
+    def _migrate(self):
+        self.engine.export_top(self.k, self.out_rows, self.out_scores)
+        self.comm.ring_exchange(self.out_rows, self.in_rows)
+        self.comm.ring_exchange(self.out_scores, self.in_scores)
+        self.engine.import_migrants(self.k, self.in_rows, self.in_scores)
+
     def step(self, n=1):
+        migrating = self.migrate_every > 0 and self.comm.world > 1 and self.k > 0
         with self._scope():
+            if self.fused:
+                left = n
+                while left > 0:        # up to the next migration point in one call
+                    chunk = min(left, self.migrate_every - self.generation % self.migrate_every) if migrating else left
+                    self.engine.step(chunk)
+                    self.generation += chunk
+                    left -= chunk
+                    if migrating and migration_due(self.generation, self.migrate_every):
+                        self._migrate()
+                return
             for _ in range(n):
                 self.engine.step(1)
                 self.generation += 1
                 self.engine.export_best(self.mine)
                 self.comm.all_gather(self.all, self.mine)
-                if migration_due(self.generation, self.migrate_every) and self.comm.world > 1:
-                    self.engine.export_top(self.k, self.out_rows, self.out_scores)
-                    self.comm.ring_exchange(self.out_rows, self.in_rows)
-                    self.comm.ring_exchange(self.out_scores, self.in_scores)
-                    self.engine.import_migrants(self.k, self.in_rows, self.in_scores)
+                if migrating and migration_due(self.generation, self.migrate_every):
+                    self._migrate()
+
+    def _gathered(self):
+        """uint8 [world, record_bytes]: the newest record of every island."""
+        if self.fused:
+            # every island has finished its enqueued generations (-> its stores into the peers' windows have landed)
+            # before anybody reads, and nobody steps on before everybody has read
+            self.stream.synchronize()
+            with self._scope():
+                self.comm.barrier()
+                self.stream.synchronize()
+                recs = self.engine.read_exchange(self.comm.world)
+                self.comm.barrier()
+            self.stream.synchronize()
+            return recs
+        self.stream.synchronize()
+        return self.all.cpu().numpy().reshape(self.comm.world, self.rb)
 
     def sync(self):
-        """Local island status plus the global best over the last all-gather."""
+        """Local island status plus the global best over the islands' newest records."""
         st = self.engine.sync()
-        self.stream.synchronize()
-        recs = self.all.cpu().numpy()
-        heads = [parse_record(recs[r * self.rb:r * self.rb + HEADER_BYTES]) for r in range(self.comm.world)]
+        self._records = recs = self._gathered()
+        heads = [parse_record(recs[r, :HEADER_BYTES]) for r in range(self.comm.world)]
         win = select_best(heads)
         st["global_best_value"] = heads[win]["value"] if win >= 0 else st["f_value"]
         st["global_best_rank"] = win
@@ -418,8 +480,7 @@ class IslandDE:
         st = self.sync()
         r = max(st["global_best_rank"], 0)
         dt = np.float64 if self.cfg.dtype == 1 else np.float32
-        raw = self.all.cpu().numpy()[r * self.rb + HEADER_BYTES:(r + 1) * self.rb]
-        return raw.view(dt)[:self.cfg.dim].copy()
+        return self._records[r, HEADER_BYTES:].view(dt)[:self.cfg.dim].copy()
 
     def close(self):
         self.engine.close()

@@ -200,6 +200,18 @@ class DEPopulation:
     def import_migrants(self, k, rows_ptr, scores_ptr):
         L.check(L.lib().nls_de_import_migrants(self._h, k, C.c_void_p(rows_ptr), C.c_void_p(scores_ptr)))
 
+    def attach_exchange(self, window):
+        """From here on the commit kernel of every generation stores the island's record into every peer's window."""
+        L.check(L.lib().nls_de_attach_exchange(self._h, window.handle))
+        self._window = window
+
+    def read_exchange(self, world):
+        """Newest record of every island out of this island's own window: uint8 [world, record_bytes]."""
+        rb = L.lib().nls_record_bytes(self.cfg.dtype, self.cfg.dim)
+        out = np.zeros((world, rb), np.uint8)
+        L.check(L.lib().nls_de_read_exchange(self._h, out.ctypes.data))
+        return out
+
     def close(self):
         if self._h:
             L.lib().nls_de_destroy(self._h)

@@ -63,11 +63,13 @@ def test_two_islands_with_ring_migration_match_restatement(obj, strategy, P, d):
     ctx.close()
 
 
-def test_island_de_single_rank_wrapper_runs():
-    """IslandDE at world size 1 (what bench.py drives at --gpus 1): plain DE plus the per-generation best export."""
+@pytest.mark.parametrize("exchange", ["peer", "nccl"])
+def test_island_de_single_rank_wrapper_runs(exchange):
+    """IslandDE at world size 1 (what bench.py drives at --gpus 1): plain DE plus the per-generation best record —
+    published by the commit kernel into the exchange window ("peer") or exported by a kernel of its own ("nccl")."""
     d, P, gens = 40, 2000, 6
     cfg = nb.de_cfg(objective=nb.RASTRIGIN, pop_size=P, dim=d, eps=0.0, max_iter=1 << 40, best_val_no_change=1 << 40, seed=9)
-    isl = D.IslandDE(cfg, np.full(d, 10.24), device=0, migrate_every=2, migrants=4)
+    isl = D.IslandDE(cfg, np.full(d, 10.24), device=0, migrate_every=2, migrants=4, exchange=exchange)
     isl.step(gens)
     st = isl.sync()
     so, ao = B.de_run(B.oracle(), B.de_cfg(objective=B.RASTRIGIN, pop_size=P, dim=d, eps=0.0, max_iter=gens,
@@ -76,3 +78,51 @@ def test_island_de_single_rank_wrapper_runs():
     assert abs(st["global_best_value"] - so["f_value"]) <= 1e-12 * abs(so["f_value"]) and st["global_best_rank"] == 0
     assert np.allclose(isl.global_best_row(), ao["x_best"], rtol=1e-12, atol=0)
     isl.close()
+
+
+@pytest.mark.parametrize("dtype,P,d,strategy", [(nb.F64, 3000, 37, nb.DE_RANDOM), (nb.F32, 700, 130, nb.DE_BEST),
+                                                 (nb.F64, 64, 5, nb.DE_RANDOM)])
+def test_commit_kernel_publishes_the_island_record_every_generation(dtype, P, d, strategy):
+    """With an exchange window attached the commit kernel's last block stores the island's record (value, global id,
+    score moments, best row) into the window: after every generation it equals the record the stand-alone export
+    kernel writes, bit for bit, in either parity slot; stepping several generations per call (graph replay / one-launch
+    kernels for small populations) publishes the same records; a stop rule freezes the last one."""
+    import torch
+    stream = torch.cuda.Stream()
+    ctx = nb.Context(0, stream.cuda_stream)
+    offset = 5 * P
+    cfg = nb.de_cfg(dtype=dtype, objective=nb.SPHERE, strategy=strategy, pop_size=P, dim=d, eps=0.0, max_iter=9,
+                    differential_weight=0.4, best_val_no_change=1 << 40, seed=31, agent_offset=offset)
+    x0 = np.full(d, 3.0)
+    rb = nb.lib().nls_record_bytes(dtype, d)
+    assert rb == D.record_bytes(8 if dtype == nb.F64 else 4, d)
+    pop, twin = nb.DEPopulation(ctx, cfg, x0), nb.DEPopulation(ctx, cfg, x0)
+    win = nb.ExchangeWindow(ctx, rb, 1, 0)
+    pop.attach_exchange(win)
+    with torch.cuda.stream(stream):
+        rec = torch.zeros(rb, dtype=torch.uint8, device="cuda")
+
+        def exported(p):
+            p.export_best(rec.data_ptr())
+            stream.synchronize()
+            return rec.cpu().numpy().copy()
+        assert np.array_equal(pop.read_exchange(1)[0], exported(pop))        # the record of the initial population
+        for g in range(1, 5):
+            pop.step(1)
+            got = pop.read_exchange(1)[0]
+            assert np.array_equal(got, exported(pop)), g
+            h = D.parse_record(got)
+            st = pop.sync()
+            assert h["valid"] == 1 and h["value"] == st["f_value"] and h["index"] == offset + st["best_index"] and h["n"] == P
+        pop.step(20)                                                          # runs into max_iter = 9 and stops there
+        twin.step(20)
+        st, ts = pop.sync(), twin.sync()
+        # (repair_reruns / repair_rounds are diagnostics of the fixed-point repair and may depend on timing)
+        same = ("f_value", "iterations", "function_calls", "best_index", "val_no_change", "stop_reason", "accepted_total")
+        assert st["stopped"] and st["iterations"] == 9 and all(st[k] == ts[k] for k in same)
+        assert np.array_equal(pop.read_exchange(1)[0], exported(twin))
+        assert np.array_equal(pop.population(), twin.population())            # attaching a window changes no decision
+    pop.close()
+    twin.close()
+    win.close()
+    ctx.close()

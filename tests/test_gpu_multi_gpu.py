@@ -32,5 +32,7 @@ def test_multi_gpu_check_under_torchrun():
     out = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=900)
     assert out.returncode == 0, out.stdout[-4000:] + out.stderr[-4000:]
     for needle in ("identical to single-GPU swarm = True", "identical to the NCCL path = True",
-                   "equal the restatement = True", "equal the oracle = True"):
+                   "(nccl exchange): every island and the global best equal the restatement = True",
+                   "(peer exchange): every island and the global best equal the restatement = True",
+                   "equal the oracle = True"):
         assert needle in out.stdout, out.stdout[-4000:]

@@ -71,11 +71,6 @@ def main():
     dkw = dict(objective=nb.ROSENBROCK, strategy=nb.DE_BEST, pop_size=Pi, dim=di, eps=0.0, max_iter=1 << 40,
                best_val_no_change=1 << 40, seed=77)
     x0 = np.full(di, 4.096)
-    isl = D.IslandDE(nb.de_cfg(**dkw), x0, device=local, migrate_every=every, migrants=k)
-    isl.step(gens)
-    ist = isl.sync()
-    rows = isl.engine.pop.population()
-    grow = isl.global_best_row()
     steppers = [B.DEStepper(oracle_de_cfg(nb.de_cfg(**dict(dkw, agent_offset=r * Pi))), x0) for r in range(world)]
     for g in range(1, gens + 1):
         for s in steppers:
@@ -86,15 +81,24 @@ def main():
                 s.import_migrants(*out[D.ring_neighbors(r, world)[1]])
     want = [s.report() for s in steppers]
     gbest = min(range(world), key=lambda r: (want[r][0]["f_value"], r))
-    mine = (np.array_equal(rows, want[rank][1]["rows"]) and ist["f_value"] == want[rank][0]["f_value"]
-            and ist["global_best_rank"] == gbest and ist["global_best_value"] == want[gbest][0]["f_value"]
-            and np.array_equal(grow, want[gbest][1]["x_best"]))
-    flag = torch.tensor([1 if mine else 0], device=f"cuda:{local}")
-    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-    if rank == 0:
-        print(f"island DE x{world}: every island and the global best equal the restatement = {bool(flag.item())}", flush=True)
-    ok &= bool(flag.item())
-    isl.close()
+    # "nccl": export kernel + all-gather after every generation; "peer": the commit kernel stores the island's record
+    # into every peer's window over NVLink, generations between two migrations are one call
+    for exchange in ("nccl", "peer"):
+        isl = D.IslandDE(nb.de_cfg(**dkw), x0, device=local, migrate_every=every, migrants=k, exchange=exchange)
+        isl.step(gens)
+        ist = isl.sync()
+        rows = isl.engine.pop.population()
+        grow = isl.global_best_row()
+        mine = (np.array_equal(rows, want[rank][1]["rows"]) and ist["f_value"] == want[rank][0]["f_value"]
+                and ist["global_best_rank"] == gbest and ist["global_best_value"] == want[gbest][0]["f_value"]
+                and np.array_equal(grow, want[gbest][1]["x_best"]))
+        flag = torch.tensor([1 if mine else 0], device=f"cuda:{local}")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if rank == 0:
+            print(f"island DE x{world} ({exchange} exchange): every island and the global best equal the restatement = "
+                  f"{bool(flag.item())}", flush=True)
+        ok &= bool(flag.item())
+        isl.close()
 
     # ---- SANN chains sharded by global chain id: no exchange while the chains run, one all-gather for the batch best ----
     n, ds, it = 1000 + 3, 24, 30
