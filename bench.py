@@ -5,8 +5,9 @@ Workload at N = 1: BASELINE.json configs[1] — DE, random recombination, Rastri
 fp64, CR = 0.9, F = 0.8, x0[j] = 10.24 (agents start uniform in [-5.12, 5.12]); stop rules disabled (eps = 0,
 best_val_no_change = inf) so only the step count ends the run.  A "step" is one generation: one pass
 of the hot path over the whole population = P agent evaluations.  At N > 1 DE does not shard a single population
-(SURVEY.md §8e), so every rank runs one such island (weak scaling) with the per-generation best all-gather and the
-ring migration every 10 generations; `value` is the whole-job agent-evaluations per second.
+(SURVEY.md §8e), so every rank runs one such island (weak scaling); the island bests are exchanged every generation —
+the commit kernel stores the island's record into every peer's exchange window over NVLink — and the 64 best rows go
+around the ring every 10 generations; `value` is the whole-job agent-evaluations per second.
 
     python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's CUDA path
     python bench.py --impl reference [--gpus N] [--steps K] ...    # the reference's own CPU path, all host threads
@@ -326,9 +327,10 @@ def bench_config2(b):
                 "call": "nlsolver_b200.DE(...).minimize(x) -> nls_de_solve: H2D x0 + init + K generations + D2H best "
                         "row/status, after one warm-up call of the same shape (device buffers are cached by the "
                         "context); the population is generated on the device, as in the reference"},
-        "roofline": {"bound": "hbm", "kernel": "de_generation_kernel<double, Rastrigin>", "achieved": achieved,
+        "roofline": {"bound": "hbm", "kernel": "de_generation_bulk_kernel<double, Rastrigin, 2, 2> (K2, rows staged by TMA bulk copies)",
+                     "achieved": achieved,
                      "peak": b.peak, "unit": "GB/s", "frac": achieved / b.peak, "peak_source": b.peak_src,
-                     "traffic": committed_traffic("de_generation_kernel"),
+                     "traffic": committed_traffic("de_generation_bulk_kernel"),
                      "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": k2_ms,
                      "step_share": {"generation": kernel_ms[0] / total_ms, "repair": kernel_ms[1] / total_ms,
                                     "commit_reduce": kernel_ms[2] / total_ms}},

@@ -491,27 +491,45 @@ __device__ __forceinline__ void de_repair_pass(const DEState &s, DETileEntry *ti
   u32 k = 1;
   for (;; k++) {
     const u32 want = k - 1, cur = k % 3u;
-    // ---- scan
-    for (u64 base = warp << 5; base < P; base += n_threads) {
-      const u64 mine = base + lane;
-      bool hit = false;
-      if (mine < P) {
-        const uint4 dc = s.dec[mine];
-        const u32 don[4] = {dc.x, dc.y, dc.z, u32(best_id)};
+    // ---- scan: kScan agents per lane and trip.  All decision loads of the trip are issued first, then all stamp loads
+    // (two dependent L2 round trips per trip instead of two per agent), and the warp reserves list space with ONE atomic
+    // per trip — the round trip of a per-32-agents atomic, 37 times in a row at P = 2^22, was most of a scan.
+    constexpr int kScan = 4;
+    for (u64 base = warp * (32u * kScan); base < P; base += n_threads * kScan) {
+      uint4 dc[kScan];
+      u32 f[kScan][4];
+#pragma unroll
+      for (int u = 0; u < kScan; u++) {
+        const u64 mine = base + u64(u) * 32u + lane;
+        dc[u] = mine < P ? s.dec[mine] : make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0u);
+      }
+#pragma unroll
+      for (int u = 0; u < kScan; u++) {
+        const u64 mine = base + u64(u) * 32u + lane;
+        const u32 don[4] = {dc[u].x, dc[u].y, dc[u].z, u32(best_id)};
 #pragma unroll
         for (int q = 0; q < 4; q++) {
-          const bool low = don[q] < mine && (q < 3 || best_mode);
+          const bool low = mine < P && don[q] < mine && (q < 3 || best_mode);
           // (predicated load: the stamp of a donor that is not lower is never needed)
-          const u32 f = low ? u32(__ldcg(s.fin + don[q])) : 0x10000u;
-          hit |= f == want;
+          f[u][q] = low ? u32(__ldcg(s.fin + don[q])) : 0x10000u;
         }
       }
-      const u32 vote = __ballot_sync(kFull, hit);
-      if (vote) {
+      u32 vote[kScan], n_hits = 0;
+#pragma unroll
+      for (int u = 0; u < kScan; u++) {
+        const bool hit = f[u][0] == want || f[u][1] == want || f[u][2] == want || f[u][3] == want;
+        vote[u] = __ballot_sync(kFull, hit);
+        n_hits += __popc(vote[u]);
+      }
+      if (n_hits) {                                         // warp-uniform
         u32 slot = 0;
-        if (lane == 0) slot = atomicAdd(&ctrl->list_count[cur], __popc(vote));
+        if (lane == 0) slot = atomicAdd(&ctrl->list_count[cur], n_hits);
         slot = __shfl_sync(kFull, slot, 0);
-        if (hit) s.list[slot + __popc(vote & ((1u << lane) - 1u))] = u32(mine);
+#pragma unroll
+        for (int u = 0; u < kScan; u++) {
+          if (vote[u] & (1u << lane)) s.list[slot + __popc(vote[u] & ((1u << lane) - 1u))] = u32(base + u64(u) * 32u + lane);
+          slot += __popc(vote[u]);
+        }
       }
     }
     sync();

@@ -190,14 +190,18 @@ struct Objective {
             a = A::add(a, A::add(A::mul(t1, t1), A::mul(A::mul(T(100), t2), t2)));
           }
         }
+      } else if (OBJ == OBJ_ACKLEY) {
+        // branch-free (a padding coordinate is evaluated and dropped): a jump around the cos polynomial would end the
+        // basic block, and the terms of the lane's V coordinates would be evaluated one dependent chain after the other
+        const T sq = A::mul(xj, xj), c = cos2pi<T>(xj);
+        const bool valid = j < d;
+        a = valid ? A::add(a, sq) : a;
+        b = valid ? A::add(b, c) : b;
       } else if (j < d) {
         if (OBJ == OBJ_SPHERE) {
           a = A::add(a, A::mul(xj, xj));
         } else if (OBJ == OBJ_RASTRIGIN) {                 // x*x - 10*cos(2*pi*x)
           a = A::add(a, A::sub(A::mul(xj, xj), A::mul(T(10), cos2pi<T>(xj))));
-        } else if (OBJ == OBJ_ACKLEY) {
-          a = A::add(a, A::mul(xj, xj));
-          b = A::add(b, cos2pi<T>(xj));
         } else if (OBJ == OBJ_STYBLINSKI_TANG) {         // pow(x,4) - 16*pow(x,2) + 5*x, test_functions.h:246-252
           const T x2 = A::mul(xj, xj);
           a = A::add(a, A::add(A::sub(A::mul(x2, x2), A::mul(T(16), x2)), A::mul(T(5), xj)));

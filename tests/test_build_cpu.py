@@ -1,0 +1,54 @@
+"""The build's own report (nvcc -Xptxas -v, kept per translation unit under nlsolver_b200/csrc/build/ by the Makefile) is
+checked, not just collected: the kernels the BASELINE configurations run in fp64 must not spill at all, and no shipped
+kernel may spill more than a few registers' worth (a launch bound that starts to spill a hot loop shows up here, on CPU,
+before it shows up as a slower number)."""
+import glob
+import os
+import re
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LOGS = sorted(glob.glob(os.path.join(ROOT, "nlsolver_b200", "csrc", "build", "*.ptxas.log")))
+
+# (demangled-name pattern, what runs it)
+NO_SPILL = [
+    (r"de_generation_bulk_kernel<double, 2, 2, 2>", "config 2: DE-random Rastrigin d=1000"),
+    (r"de_generation_bulk_kernel<double, 1, 2, 2>", "config 4: DE-best Rosenbrock d=4096"),
+    (r"de_repair_kernel<double, [012], 32, 1, 1, true>", "configs 2 / 4 and the accepting regime: repair of long rows"),
+    (r"de_commit_kernel<double>", "configs 2 / 4 / 5: commit + reduce"),
+    (r"pso_move_kernel<double, 3, 1, 32, 1, 1>", "config 3: accelerated PSO, Ackley d=256"),
+    (r"pso_candidate_kernel<double>|pso_apply_kernel<double>|pso_candidate_publish_kernel<double>|pso_gather_apply_kernel<double>",
+     "config 3: min-loc reduction and exchange"),
+    (r"de_generation_kernel<double, 0, 16, 2, 2, false>", "config 5: DE Sphere d=64 fp64"),
+    (r"pso_move_kernel<double, 0, 0, 16, 2, 2>", "config 5: vanilla PSO Sphere d=64 fp64"),
+]
+MAX_SPILL_BYTES = 128
+
+
+def kernels():
+    rows = []
+    for path in LOGS:
+        for block in re.split(r"ptxas info\s+: Compiling entry function '", open(path).read())[1:]:
+            m = re.search(r"(\d+) bytes stack frame, (\d+) bytes spill stores, (\d+) bytes spill loads", block)
+            r = re.search(r"Used (\d+) registers", block)
+            if m and r:
+                rows.append([block.split("'")[0], int(r.group(1)), int(m.group(2)), int(m.group(3))])
+    names = subprocess.run(["c++filt"], input="\n".join(r[0] for r in rows), capture_output=True, text=True, check=True)
+    for row, name in zip(rows, names.stdout.splitlines()):
+        row[0] = name.replace("nls::", "").split("(")[0].replace("void ", "")
+    return rows
+
+
+@pytest.mark.skipif(not LOGS, reason="no build logs: run __graft_entry__.build() first")
+def test_headline_kernels_do_not_spill_and_no_kernel_spills_much():
+    rows = kernels()
+    assert len(rows) > 500, "the ptxas logs of every translation unit are expected"
+    for pattern, what in NO_SPILL:
+        hit = [r for r in rows if re.search(pattern, r[0])]
+        assert hit, f"no kernel matches {pattern} ({what})"
+        for name, regs, st, ld in hit:
+            assert st == 0 and ld == 0, f"{name} ({what}) spills {st} / {ld} bytes at {regs} registers"
+    worst = max(rows, key=lambda r: r[2])
+    assert worst[2] <= MAX_SPILL_BYTES, f"{worst[0]} spills {worst[2]} bytes"

@@ -25,4 +25,13 @@ run k2_config4 "de_generation" 3 1 python tools/probe_de.py --pop 262144 --dim 4
 # accelerated PSO, config-3 shard shape; vanilla PSO fp32 d=64 (config-5 point)
 run pso_accel_config3 "pso_move_kernel" 4 1 python tests/tools/quick_time_pso.py 2097152 256 3 3 1 1
 run pso_vanilla_f32_d64 "pso_move_kernel" 4 1 python tests/tools/quick_time_pso.py 4194304 64 3 0 0 0
-ls -la $O
+# gpurun brings back at most 64 MiB: export the pages here, keep only the headline kernel's report
+for f in $O/*.ncu-rep; do
+  n=${f%.ncu-rep}
+  ncu -i $f --page raw --csv > $n.raw.csv 2>/dev/null
+  ncu -i $f --page source --csv > $n.source.csv 2>/dev/null
+  ncu -i $f --page details > $n.details.txt 2>/dev/null
+  case $f in *k2_config2*) ;; *) rm -f $f ;; esac
+done
+gzip -9 $O/*.source.csv
+ls -la $O; du -sh gpurun_out
