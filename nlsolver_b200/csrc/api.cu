@@ -432,6 +432,8 @@ static int de_build(nls_ctx *ctx, const nls_de_cfg *cfg, const void *x0_host, nl
   NLS_ALLOC(s.dec, P * sizeof(uint4));
   NLS_ALLOC(s.rej, P * sizeof(uint32_t));
   NLS_ALLOC(s.list, P * sizeof(uint32_t));
+  s.coarse_words = (P + 1023) / 1024;
+  NLS_ALLOC(s.coarse, 3 * s.coarse_words * sizeof(uint32_t));
   NLS_ALLOC(s.ctrl, sizeof(DECtrl));
   // (the one-launch path reduces with up to 16 blocks whatever the population)
   const size_t n_part = std::max(de->g.reduce_blocks, 16);
@@ -450,6 +452,7 @@ static int de_build(nls_ctx *ctx, const nls_de_cfg *cfg, const void *x0_host, nl
   NLS_CUDA(cudaMemsetAsync(s.fin, 0, P * sizeof(uint16_t), st));
   NLS_CUDA(cudaMemsetAsync(s.dec, 0, P * sizeof(uint4), st));
   NLS_CUDA(cudaMemsetAsync(s.rej, 0, P * sizeof(uint32_t), st));
+  NLS_CUDA(cudaMemsetAsync(s.coarse, 0, 3 * s.coarse_words * sizeof(uint32_t), st));
   if (s.masks) NLS_CUDA(cudaMemsetAsync(s.masks, 0, P * d, st));
   NLS_CUDA(cudaMemcpyAsync(x0_dev, x0_host, d * de->elem, cudaMemcpyHostToDevice, st));
   NLS_CUDA(de->ops->init(s, x0_dev, de->g, st));

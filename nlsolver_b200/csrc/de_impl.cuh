@@ -297,7 +297,15 @@ __device__ __forceinline__ void de_tile_body(const DEState &s, const DETileEntry
 #ifndef NLS_DE_BULK_BLOCKS
 #define NLS_DE_BULK_BLOCKS 2
 #endif
-template <int U> struct DEBlocksPerSM { static constexpr int value = U >= 2 ? 3 : 4; };
+// Sweep steps in flight per lane when the repair re-evaluates LONG rows.  A listed agent is four random rows read by
+// one warp, and a warp gets a handful of agents per iteration, so what an iteration costs is the latency of a row, i.e.
+// (steps per row) / (steps in flight) DRAM round trips.  K2r at the config-2 shape with 2-3 % of the trials accepted:
+// 0.52 / 0.42 / 0.36 ms with one step in flight, 0.37 / 0.29 / 0.26 with two, 0.34 / 0.26 / 0.23 with four (128
+// registers, two blocks per SM — occupancy is not what this pass needs).
+#ifndef NLS_DE_REPAIR_U
+#define NLS_DE_REPAIR_U 4
+#endif
+template <int U> struct DEBlocksPerSM { static constexpr int value = U >= 4 ? 2 : (U >= 2 ? 3 : 4); };
 // barriers of the multi-phase passes: the whole grid (cooperative launch) or one thread-block cluster (the one-launch
 // path for small populations, where a generation is a handful of microseconds and the barrier latency is what counts)
 struct GridSync {
@@ -493,8 +501,17 @@ __device__ __forceinline__ void de_repair_pass(const DEState &s, DETileEntry *ti
     const u32 want = k - 1, cur = k % 3u;
     // ---- scan: kScan agents per lane and trip.  All decision loads of the trip are issued first, then all stamp loads
     // (two dependent L2 round trips per trip instead of two per agent), and the warp reserves list space with ONE atomic
-    // per trip — the round trip of a per-32-agents atomic, 37 times in a row at P = 2^22, was most of a scan.
+    // per trip.  A scan is bound by the random 32-byte sectors of the stamp lookups (1.5 per agent), so from the second
+    // iteration on they are filtered through a coarse bitmap the previous re-evaluation filled — one bit per 32 agents,
+    // small enough to live in L1: in the late iterations, where a few thousand agents were stamped, almost every lookup
+    // stops there and the scan streams the decisions only.  (Ordinary loads: the grid / cluster barrier that separates
+    // the bitmap's writers from these readers makes them visible.)
     constexpr int kScan = 4;
+    const u32 *cb_prev = (s.coarse != nullptr && k >= 2) ? s.coarse + u64((k - 1) % 3u) * s.coarse_words : nullptr;
+    u32 *cb_cur = s.coarse != nullptr ? s.coarse + u64(cur) * s.coarse_words : nullptr;
+    // the bitmap this iteration's re-evaluation fills: its last readers were the scan two iterations ago
+    if (cb_cur != nullptr)
+      for (u64 w = tid; w < s.coarse_words; w += n_threads) cb_cur[w] = 0u;
     for (u64 base = warp * (32u * kScan); base < P; base += n_threads * kScan) {
       uint4 dc[kScan];
       u32 f[kScan][4];
@@ -503,16 +520,23 @@ __device__ __forceinline__ void de_repair_pass(const DEState &s, DETileEntry *ti
         const u64 mine = base + u64(u) * 32u + lane;
         dc[u] = mine < P ? s.dec[mine] : make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0u);
       }
+      bool look[kScan][4];
 #pragma unroll
       for (int u = 0; u < kScan; u++) {
         const u64 mine = base + u64(u) * 32u + lane;
         const u32 don[4] = {dc[u].x, dc[u].y, dc[u].z, u32(best_id)};
 #pragma unroll
         for (int q = 0; q < 4; q++) {
-          const bool low = mine < P && don[q] < mine && (q < 3 || best_mode);
-          // (predicated load: the stamp of a donor that is not lower is never needed)
-          f[u][q] = low ? u32(__ldcg(s.fin + don[q])) : 0x10000u;
+          // (predicated loads: the stamp of a donor that is not lower is never needed)
+          look[u][q] = mine < P && don[q] < mine && (q < 3 || best_mode);
+          if (cb_prev != nullptr && look[u][q]) look[u][q] = (cb_prev[don[q] >> 10] >> ((don[q] >> 5) & 31u)) & 1u;
         }
+      }
+#pragma unroll
+      for (int u = 0; u < kScan; u++) {
+        const u32 don[4] = {dc[u].x, dc[u].y, dc[u].z, u32(best_id)};
+#pragma unroll
+        for (int q = 0; q < 4; q++) f[u][q] = look[u][q] ? u32(__ldcg(s.fin + don[q])) : 0x10000u;
       }
       u32 vote[kScan], n_hits = 0;
 #pragma unroll
@@ -549,7 +573,11 @@ __device__ __forceinline__ void de_repair_pass(const DEState &s, DETileEntry *ti
       __syncwarp();
       const int n_here = (n_list - first) < tile_size ? int(n_list - first) : int(tile_size);
       de_tile_body<T, OBJ, W, U, S, SKIP_BASE>(s, tile_entries, n_here, false, lane, [&](const DETileEntry &e, bool ok) {
-        if ((e.flags >> 1) | u32(ok)) { s.fin[e.agent] = uint16_t(k); n_changed++; }
+        if ((e.flags >> 1) | u32(ok)) {
+          s.fin[e.agent] = uint16_t(k);
+          if (cb_cur != nullptr) atomicOr(cb_cur + (e.agent >> 10), 1u << ((e.agent >> 5) & 31u));
+          n_changed++;
+        }
       });
       __syncwarp();
     }
@@ -969,7 +997,7 @@ cudaError_t de_launch_repair(const DEState &s, const LaunchGeom &g, cudaStream_t
   if (vecs <= 4) return de_launch_repair_w<T, O, 4, 1, 1, false>(s, g, st);
   if (vecs <= 8) return de_launch_repair_w<T, O, 8, 1, 1, false>(s, g, st);
   if (vecs <= 16) return de_launch_repair_w<T, O, 16, 1, 1, false>(s, g, st);
-  return de_launch_repair_w<T, O, 32, 1, 1, true>(s, g, st);
+  return de_launch_repair_w<T, O, 32, NLS_DE_REPAIR_U, 1, true>(s, g, st);
 }
 
 // one generation: K2, K2r (cooperative), K3

@@ -38,6 +38,9 @@ struct DEState {
   uint32_t *rej;         // [P] rejected index proposals (draw offset of the crossover draws = 4 + rej)
   uint8_t *masks;        // [P*d] crossover mask of the last generation, or NULL
   uint32_t *list;        // [P] repair: agents to re-evaluate in the current iteration; migration: the top-k picks
+  uint32_t *coarse;      // [3][coarse_words] repair: one bit per 32 agents, "an agent of this group was stamped in iteration k"
+                         // (bitmap k % 3); NULL: no filter
+  unsigned long long coarse_words;
   void *topk_scratch;    // migration top-k candidates: ceil(P / 4096) * k (key, visit) pairs
   DECtrl *ctrl;
   // reduction partials [n_partials]

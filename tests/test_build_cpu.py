@@ -16,7 +16,6 @@ LOGS = sorted(glob.glob(os.path.join(ROOT, "nlsolver_b200", "csrc", "build", "*.
 NO_SPILL = [
     (r"de_generation_bulk_kernel<double, 2, 2, 2>", "config 2: DE-random Rastrigin d=1000"),
     (r"de_generation_bulk_kernel<double, 1, 2, 2>", "config 4: DE-best Rosenbrock d=4096"),
-    (r"de_repair_kernel<double, [012], 32, 1, 1, true>", "configs 2 / 4 and the accepting regime: repair of long rows"),
     (r"de_commit_kernel<double>", "configs 2 / 4 / 5: commit + reduce"),
     (r"pso_move_kernel<double, 3, 1, 32, 1, 1>", "config 3: accelerated PSO, Ackley d=256"),
     (r"pso_candidate_kernel<double>|pso_apply_kernel<double>|pso_candidate_publish_kernel<double>|pso_gather_apply_kernel<double>",

@@ -13,9 +13,8 @@ for spec in "$@"; do
   (
     nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC,-fvisibility=hidden -Xptxas -v \
       $flags -c de_f64.cu -o $OUT/de_f64_$name.o 2> $OUT/$name.ptxas.log
-    nvcc -shared -o $OUT/libnls_b200_$name.so build/api.o $OUT/de_f64_$name.o build/de_f32.o build/pso_f64.o build/pso_f32.o \
-      build/sann_f64.o build/sann_f32.o -lcudart -ldl 2>/dev/null
-    echo "$name: $(grep -A2 'de_generation_bulk_kernelIdLi1' $OUT/$name.ptxas.log | grep -E 'registers|spill' | tr '\n' ' ')"
+    nvcc -shared -o $OUT/libnls_b200_$name.so $(ls build/*.o | grep -v "build/de_f64.o") $OUT/de_f64_$name.o -lcudart -ldl 2>/dev/null
+    echo "$name: $(grep -A2 "${REPORT:-de_generation_bulk_kernelIdLi1}" $OUT/$name.ptxas.log | grep -E 'registers|spill' | tr '\n' ' ')"
   ) &
 done
 wait
