@@ -997,6 +997,9 @@ cudaError_t de_launch_repair(const DEState &s, const LaunchGeom &g, cudaStream_t
   if (vecs <= 4) return de_launch_repair_w<T, O, 4, 1, 1, false>(s, g, st);
   if (vecs <= 8) return de_launch_repair_w<T, O, 8, 1, 1, false>(s, g, st);
   if (vecs <= 16) return de_launch_repair_w<T, O, 16, 1, 1, false>(s, g, st);
+  // long rows: NLS_DE_REPAIR_U sweep steps in flight per lane (NLS_DE_REPAIR_U=2 in the environment: two)
+  static const int steps = [] { const char *e = std::getenv("NLS_DE_REPAIR_U"); return e ? std::atoi(e) : NLS_DE_REPAIR_U; }();
+  if (steps == 2) return de_launch_repair_w<T, O, 32, 2, 1, true>(s, g, st);
   return de_launch_repair_w<T, O, 32, NLS_DE_REPAIR_U, 1, true>(s, g, st);
 }
 
