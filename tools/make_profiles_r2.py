@@ -126,7 +126,8 @@ def main():
                      ("r2_n8/bench_n1.json", "r2_bench_n1_same_box_as_n8.json"),
                      ("r2_n8/multi_gpu_check_n8.txt", "r2_multi_gpu_check_n8.txt"), ("r2_n8/group_n8.json", "r2_device_group_n8.json"),
                      ("r2_final/bench_n1.json", "r2_bench_n1.json"), ("r2_final/bench_ref.json", "r2_bench_reference_arm.json"),
-                     ("r2_final/bench_small.json", "r2_bench_small.json"), ("r2_final/sann.json", "r2_sann_bench_n1.json")):
+                     ("r2_final/bench_small.json", "r2_bench_small.json"), ("r2_final/sann.json", "r2_sann_bench_n1.json"),
+                     ("r2_sweep/sweep.md", "r2_sweep_d64.md")):
         copy(src, dst)
     for d in ("r2_s2b", "r2_final_ncu"):
         src = os.path.join(OUT, d)
