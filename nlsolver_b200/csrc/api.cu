@@ -580,7 +580,7 @@ static int de_status(nls_de *de, nls_status *status) {
 }
 
 // re-scan the best and (with an exchange window attached) publish the island's record again
-static int nls_de_republish(nls_de *de) {
+static int de_republish(nls_de *de) {
   NLS_CUDA(de->ops->rescan(de->s, de->g, de->ctx->stream));
   return NLS_OK;
 }
@@ -1452,7 +1452,7 @@ int nls_de_attach_exchange(nls_de *de, nls_xchg *x) {
   de->s.xw = static_cast<const XchgWindow *>(dev);
   de->graph.reset();                                     // captured launches carry the state by value
   // publish the record of the population as it stands (a best re-scan changes nothing else)
-  return nls_de_republish(de);
+  return de_republish(de);
 }
 
 int nls_de_read_exchange(nls_de *de, void *records_host) {

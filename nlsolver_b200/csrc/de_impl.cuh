@@ -305,6 +305,25 @@ __device__ __forceinline__ void de_tile_body(const DEState &s, const DETileEntry
 #ifndef NLS_DE_REPAIR_U
 #define NLS_DE_REPAIR_U 4
 #endif
+// Tile size (log2, <= 5) for a pass over n agents by n_warps warps that stream G agents at a time.  A tile costs one
+// prologue — a chain of dependent round trips: draws -> donor ids -> row locations -> scores — plus ceil(tile / G) body
+// trips of one row latency each, and the pass lasts as long as the warp with the most tiles.  `prologue` is the cost of
+// a prologue in body trips (about 2 for short rows, a fraction for long ones).  Large populations end up with the
+// largest tile (fewest prologues; every warp still gets many tiles), small ones with few, larger tiles per warp instead
+// of many one-agent tiles whose prologue latency nothing hides: K2 at P = 2^16, d = 64 is 9 trips of (prologue + one row)
+// per warp with 2-agent tiles, and 3 x (prologue + 4 rows) with 8-agent tiles.
+__host__ __device__ inline int de_tile_shift(unsigned long long n, unsigned long long n_warps, int G, double prologue) {
+  int best = 0;
+  double best_cost = 1e300;
+  for (int shift = 0; shift <= 5; shift++) {
+    const unsigned long long tiles = (n + (1ull << shift) - 1) >> shift;
+    const unsigned long long per_warp = (tiles + n_warps - 1) / n_warps;
+    const double cost = double(per_warp) * (prologue + double(((1u << shift) + G - 1) / G));
+    if (cost <= best_cost) { best_cost = cost; best = shift; }     // ties: the larger tile
+  }
+  return best;
+}
+
 template <int U> struct DEBlocksPerSM { static constexpr int value = U >= 4 ? 2 : (U >= 2 ? 3 : 4); };
 // barriers of the multi-phase passes: the whole grid (cooperative launch) or one thread-block cluster (the one-launch
 // path for small populations, where a generation is a handful of microseconds and the barrier latency is what counts)
@@ -563,8 +582,7 @@ __device__ __forceinline__ void de_repair_pass(const DEState &s, DETileEntry *ti
     if (tid == 0) { ctrl->list_count[(k + 2u) % 3u] = 0; ctrl->changed[(k + 2u) % 3u] = 0; }
     if (n_list == 0) break;
     // ---- re-evaluate: tiles of the list, sized so that every warp gets work (a short list is spread thin)
-    int shift = 5;
-    while (shift > 0 && ((u64(n_list) + (1ull << shift) - 1) >> shift) < 4ull * n_warps) shift--;
+    const int shift = de_tile_shift(n_list, n_warps, 32 / W, W == 32 ? 0.5 : 2.0);
     const u64 tile_size = 1ull << shift, n_tiles = (u64(n_list) + tile_size - 1) >> shift;
     u32 n_changed = 0;
     for (u64 tile = warp; tile < n_tiles; tile += n_warps) {
@@ -926,8 +944,7 @@ void de_launch_k2_w(const DEState &s, const LaunchGeom &g, cudaStream_t st) {
   const u64 want = (s.P + kWarpsPerBlock - 1) / kWarpsPerBlock;
   auto kernel = de_generation_kernel<T, O, W, U, S, SKIP_BASE>;
   const unsigned int grid = clamp_grid(want, u64(g.sm_count) * blocks_per_sm(kernel));
-  int shift = 5;                                       // largest tile that still gives >= 8 tiles per warp
-  while (shift > 0 && ((s.P + (1ull << shift) - 1) >> shift) < 8ull * grid * kWarpsPerBlock) shift--;
+  const int shift = de_tile_shift(s.P, u64(grid) * kWarpsPerBlock, 32 / W, W == 32 ? 0.5 : 2.0);
   kernel<<<grid, kBlock, 0, st>>>(s, shift);
 }
 // NLS_DE_BULK in the environment overrides the staging policy: 0 never, 1 best recombination only, 2 both
@@ -953,8 +970,7 @@ void de_launch_k2_bulk(const DEState &s, const LaunchGeom &g, cudaStream_t st) {
   }
   const u64 want = (s.P + kWarpsPerBlock - 1) / kWarpsPerBlock;
   const unsigned int grid = clamp_grid(want, u64(g.sm_count) * per_sm);
-  int shift = 5;                                       // largest tile that still gives >= 8 tiles per warp
-  while (shift > 0 && ((s.P + (1ull << shift) - 1) >> shift) < 8ull * grid * kWarpsPerBlock) shift--;
+  const int shift = de_tile_shift(s.P, u64(grid) * kWarpsPerBlock, 1, 0.25);
   kernel<<<grid, kBlock, smem, st>>>(s, shift);
 }
 // lane-group shape by row length in 128-bit vectors (see de_generation_kernel)
