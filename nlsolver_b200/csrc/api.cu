@@ -61,7 +61,7 @@ struct ObjectivePlugin {
   const SANNOps *sann_f64, *sann_f32;
 };
 constexpr int kFirstPluginId = 100;
-constexpr int kPluginAbi = 4;
+constexpr int kPluginAbi = 5;
 constexpr int kMaxPlugins = 256;
 // fixed-capacity registry: entries are written once under the mutex and published by the count, so lookups from solver
 // threads never see a reallocating container
@@ -957,8 +957,7 @@ int nls_pso_step(nls_pso *p, uint64_t n_generations) {
       const bool ok = graph_replay(p->graph, st, [&] {
         for (int g = 0; g < kGraphGens; g++) {
           if (p->ops->move(p->s, p->g, st) != cudaSuccess) return false;
-          if (p->ops->candidate(p->s, p->record, p->g, st) != cudaSuccess) return false;
-          if (p->ops->apply(p->s, p->record, 1, p->record_bytes, 0, st) != cudaSuccess) return false;
+          if (p->ops->candidate_apply(p->s, p->record, p->record_bytes, p->g, st) != cudaSuccess) return false;
         }
         return true;
       });
@@ -967,11 +966,12 @@ int nls_pso_step(nls_pso *p, uint64_t n_generations) {
       p->enqueued += kGraphGens;
     }
   }
+  if (left > 0 && p->first_apply_pending) return fail(NLS_ERR_STATE, "nls_pso_step: apply the initial candidates first");
+  NLS_CUDA(cudaSetDevice(p->ctx->device));
   for (uint64_t g = 0; g < left; g++) {
-    int rc = nls_pso_step_local(p, nullptr);
-    if (rc != NLS_OK) return rc;
-    rc = nls_pso_apply_candidates(p, p->record, 1);
-    if (rc != NLS_OK) return rc;
+    NLS_CUDA(p->ops->move(p->s, p->g, p->ctx->stream));
+    NLS_CUDA(p->ops->candidate_apply(p->s, p->record, p->record_bytes, p->g, p->ctx->stream));
+    p->enqueued++;
   }
   return NLS_OK;
 }

@@ -609,12 +609,20 @@ __device__ __forceinline__ void de_repair_pass(const DEState &s, DETileEntry *ti
   if (tid == 0) ctrl->rounds += k;
 }
 
+template <class T>
+__device__ __forceinline__ void de_commit_pass(const DEState &s, int mode);
+
+// commit != 0: K3 runs behind the repair in the same launch (small populations, where a generation is bound by launch
+// latency; the launcher only asks for it when this grid is the commit kernel's grid, so partials and results are the
+// same).  Every way out of the repair pass is right behind a grid barrier — or nothing was written at all — so the
+// commit pass may read what the repair wrote.
 template <class T, int OBJ, int W, int U, int S, bool SKIP_BASE>
-__global__ void __launch_bounds__(kBlock, DEBlocksPerSM<U>::value) de_repair_kernel(DEState s) {
+__global__ void __launch_bounds__(kBlock, DEBlocksPerSM<U>::value) de_repair_kernel(DEState s, int commit) {
   __shared__ DETileEntry tile_mem[kWarpsPerBlock][32];
   if (s.ctrl->stop) return;                              // uniform over the grid: only K3 changes it
   GridSync sync{cg::this_grid()};
   de_repair_pass<T, OBJ, W, U, S, SKIP_BASE>(s, tile_mem[threadIdx.x >> 5], sync);
+  if (commit) de_commit_pass<T>(s, 0);
 }
 
 // ------------------------------------------------------------------------------------------------ K3 commit + reduce
@@ -997,48 +1005,52 @@ void de_launch_k2(const DEState &s, const LaunchGeom &g, cudaStream_t st) {
   else de_launch_k2_w<T, O, 32, 1, 1, true>(s, g, st);
 }
 
+// *commit (in): the caller would like K3 fused behind the repair; (out): whether this launch does it
 template <class T, int O, int W, int U, int S, bool SKIP_BASE>
-cudaError_t de_launch_repair_w(const DEState &s, const LaunchGeom &g, cudaStream_t st) {
+cudaError_t de_launch_repair_w(const DEState &s, const LaunchGeom &g, cudaStream_t st, bool *commit) {
   DEState arg = s;
-  void *args[] = {&arg};
   auto kernel = de_repair_kernel<T, O, W, U, S, SKIP_BASE>;
   const unsigned int grid = clamp_grid((s.P + kBlock - 1) / kBlock, u64(g.sm_count) * blocks_per_sm(kernel));
+  *commit = *commit && grid == static_cast<unsigned int>(g.reduce_blocks);
+  int fuse = *commit ? 1 : 0;
+  void *args[] = {&arg, &fuse};
   return cudaLaunchCooperativeKernel(reinterpret_cast<void *>(kernel), dim3(grid), dim3(kBlock), args, 0, st);
 }
 // one sweep step per agent where it covers the row (W = 4 / 8 / 16 lanes), else a full warp looping over the row
 template <class T, int O>
-cudaError_t de_launch_repair(const DEState &s, const LaunchGeom &g, cudaStream_t st) {
+cudaError_t de_launch_repair(const DEState &s, const LaunchGeom &g, cudaStream_t st, bool *commit) {
   const u64 vecs = (s.d + Vec<T>::V - 1) / Vec<T>::V;
-  if constexpr (closed_form_dim(O) > 0) return de_launch_repair_w<T, O, 4, 1, 1, false>(s, g, st);
-  if (vecs <= 4) return de_launch_repair_w<T, O, 4, 1, 1, false>(s, g, st);
-  if (vecs <= 8) return de_launch_repair_w<T, O, 8, 1, 1, false>(s, g, st);
-  if (vecs <= 16) return de_launch_repair_w<T, O, 16, 1, 1, false>(s, g, st);
+  if constexpr (closed_form_dim(O) > 0) return de_launch_repair_w<T, O, 4, 1, 1, false>(s, g, st, commit);
+  if (vecs <= 4) return de_launch_repair_w<T, O, 4, 1, 1, false>(s, g, st, commit);
+  if (vecs <= 8) return de_launch_repair_w<T, O, 8, 1, 1, false>(s, g, st, commit);
+  if (vecs <= 16) return de_launch_repair_w<T, O, 16, 1, 1, false>(s, g, st, commit);
   // long rows: NLS_DE_REPAIR_U sweep steps in flight per lane (NLS_DE_REPAIR_U=2 in the environment: two)
   static const int steps = [] { const char *e = std::getenv("NLS_DE_REPAIR_U"); return e ? std::atoi(e) : NLS_DE_REPAIR_U; }();
-  if (steps == 2) return de_launch_repair_w<T, O, 32, 2, 1, true>(s, g, st);
-  return de_launch_repair_w<T, O, 32, NLS_DE_REPAIR_U, 1, true>(s, g, st);
+  if (steps == 2) return de_launch_repair_w<T, O, 32, 2, 1, true>(s, g, st, commit);
+  return de_launch_repair_w<T, O, 32, NLS_DE_REPAIR_U, 1, true>(s, g, st, commit);
 }
 
-// one generation: K2, K2r (cooperative), K3
+// one generation: K2, K2r (cooperative), K3 — K3 inside the K2r launch for launch-bound populations (two launches
+// per generation instead of three; not while the kernels are being timed one by one)
 template <class T>
 cudaError_t de_launch_generation(const DEState &s, const LaunchGeom &g, cudaStream_t st, cudaEvent_t *ev) {
   cudaError_t e = cudaSuccess;
+  bool commit = ev == nullptr && s.P * s.d <= (1ull << 24);
   if (ev) cudaEventRecord(ev[0], st);
 #define NLS_CALL(O)                                                                                                 \
   de_launch_k2<T, O>(s, g, st);                                                                                     \
   e = cudaGetLastError();                                                                                           \
   if (e != cudaSuccess) return e;                                                                                   \
   if (ev) cudaEventRecord(ev[1], st);                                                                               \
-  e = de_launch_repair<T, O>(s, g, st);
+  e = de_launch_repair<T, O>(s, g, st, &commit);
   NLS_OBJ_SWITCH(s.objective, NLS_CALL)
 #undef NLS_CALL
   if (e != cudaSuccess) return e;
   if (ev) cudaEventRecord(ev[2], st);
-  e = de_launch_commit<T>(s, 0, g, st);
+  if (!commit) e = de_launch_commit<T>(s, 0, g, st);
   if (ev) cudaEventRecord(ev[3], st);
   return e;
 }
-
 
 // the one-launch path (de_persist.cuh, compiled in its own translation units)
 template <class T>

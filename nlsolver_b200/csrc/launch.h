@@ -31,6 +31,9 @@ struct PSOOps {
   // small single-GPU swarms: n generations (move + candidate + apply each) in ONE launch on one thread-block cluster
   cudaError_t (*persistent)(const PSOState &s, void *record, unsigned long long record_bytes,
                             unsigned long long n_generations, cudaStream_t st);
+  // unsharded swarms: candidate reduction and apply in one launch (the last block applies its own record)
+  cudaError_t (*candidate_apply)(const PSOState &s, void *record, unsigned long long record_bytes, const LaunchGeom &g,
+                                 cudaStream_t st);
 };
 struct SANNOps {
   // x0: device, x0_count rows of d elements (1 = shared start)

@@ -30,7 +30,7 @@
 #include "pso_impl.cuh"
 #include "sann_impl.cuh"
 
-#define NLS_PLUGIN_ABI 4
+#define NLS_PLUGIN_ABI 5
 struct nls_objective_plugin {
   int abi;
   unsigned full_dim;   // 0: separable / pairwise sum of any dimension; D > 0: closed form, the solver's dim must be D

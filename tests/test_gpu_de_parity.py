@@ -262,6 +262,34 @@ def test_de_one_launch_path_equals_separate_kernels(ctx, monkeypatch, dtype, obj
         assert np.array_equal(bits(da[k]), bits(db[k])), k
 
 
+@pytest.mark.parametrize("dtype,obj,strategy,P,d,scale,F", [
+    (B.F64, B.SPHERE, B.DE_RANDOM, 5000, 64, 10.24, 0.4),
+    (B.F32, B.ROSENBROCK, B.DE_BEST, 900, 24, 4.096, 0.8),
+    (B.F64, B.RASTRIGIN, B.DE_RANDOM, 2000, 300, 10.24, 0.2),     # long rows: repair with four steps in flight
+])
+def test_de_commit_inside_the_repair_launch_equals_three_kernels(ctx, monkeypatch, dtype, obj, strategy, P, d, scale, F):
+    """Launch-bound populations run K3 behind the repair in the same cooperative launch (two launches per generation);
+    with kernel timing enabled the generation is the three separate kernels.  Same bits, same counters, same std_err."""
+    monkeypatch.setenv("NLS_DE_ONE_LAUNCH", "0")
+    seed, x0 = 1234 + P, np.full(d, scale)
+    out = []
+    for timed in (False, True):
+        pop = gpu_de(ctx, dtype, obj, strategy, True, P, d, seed, x0, f=F, masks=False)
+        pop.enable_kernel_timing(timed)
+        for n in (1, 8, 11):
+            pop.step(n)
+        st = pop.sync()
+        out.append((st, pop.population(), pop.scores(), pop.decisions()))
+        pop.close()
+    (sa, ra, ca, da), (sb, rb, cb, db) = out
+    assert sa["iterations"] == sb["iterations"] == 20 and sa["accepted_total"] > 0
+    for k in ("f_value", "function_calls", "best_index", "val_no_change", "std_err", "accepted_total"):
+        assert sa[k] == sb[k], k
+    assert np.array_equal(bits(ra), bits(rb)) and np.array_equal(bits(ca), bits(cb))
+    for k in ("donors", "dim_idx", "rejects", "accepted", "trial_scores"):
+        assert np.array_equal(bits(da[k]), bits(db[k])), k
+
+
 TINY_CASES = [
     # dtype, objective, strategy, minimize, P, d, scale, max_iter
     (B.F64, B.ROSENBROCK_EX, B.DE_RANDOM, True, 50, 2, 5.0, 1000),       # BASELINE configs[0]: the README snippet's shape

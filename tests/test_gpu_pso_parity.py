@@ -208,3 +208,33 @@ def test_pso_one_launch_path_equals_separate_kernels(ctx, monkeypatch, dtype, ob
     for k in ("f_value", "function_calls", "best_index", "val_no_change", "std_err"):
         assert sa[k] == sb[k], k
     assert np.array_equal(bits(pa), bits(pb)) and np.array_equal(bits(ba), bits(bb)) and np.array_equal(bits(xa), bits(xb))
+
+
+@pytest.mark.parametrize("dtype,obj,ptype,P,d", [(B.F64, B.ACKLEY, B.PSO_ACCELERATED, 3000, 64),
+                                                (B.F32, B.SPHERE, B.PSO_VANILLA, 40, 48),
+                                                (B.F64, B.RASTRIGIN, B.PSO_ACCELERATED, 700, 300)])
+def test_pso_fused_candidate_apply_equals_the_two_kernels(ctx, monkeypatch, dtype, obj, ptype, P, d):
+    """An unsharded swarm reduces and applies in ONE launch (the block that finishes the reduction applies its own
+    record); the shard-style path — step_local, then apply_candidates on the exported record — is the two kernels.
+    Same bits either way, stop statistic included."""
+    import torch
+    monkeypatch.setenv("NLS_DE_ONE_LAUNCH", "0")
+    up = np.full(d, 5.12)
+    kw = dict(dtype=dtype, objective=obj, pso_type=ptype, n_particles=P, dim=d, eps=0.0, max_iter=1 << 40,
+              best_val_no_change=1 << 40, seed=11)
+    a = nb.PSOSwarm(ctx, nb.pso_cfg(**kw), -up, up)
+    b = nb.PSOSwarm(ctx, nb.pso_cfg(**kw), -up, up)
+    rec = torch.zeros(nb.lib().nls_record_bytes(dtype, d), dtype=torch.uint8, device="cuda")
+    for n in (1, 8, 11):
+        a.step(n)
+    for _ in range(20):
+        b.step_local(rec.data_ptr())
+        b.apply_candidates(rec.data_ptr(), 1)
+    sa, sb = a.sync(), b.sync()
+    assert sa["iterations"] == sb["iterations"] == 20
+    for k in ("f_value", "function_calls", "best_index", "val_no_change", "std_err"):
+        assert sa[k] == sb[k], k
+    assert np.array_equal(bits(a.positions()), bits(b.positions())) and np.array_equal(bits(a.best()), bits(b.best()))
+    assert np.array_equal(bits(a.pbest_values()), bits(b.pbest_values()))
+    a.close()
+    b.close()
