@@ -351,6 +351,7 @@ __device__ __forceinline__ void de_generation_pass(const DEState &s, DETileEntry
     const int n_here = (P - first) < tile_size ? int(P - first) : int(tile_size);
     de_tile_body<T, OBJ, W, U, S, SKIP_BASE>(s, tile_entries, n_here, !random_mode, lane, [&](const DETileEntry &e, bool ok) {
       s.fin[e.agent] = ok ? uint16_t(0) : kNeverChanged;     // pass 0 of the repair's fixed-point iteration
+      if (ok && s.coarse != nullptr) atomicOr(s.coarse + (e.agent >> 10), 1u << ((e.agent >> 5) & 31u));   // bitmap 0
       n_ok += ok;
     });
     __syncwarp();                                          // tile_entries is rewritten by the next tile's prologue
@@ -476,6 +477,7 @@ __global__ void __launch_bounds__(kBlock, NLS_DE_BULK_BLOCKS) de_generation_bulk
         static_cast<T *>(s.tscore)[i] = sc;
         s.acc[i] = ok;
         s.fin[i] = ok ? uint16_t(0) : kNeverChanged;
+        if (ok && s.coarse != nullptr) atomicOr(s.coarse + (i >> 10), 1u << ((u32(i) >> 5) & 31u));   // bitmap 0
         n_ok += ok;
       }
     }
@@ -520,13 +522,14 @@ __device__ __forceinline__ void de_repair_pass(const DEState &s, DETileEntry *ti
     const u32 want = k - 1, cur = k % 3u;
     // ---- scan: kScan agents per lane and trip.  All decision loads of the trip are issued first, then all stamp loads
     // (two dependent L2 round trips per trip instead of two per agent), and the warp reserves list space with ONE atomic
-    // per trip.  A scan is bound by the random 32-byte sectors of the stamp lookups (1.5 per agent), so from the second
-    // iteration on they are filtered through a coarse bitmap the previous re-evaluation filled — one bit per 32 agents,
-    // small enough to live in L1: in the late iterations, where a few thousand agents were stamped, almost every lookup
-    // stops there and the scan streams the decisions only.  (Ordinary loads: the grid / cluster barrier that separates
-    // the bitmap's writers from these readers makes them visible.)
+    // per trip.  A scan is bound by the random 32-byte sectors of the stamp lookups (1.5 per agent), so the
+    // lookups are filtered through a coarse bitmap the previous re-evaluation filled (bitmap 0: the speculative pass) —
+    // one bit per 32 agents, small enough to live in L1: wherever few agents were stamped — the late iterations, or every
+    // iteration of a generation that accepts little — almost every lookup stops there and the scan streams the decisions
+    // only.  (Ordinary loads: the kernel boundary / grid / cluster barrier that separates the bitmap's writers from these
+    // readers makes them visible.)  K3 clears bitmap 0 for the next generation.
     constexpr int kScan = 4;
-    const u32 *cb_prev = (s.coarse != nullptr && k >= 2) ? s.coarse + u64((k - 1) % 3u) * s.coarse_words : nullptr;
+    const u32 *cb_prev = s.coarse != nullptr ? s.coarse + u64((k - 1) % 3u) * s.coarse_words : nullptr;
     u32 *cb_cur = s.coarse != nullptr ? s.coarse + u64(cur) * s.coarse_words : nullptr;
     // the bitmap this iteration's re-evaluation fills: its last readers were the scan two iterations ago
     if (cb_cur != nullptr)
@@ -673,6 +676,9 @@ __device__ __forceinline__ void de_commit_pass(const DEState &s, int mode) {
     n_acc = __reduce_add_sync(kFull, n_acc);
     if ((threadIdx.x & 31) == 0 && n_acc) atomicAdd(&ctrl->acc_partial, n_acc);
   };
+  // the repair's coarse bitmap 0 (agents accepted by the speculative pass) is rebuilt by the next generation's K2
+  if (s.coarse != nullptr)
+    for (u64 w = u64(blockIdx.x) * kBlock + threadIdx.x; w < s.coarse_words; w += u64(gridDim.x) * kBlock) s.coarse[w] = 0u;
   MinLoc ml;
   Moments mo;
   if (!population_reduce(s.P, s.part_min, s.part_idx, s.part_mom, &ctrl->ticket, item, store, post, ml, mo)) return;
@@ -1035,7 +1041,8 @@ cudaError_t de_launch_repair(const DEState &s, const LaunchGeom &g, cudaStream_t
 template <class T>
 cudaError_t de_launch_generation(const DEState &s, const LaunchGeom &g, cudaStream_t st, cudaEvent_t *ev) {
   cudaError_t e = cudaSuccess;
-  bool commit = ev == nullptr && s.P * s.d <= (1ull << 24);
+  static const int fuse_mode = [] { const char *e = std::getenv("NLS_DE_FUSE_COMMIT"); return e ? std::atoi(e) : 1; }();
+  bool commit = ev == nullptr && fuse_mode != 0 && (fuse_mode == 2 || s.P * s.d <= (1ull << 24));
   if (ev) cudaEventRecord(ev[0], st);
 #define NLS_CALL(O)                                                                                                 \
   de_launch_k2<T, O>(s, g, st);                                                                                     \

