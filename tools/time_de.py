@@ -1,3 +1,5 @@
+"""Device milliseconds per DE generation (CUDA events around step(20), best of three) for one shape — the quick A/B aid
+behind the NLS_DE_* environment switches.   usage: python tools/time_de.py <pop> <dim> <f32|f64> <F>"""
 import os, sys
 import numpy as np, torch
 sys.path.insert(0, os.getcwd())
