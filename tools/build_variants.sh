@@ -1,5 +1,6 @@
 #!/bin/bash
-# Builds tuning variants of libnls_b200.so into tools/ab/ (git-ignored *.so, travels to the GPU box): usage
+# Builds tuning variants of libnls_b200.so into tools/ab/ (git-ignored; listed in .gpurunignore — take it out of there
+# while variants have to travel to the GPU box): usage
 #   tools/build_variants.sh "name1:-DFLAG=1 -DOTHER=2" "name2:..."
 # Only de_f64.cu is recompiled per variant; the other objects come from the regular build.  Select a variant at run time
 # with NLS_B200_LIB=tools/ab/libnls_b200_<name>.so.
