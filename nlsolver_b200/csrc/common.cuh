@@ -125,15 +125,16 @@ template <> __device__ __forceinline__ double cos2pi<double>(double x) {
 #else
   const double magic = 6755399441055744.0;                 // 1.5 * 2^52: (x + magic) - magic == rint(x)
   const double r = x - (__dadd_rn(x, magic) - magic);      // exact, in [-1/2, 1/2]
-  double a = fabs(r);
-  const bool fold = a > 0.25;
-  a = fold ? 0.5 - a : a;                                  // exact
+  const bool fold = fabs(r) > 0.25;
+  // (only a^2 is used, so the unfolded branch keeps r's sign: no |r| has to be materialised for the select; the final
+  //  sign flip is an integer xor on the high word — the kernels that call this are bound by their FP64 operation count)
+  const double a = fold ? 0.5 - fabs(r) : r;               // exact
   const double t = a * a;
   double p = kCos2piCoef[0];
 #pragma unroll
   for (int k = 1; k < 8; k++) p = fma(p, t, kCos2piCoef[k]);
   p = fma(p, t, 1.0);
-  return fold ? -p : p;
+  return __hiloint2double(__double2hiint(p) ^ (fold ? static_cast<int>(0x80000000u) : 0), __double2loint(p));
 #endif
 }
 template <> __device__ __forceinline__ float cos2pi<float>(float x) {
