@@ -1,5 +1,5 @@
 #!/bin/bash
-# session 2, one GPU, the library as committed: tests, fp32 A/B of the repair's steps in flight, the bench lines for
+# session 2, one GPU, the library as committed: tests, the bench lines for
 # profiles/ (b200 arm with extras, reference arm), the small-shape and SANN benches, ncu of the changed kernels
 set -x
 O=gpurun_out/r2_final
@@ -7,15 +7,12 @@ N=gpurun_out/r2_final_ncu
 mkdir -p $O $N
 timeout 1200 python -m pytest tests -m gpu -x -q > $O/pytest.txt 2>&1
 tail -4 $O/pytest.txt
-for u in 2 4 2 4; do
-NLS_DE_REPAIR_U=$u python tools/probe_de.py --pop 1048576 --dim 1000 --objective sphere --dtype f32 --F 0.2 --blocks 2 --tag f32_u$u
-done
-NLS_DE_REPAIR_U=2 python tools/probe_de.py --pop 1048576 --dim 1000 --objective sphere --F 0.2 --blocks 2 --tag f64_u2
-NLS_DE_REPAIR_U=4 python tools/probe_de.py --pop 1048576 --dim 1000 --objective sphere --F 0.2 --blocks 2 --tag f64_u4
 python bench.py --impl reference --steps 10 --warmup 3 > $O/bench_ref.json 2> $O/bench_ref.err; tail -c 300 $O/bench_ref.json
 python bench.py --steps 20 --warmup 5 > $O/bench_n1.json 2> $O/bench_n1.err; tail -c 300 $O/bench_n1.err
 python tools/bench_small.py > $O/bench_small.json 2> $O/bench_small.err; tail -2 $O/bench_small.err
 python tools/bench_sann.py > $O/sann.json 2> $O/sann.err; tail -2 $O/sann.err
+mkdir -p gpurun_out/r2_sweep; python tools/sweep.py --big > gpurun_out/r2_sweep/sweep.md 2> gpurun_out/r2_sweep/sweep.err; tail -2 gpurun_out/r2_sweep/sweep.err
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
 NCU="ncu --set full --clock-control none --import-source on"
 run() {
   local name=$1 rx=$2 skip=$3 cnt=$4; shift 4
@@ -24,7 +21,8 @@ run() {
 }
 run repair_d64_f32 "de_repair_kernel" 3 1 python tools/probe_de.py --pop 4194304 --dim 64 --objective sphere --dtype f32 --F 0.3 --blocks 1 --gens 6
 run repair_d1000 "de_repair_kernel" 3 1 python tools/probe_de.py --pop 1048576 --dim 1000 --objective sphere --F 0.2 --blocks 1 --gens 6
-run pso_accel_config3_branchfree "pso_move_kernel" 4 1 python tests/tools/quick_time_pso.py 2097152 256 3 3 1 1
+run pso_accel_config3_final "pso_move_kernel" 4 1 python tests/tools/quick_time_pso.py 2097152 256 3 3 1 1
+run pso_vanilla_f32_d64_final "pso_move_kernel" 4 1 python tests/tools/quick_time_pso.py 4194304 64 3 0 0 0
 for f in $N/*.ncu-rep; do
   n=${f%.ncu-rep}
   ncu -i $f --page raw --csv > $n.raw.csv 2>/dev/null
