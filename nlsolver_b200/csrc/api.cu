@@ -860,7 +860,9 @@ static int pso_build(nls_ctx *ctx, const nls_pso_cfg *cfg, const void *lower, co
   NLS_ALLOC(p->record, p->record_bytes);
   std::vector<double> inertia_table;
   if (cfg->pso_type == NLS_PSO_ACCELERATED) {
-    const u64 n = std::min<u64>(cfg->max_iter == ~0ull ? 16384 : cfg->max_iter + 1, 16384);
+    // one entry per iteration, host libm like the reference; 2^20 entries (8 MB) cover any run that is not endless —
+    // 0.8^k underflows to zero after ~3400 iterations — and only beyond the table does the device evaluate pow itself
+    const u64 n = std::min<u64>(cfg->max_iter == ~0ull ? 16384 : cfg->max_iter + 1, cfg->max_iter > (1ull << 20) ? 16384 : (1ull << 20));
     inertia_table.resize(n);
     for (u64 k = 0; k < n; k++) inertia_table[k] = pso_inertia(p, k);
     double *tab = nullptr;
@@ -1119,7 +1121,7 @@ static int sann_build(nls_ctx *ctx, const nls_sann_cfg *cfg, const void *x0_host
   NLS_ALLOC(s.n_imp, C * sizeof(uint32_t));
   NLS_ALLOC(s.ctrl, sizeof(SANNCtrl));
   sa->dense = nullptr;
-  const u64 tn = std::min<u64>(std::max<u64>(cfg->max_iter, 1), 1u << 16);
+  const u64 tn = std::min<u64>(std::max<u64>(cfg->max_iter, 1), 1u << 20);   // host libm values; device log only beyond
   std::vector<double> table(tn);
   for (u64 k = 0; k < tn; k++)
     table[k] = sann_temperature(cfg->dtype, cfg->temperature_max, k);
