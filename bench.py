@@ -563,20 +563,29 @@ def multi_gpu_parity(b):
 def run_b200_arm(args, rank, world):
     b = Bench(args, rank, world)
     headline_shape = (args.pop, args.dim) == (POP, DIM)
-    cold = None if args.no_extras else bench_cold_call(b, args.pop, args.dim, args.steps)
+    def section(fn, *a):
+        """An extra section must never cost the headline line: a failure (e.g. 2 x 64 GiB of rows on a box with less
+        free memory) is reported in its place.  Every rank takes the same branch: the flag is reduced over the ranks."""
+        try:
+            out, err = fn(*a), None
+        except Exception as exc:
+            out, err = None, f"{type(exc).__name__}: {exc}"[:300]
+        if not b.all_true(err is None):
+            return {"unavailable": err or "failed on another rank"}
+        return out
+
+    cold = None if args.no_extras else section(bench_cold_call, b, args.pop, args.dim, args.steps)
+    if cold is not None and "unavailable" in cold:
+        cold = {"cold_call": "unavailable: " + cold["unavailable"]}
     main_part = bench_config2(b)
     extra = {}
     if not args.no_extras:
         if world > 1:
-            extra["multi_gpu_parity"] = multi_gpu_parity(b)
-        extra["accepting"] = bench_accepting(b)
-        configs = {"config3_pso_accelerated_ackley_d256": bench_config3(b)}
-        try:
-            configs["config4_island_de_best_rosenbrock_d4096"] = bench_config4(b)
-        except Exception as exc:       # 2 x 64 GiB of rows: a box with less free memory reports why instead of a number
-            configs["config4_island_de_best_rosenbrock_d4096"] = {"unavailable": str(exc)[:300]}
-        configs["config5_sweep_d64"] = bench_sweep(b)
-        extra["configs"] = configs
+            extra["multi_gpu_parity"] = section(multi_gpu_parity, b)
+        extra["accepting"] = section(bench_accepting, b)
+        extra["configs"] = {"config3_pso_accelerated_ackley_d256": section(bench_config3, b),
+                            "config4_island_de_best_rosenbrock_d4096": section(bench_config4, b),
+                            "config5_sweep_d64": section(bench_sweep, b)}
     if rank != 0:
         return
     line = {"metric": METRIC, "value": main_part["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
