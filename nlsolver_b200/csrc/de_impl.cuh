@@ -56,10 +56,12 @@ constexpr uint16_t kNeverChanged = 0xFFFFu;
 // and shared by every agent, so it goes through L1 instead of being re-fetched from L2 per agent.
 // Tuning (B200, fp64 d=1000 Rastrigin, P=2^20, K2 time): U=2 / 2 blocks per SM 6.29 ms; U=2 / 3 blocks 5.68 ms;
 // U=1 / 4 blocks (64 registers, 32 warps per SM, no spills) 5.63 ms — occupancy beats per-warp unrolling for long rows.
+//   KEEP (rows that one trip covers): the trial's coordinates are also handed back in `keep[u][q]`, so that an accepted
+// trial is stored from registers instead of being rebuilt by a second sweep over the four rows.
 template <class T, int OBJ, bool EVAL, bool WRITE, int W = 32, bool SHARED_BASE = false, int U = 1, int S = 1,
-          bool SKIP_BASE = true>
+          bool SKIP_BASE = true, bool KEEP = false>
 __device__ __forceinline__ T de_sweep(const DEState &s, const T *p0, const T *p1, const T *p2, const T *p3, T *dst,
-                                      u64 sbase, u32 dim, u64 i, int lane) {
+                                      u64 sbase, u32 dim, u64 i, int lane, T (*keep)[Vec<T>::V] = nullptr) {
   constexpr int V = Vec<T>::V;
   constexpr u32 kStride = W * V;                       // coordinates per group step
   static_assert(S == 1 || U <= S, "with accumulator slots the row is one unrolled iteration: step u feeds slot u");
@@ -114,6 +116,10 @@ __device__ __forceinline__ T de_sweep(const DEState &s, const T *p0, const T *p1
       for (int q = 0; q < V; q++)
         t[q] = mut[u][q] ? A::add(x1[u][q], A::mul(F, A::sub(x2[u][q], x3[u][q]))) : x0[u][q];
       if (WRITE && jj < d) st_row(dst + jj, t);
+      if (KEEP) {
+#pragma unroll
+        for (int q = 0; q < V; q++) keep[u][q] = t[q];
+      }
       if (EVAL) {
         obj.step(t, jj, d, lane, S == 1 ? 0 : u);
         if (s.masks != nullptr) {
@@ -260,14 +266,26 @@ __device__ __forceinline__ void de_tile_body(const DEState &s, const DETileEntry
     const T *p2 = static_cast<const T *>(e.p2), *p3 = static_cast<const T *>(e.p3);
     const u64 sbase = tape_state(e.key, 4 + e.rej);     // draws 0..2+rej: indices, 3+rej: dim, then one per coordinate
     // (warp-uniform branch: in the speculative pass of best mode every base row is the pre-generation best row)
+    // short rows (the kernels without the base-row skip): one trip of U steps covers the row, the trial stays in registers
+    constexpr bool kKeep = !SKIP_BASE;
+    constexpr int V = Vec<T>::V;
+    T keep[U][V];
     const T raw = shared_base
-                      ? de_sweep<T, OBJ, true, false, W, true, U, S, SKIP_BASE>(s, p0, p1, p2, p3, nullptr, sbase, e.dim, i, sub)
-                      : de_sweep<T, OBJ, true, false, W, false, U, S, SKIP_BASE>(s, p0, p1, p2, p3, nullptr, sbase, e.dim, i, sub);
+                      ? de_sweep<T, OBJ, true, false, W, true, U, S, SKIP_BASE, kKeep>(s, p0, p1, p2, p3, nullptr, sbase, e.dim, i, sub, keep)
+                      : de_sweep<T, OBJ, true, false, W, false, U, S, SKIP_BASE, kKeep>(s, p0, p1, p2, p3, nullptr, sbase, e.dim, i, sub, keep);
     const T sc = Ar<T>::mul(static_cast<T>(s.fm), raw);
     const bool ok = active && sc < static_cast<T>(e.score);   // strict <, NaN never accepted (nlsolver.h:2466)
     if (ok) {
       T *dst = static_cast<T *>(s.buf[(e.flags & 1u) ^ 1u]) + i * s.stride;
-      de_sweep<T, OBJ, false, true, W, false, U, S, SKIP_BASE>(s, p0, p1, p2, p3, dst, sbase, e.dim, i, sub);
+      if (kKeep && static_cast<u32>(s.d) <= u32(U * W * V)) {
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+          const u32 jj = u32(sub * V + u * W * V);
+          if (jj < static_cast<u32>(s.d)) st_row(dst + jj, keep[u]);
+        }
+      } else {
+        de_sweep<T, OBJ, false, true, W, false, U, S, SKIP_BASE>(s, p0, p1, p2, p3, dst, sbase, e.dim, i, sub);
+      }
     }
     if (active && sub == 0) {
       static_cast<T *>(s.tscore)[i] = sc;
