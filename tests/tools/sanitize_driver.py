@@ -102,6 +102,36 @@ for dtype, obj, n, d in ((nb.F64, nb.RASTRIGIN, 33, 3), (nb.F64, nb.SPHERE, 10, 
     ch.close()
     n_launch_groups += 1
 
+# ---- DE with an exchange window (the commit kernel publishes the island record), high acceptance (repair iterations
+#      behind the coarse bitmaps), long rows (TMA-staged K2, four-step re-evaluation), one-shot solves (tiny solver) ----
+for dtype, obj, strat, P, d, F in ((nb.F64, nb.SPHERE, nb.DE_RANDOM, 3001, 37, 0.3), (nb.F32, nb.SPHERE, nb.DE_BEST, 1500, 300, 0.3),
+                                   (nb.F64, nb.RASTRIGIN, nb.DE_RANDOM, 700, 1000, 0.2)):
+    cfg = nb.de_cfg(dtype=dtype, objective=obj, strategy=strat, pop_size=P, dim=d, differential_weight=F, eps=0.0,
+                    max_iter=NEVER, best_val_no_change=NEVER, seed=11)
+    pop = nb.DEPopulation(ctx, cfg, np.full(d, 3.0))
+    win = nb.ExchangeWindow(ctx, nb.lib().nls_record_bytes(dtype, d), 1, 0)
+    pop.attach_exchange(win)
+    pop.step(1)
+    pop.step(12)
+    st = pop.sync()
+    assert st["iterations"] == 13 and st["accepted_total"] > 0
+    pop.read_exchange(1)
+    pop.close()
+    win.close()
+    n_launch_groups += 1
+for dtype in (nb.F64, nb.F32):
+    x = np.array([5.0, 7.0])
+    st = nb.DE(nb.RosenbrockExample, lambda: 0.5, scalar_t=np.float64 if dtype == nb.F64 else np.float32, ctx=ctx).minimize(x)
+    assert st.iteration > 0
+    n_launch_groups += 1
+
+# ---- NelderMeadPSO batches: one warp per solver ----
+for dtype, obj, n, d in ((nb.F64, nb.SPHERE, 33, 5), (nb.F32, nb.ROSENBROCK, 10, 12), (nb.F64, nb.RASTRIGIN, 7, 100)):
+    xs = np.random.default_rng(d).uniform(-2, 2, size=(n, d))
+    st, a = nb.nmpso_solve(ctx, nb.nmpso_cfg(dtype=dtype, objective=obj, n_solvers=n, dim=d, max_iter=40, seed=9), xs)
+    assert a["x_best"].shape == (n, d)
+    n_launch_groups += 1
+
 ctx.close()
 bad = nb.lib().nls_debug_guard_violations()
 print(f"sanitize driver: {n_launch_groups} solver configurations completed; guard mode "
