@@ -132,8 +132,7 @@ __global__ void __launch_bounds__(kBlock, S == 1 ? NLS_PSO_MINBLOCKS : NLS_SANN_
         ld_own(prow + jl, x);
 #pragma unroll
         for (int q = 0; q < V; q++) {
-          const T u_a = unit<T>(mix64(st + kGolden * (2 * q))), u_b = unit<T>(mix64(st + kGolden * (2 * q + 1)));
-          x[q] = A::add(x[q], A::mul(cs, rnorm_from<T>(u_a, u_b)));         // :2799
+          x[q] = A::add(x[q], A::mul(cs, rnorm_tape<T>(mix64(st + kGolden * (2 * q)), mix64(st + kGolden * (2 * q + 1)))));   // :2799
         }
         if (in && active) {
 #pragma unroll
