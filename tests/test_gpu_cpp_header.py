@@ -108,3 +108,31 @@ def test_plugin_example_program(tmp_path):
     out = subprocess.run([str(exe), str(so)], check=True, capture_output=True, text=True).stdout
     xs = [float(v) for v in out.strip().splitlines()[-1].rstrip(",").split(",")]
     assert len(xs) == 8 and np.allclose(xs, -2.903534, atol=2e-2), out
+
+
+def test_nmpso_example_program_matches_python_mirror(tmp_path):
+    """nlsolver::NelderMeadPSO through the header (one solver, then a batch of 512) == the Python mirror fed the same
+    generator draws: both go through nls_nmpso_solve, so every figure is identical."""
+    exe = tmp_path / "example_nmpso"
+    subprocess.run(["g++", "-std=c++17", "-O2", "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "examples", "example_nmpso.cpp"), "-L", os.path.join(ROOT, "nlsolver_b200"),
+                    "-lnls_b200", "-Wl,-rpath," + os.path.join(ROOT, "nlsolver_b200"), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout
+    gen = XorShift()
+    nm = nb.NelderMeadPSO(nb.Rosenbrock, gen)
+    x = [2.0, 5.0]
+    st = nm.minimize(x)
+    title, calls, iters, fval, _ = parse(out)[0]
+    assert "NelderMeadPSO" in title and (calls, iters) == (st.function_calls_used, st.iteration) and fval == "%g" % st.f_value
+    lines = out.strip().splitlines()
+    assert lines[4] == "".join("%.17g," % v for v in x)
+    n, d = 512, 8
+    starts = np.full((n, d), 1.5)
+    for c in range(n):
+        starts[c, c % d] += 0.001 * (c + 1)
+    xs, res = nm.minimize_batch(starts)
+    best = min(range(n), key=lambda c: (res[c].f_value, c))
+    m = re.search(r"batch of 512 solvers: iterations (\d+) calls (\d+) best solver (\d+) f (\S+)", out)
+    assert m and int(m.group(1)) == sum(r.iteration for r in res) and int(m.group(2)) == sum(r.function_calls_used for r in res)
+    assert int(m.group(3)) == best and m.group(4) == "%.17g" % res[best].f_value
+    assert lines[-1] == "".join("%.17g," % v for v in xs[best])
