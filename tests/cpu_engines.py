@@ -55,6 +55,19 @@ class OracleDEEngine:
     def import_migrants(self, k, rows, scores):
         self.s.import_migrants(rows.numpy().reshape(k, -1), scores.numpy())
 
+    # the fused exchange on the CPU: the CUDA engine's commit kernel has stored every island's record into every
+    # window by the time a reader looks; here the records are gathered when they are read (gloo), which is all the host
+    # logic of IslandDE (one engine call per migration interval, barriers around the read) can see of it
+    def open_peer_exchange(self, comm, record_bytes):
+        self.comm, self.rb = comm, record_bytes
+
+    def read_exchange(self, world):
+        mine = torch.zeros(self.rb, dtype=torch.uint8)
+        self.export_best(mine)
+        gathered = torch.zeros(self.rb * world, dtype=torch.uint8)
+        self.comm.all_gather(gathered, mine)
+        return gathered.numpy().reshape(world, self.rb)
+
     def sync(self):
         return self.s.report()[0]
 

@@ -114,9 +114,9 @@ DE_KW = dict(objective=nb.ROSENBROCK, strategy=nb.DE_BEST, pop_size=40, dim=5, e
              best_val_no_change=1 << 40, seed=5)
 
 
-def _islands(rank, world, kw, gens, every, k):
+def _islands(rank, world, kw, gens, every, k, exchange="nccl"):
     isl = D.IslandDE(nb.de_cfg(**kw), np.full(kw["dim"], 4.096), migrate_every=every, migrants=k,
-                     engine_factory=OracleDEEngine)
+                     engine_factory=OracleDEEngine, exchange=exchange)
     isl.step(gens)
     st = isl.sync()
     _, a = isl.engine.s.report()
@@ -138,10 +138,14 @@ def _restated_islands(kw, world, gens, every, k):
     return [s.report() for s in isl]
 
 
-def test_islands_two_ranks_before_and_after_migration():
+@pytest.mark.parametrize("exchange", ["nccl", "peer"])
+def test_islands_two_ranks_before_and_after_migration(exchange):
+    """exchange="nccl": export + all-gather after every generation; "peer": the host logic of the fused path — one
+    engine call per migration interval, the records read out of the window between two barriers (the window itself is
+    emulated by tests/cpu_engines.py; the real one is checked on GPUs by tests/tools/multi_gpu_check.py)."""
     every, k = 4, 3
     for gens in (3, 9):     # before the first migration; after two of them
-        out = run_ranks(_islands, 2, DE_KW, gens, every, k)
+        out = run_ranks(_islands, 2, DE_KW, gens, every, k, exchange)
         want = _restated_islands(DE_KW, 2, gens, every, k)
         best = min(range(2), key=lambda r: (want[r][0]["f_value"], r))
         for rank, (st, rows, scores, grow) in out.items():
