@@ -135,7 +135,7 @@ def cpu_runner():
 
 def cpu_baseline_single_thread():
     run, kind = cpu_runner()
-    pop, gens = 8192, 24          # ~10 s of single-thread CPU work at ~50 us per agent evaluation
+    pop, gens = 8192, 60          # ~12 s of single-thread CPU work at ~23 us per agent evaluation
     run(256, 1)
     calls, sec = run(pop, gens)
     return {"value": calls / sec, "unit": UNIT, "cores": 1, "kind": kind,
